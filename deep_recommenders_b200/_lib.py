@@ -1,0 +1,96 @@
+"""ctypes binding of libdeeprec_b200.so (include/deeprec_b200.h).
+
+There is NO fallback: if the library is missing, or a call returns non-zero, this module
+raises.  `load()` only dlopens and declares signatures, so it also works on a box without a
+GPU (used by the `-m "not gpu"` symbol test); every compute entry needs `cuda:0`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "lib" / "libdeeprec_b200.so"
+HEADER_PATH = _PKG.parent / "include" / "deeprec_b200.h"
+
+_lib = None
+
+_p = C.c_void_p
+_i64 = C.c_int64
+_i = C.c_int
+_f = C.c_float
+
+# name -> argtypes (restype is int unless listed in _RESTYPES)
+_SIGS = {
+    "dr_version": [],
+    "dr_last_error": [],
+    "dr_launch_count": [],
+    "dr_tune_set": [C.c_char_p, _i],
+    "dr_embed_fm_fwd": [_p, _p, _p, _p, _i, _p, _i64, _i, _i, _p, _p, _p, _p],
+    "dr_embed_fm_bwd": [_p, _i, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _f, _p],
+    "dr_gather_fwd": [_p, _i64, _p, _i, _i64, _i, _p, _p],
+    "dr_scatter_add": [_p, _i64, _p, _i, _i64, _i, _p, _f, _p],
+    "dr_fm_fwd": [_p, _i64, _i, _i, _p, _p],
+    "dr_fm_bwd": [_p, _p, _i64, _i, _i, _p, _p],
+    "dr_dense_fwd": [_p, _p, _p, _i64, _i, _i, _i, _p, _p],
+    "dr_dense_bwd": [_p, _p, _p, _p, _i64, _i, _i, _i, _p, _p, _p, _p, _p],
+    "dr_cross_fwd": [_p, _p, _p, _p, _p, _p, _f, _i64, _i, _i, _p, _p, _p, _p],
+    "dr_cross_bwd": [_p, _p, _p, _p, _p, _f, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    "dr_inbatch_softmax_fwd": [_p, _p, _p, _p, _p, _f, _i64, _i64, _i, _p, _p, _p],
+    "dr_inbatch_softmax_bwd": [_p, _p, _p, _p, _p, _f, _i64, _i64, _i, _p, _p, _p, _p, _p],
+    "dr_scores_fwd": [_p, _p, _p, _p, _i64, _i64, _i, _p, _p],
+    "dr_hard_negative_topk": [_p, _i64, _i64, _i, _p, _p, _p, _p],
+    "dr_shard_bucket_ids": [_p, _i, _i64, _i, _p, _p, _i, _p, _p, _p, _p, _p],
+    "dr_permute_rows": [_p, _p, _i64, _i, _p, _p],
+    "dr_unpermute_rows": [_p, _p, _i64, _i, _p, _p],
+    "dr_sgd_step": [_p, _p, _i64, _f, _p],
+    "dr_bce_logits_fwd_bwd": [_p, _p, _i64, _p, _p, _p, _p],
+}
+_RESTYPES = {"dr_last_error": C.c_char_p, "dr_launch_count": C.c_uint64}
+
+
+class DeepRecError(RuntimeError):
+    """A C-ABI call returned non-zero (mirrors the Python exceptions the reference raises)."""
+
+
+def header_symbols() -> list[str]:
+    """Every function name include/deeprec_b200.h declares."""
+    text = HEADER_PATH.read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(dr_[a-z0-9_]+)\s*\(", text)))
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise DeepRecError(
+            f"{LIB_PATH} is missing: build it with `python -m deep_recommenders_b200.build` "
+            "(there is no CPU fallback for the hot path)"
+        )
+    lib = C.CDLL(str(LIB_PATH), mode=os.RTLD_LOCAL | os.RTLD_NOW)
+    for name, argtypes in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, C.c_int)
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().dr_last_error().decode(errors="replace")
+        if rc < 0:
+            raise ValueError(f"{what}: {msg} (rc={rc})")
+        raise DeepRecError(f"{what}: CUDA error {rc}: {msg}")
+
+
+def launch_count() -> int:
+    return int(load().dr_launch_count())
+
+
+def tune(key: str, value: int) -> None:
+    check(load().dr_tune_set(key.encode(), int(value)), "dr_tune_set")

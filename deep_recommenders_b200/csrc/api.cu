@@ -1,0 +1,46 @@
+// Library-level entry points: version, thread-local error string, launch counter, and the
+// developer tuning hook used by tools/sweep_embed.py (not part of the reference-facing ABI).
+#include "common.cuh"
+#include <atomic>
+#include <string.h>
+
+namespace dr {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+extern int g_tune_embed_fwd_unroll, g_tune_embed_bwd_unroll, g_tune_embed_block, g_tune_embed_ctas_per_sm,
+    g_tune_embed_bwd_agg;
+extern int g_tune_gemm_variant, g_tune_gemm_splitk;
+
+}  // namespace dr
+
+extern "C" int dr_version(void) { return 100; /* 0.1.0 */ }
+extern "C" const char* dr_last_error(void) { return dr::g_err; }
+extern "C" uint64_t dr_launch_count(void) { return dr::g_launches.load(std::memory_order_relaxed); }
+
+// Developer hook: set a tuning knob by name.  Returns 0, or DR_EINVAL for an unknown key.
+extern "C" int dr_tune_set(const char* key, int value) {
+  using namespace dr;
+  if (!key) return DR_EINVAL;
+  if (!strcmp(key, "embed_fwd_unroll")) g_tune_embed_fwd_unroll = value;
+  else if (!strcmp(key, "embed_bwd_unroll")) g_tune_embed_bwd_unroll = value;
+  else if (!strcmp(key, "embed_block")) g_tune_embed_block = value;
+  else if (!strcmp(key, "embed_ctas_per_sm")) g_tune_embed_ctas_per_sm = value;
+  else if (!strcmp(key, "embed_bwd_agg")) g_tune_embed_bwd_agg = value;
+  else if (!strcmp(key, "gemm_variant")) g_tune_gemm_variant = value;
+  else if (!strcmp(key, "gemm_splitk")) g_tune_gemm_splitk = value;
+  else {
+    set_error("dr_tune_set: unknown key '%s'", key);
+    return DR_EINVAL;
+  }
+  return DR_OK;
+}

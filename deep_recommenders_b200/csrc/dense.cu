@@ -1,0 +1,217 @@
+// Rows D and X of SURVEY.md section 8(a): Dense layer and DCN-v2 Cross layer, forward and
+// backward, as GEMMs with fused epilogues (gemm.cuh) plus two small bandwidth-bound helpers.
+//   keras/models/ranking/deepfm.py:30-34 ; estimator/models/feature_interaction/dnn.py:9-31
+//   keras/models/ranking/dcn.py:35-88
+#include "gemm.cuh"
+
+namespace dr {
+
+// gz = gy * act'(y) (in place allowed) and gb[n] += sum_m gz[m,n].  blockDim = (32, 8).
+__global__ void __launch_bounds__(256) actgrad_colsum_kernel(const float* __restrict__ gy,
+                                                              const float* __restrict__ y, int act, int64_t M,
+                                                              int64_t N, int64_t rows_per_cta,
+                                                              float* __restrict__ gz, float* __restrict__ gb) {
+  __shared__ float part[8][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r1 = min(M, r0 + rows_per_cta);
+  for (int64_t nb = 0; nb < N; nb += 32) {
+    const int64_t n = nb + tx;
+    float acc = 0.f;
+    if (n < N) {
+      for (int64_t r = r0 + ty; r < r1; r += 8) {
+        float v = gy[r * N + n];
+        if (act != DR_ACT_NONE) {
+          v *= act_grad_from_y(__ldg(y + r * N + n), act);
+          gz[r * N + n] = v;
+        }
+        acc += v;
+      }
+    }
+    part[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && n < N && gb) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t += part[i][tx];
+      red_add_f32(gb + n, t);
+    }
+    __syncthreads();
+  }
+}
+
+// Cross backward prologue: h = g*x0 ; gx0 = g*u ; gb[n] += sum_m h[m,n].
+__global__ void __launch_bounds__(256) cross_bwd_prologue_kernel(const float* __restrict__ g,
+                                                                  const float* __restrict__ x0,
+                                                                  const float* __restrict__ u, int64_t M,
+                                                                  int64_t N, int64_t rows_per_cta,
+                                                                  float* __restrict__ h, float* __restrict__ gx0,
+                                                                  float* __restrict__ gb) {
+  __shared__ float part[8][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r1 = min(M, r0 + rows_per_cta);
+  for (int64_t nb = 0; nb < N; nb += 32) {
+    const int64_t n = nb + tx;
+    float acc = 0.f;
+    if (n < N) {
+      for (int64_t r = r0 + ty; r < r1; r += 8) {
+        const float gv = g[r * N + n];
+        const float hv = gv * __ldg(x0 + r * N + n);
+        h[r * N + n] = hv;
+        if (gx0) gx0[r * N + n] = gv * __ldg(u + r * N + n);
+        acc += hv;
+      }
+    }
+    part[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && n < N && gb) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t += part[i][tx];
+      red_add_f32(gb + n, t);
+    }
+    __syncthreads();
+  }
+}
+
+static int64_t rows_per_cta_for(int64_t M) {
+  int64_t r = (M + (int64_t)kNumSMs * 4 - 1) / ((int64_t)kNumSMs * 4);
+  r = (r + 7) / 8 * 8;
+  return r < 8 ? 8 : r;
+}
+
+static int splitk_for(int64_t Mo, int64_t No, int64_t K) {
+  if (g_tune_gemm_splitk > 0) return g_tune_gemm_splitk;
+  const int64_t bn = No > 64 ? 128 : (No > 16 ? 32 : 16);
+  const int64_t bm = No > 16 ? 128 : 256;
+  const int64_t tiles = ((Mo + bm - 1) / bm) * ((No + bn - 1) / bn);
+  int64_t s = (2 * kNumSMs + tiles - 1) / tiles;
+  const int64_t ktiles = (K + 15) / 16;
+  if (s > ktiles / 8) s = ktiles / 8;
+  if (s < 1) s = 1;
+  if (s > 1024) s = 1024;
+  return (int)s;
+}
+
+static GemmArgs mk(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+                   int64_t ldb, int64_t ldc, int epi) {
+  GemmArgs a{};
+  a.A = A; a.B = B; a.C = C; a.M = M; a.N = N; a.K = K; a.lda = lda; a.ldb = ldb; a.ldc = ldc;
+  a.epi = epi; a.splitk = 1;
+  return a;
+}
+
+// gW[Kw,N] = X^T[Kw,M] @ G[M,N] (split-K over the batch, atomics into zeroed gW)
+static int gemm_xt_g(const float* X, const float* G, float* gW, int64_t M, int64_t Kw, int64_t N,
+                     cudaStream_t st) {
+  DR_CUDA_CALL(cudaMemsetAsync(gW, 0, sizeof(float) * Kw * N, st));
+  GemmArgs a = mk(X, G, gW, Kw, N, M, Kw, N, N, EPI_ATOMIC);
+  a.splitk = splitk_for(Kw, N, M);
+  return gemm_launch(a, /*transA=*/true, /*transB=*/false, st);
+}
+
+}  // namespace dr
+
+using namespace dr;
+
+extern "C" int dr_dense_fwd(const float* x, const float* w, const float* b, int64_t M, int K, int N, int act,
+                            float* y, void* stream) {
+  DR_REQUIRE(x && w && y, DR_EINVAL, "dr_dense_fwd: null pointer");
+  DR_REQUIRE(M >= 0 && K >= 1 && N >= 1, DR_EINVAL, "dr_dense_fwd: bad shape");
+  DR_REQUIRE(act >= DR_ACT_NONE && act <= DR_ACT_TANH, DR_EINVAL, "dr_dense_fwd: unknown activation %d", act);
+  GemmArgs a = mk(x, w, y, M, N, K, K, N, N, EPI_BIAS_ACT);
+  a.bias = b; a.act = act;
+  return gemm_launch(a, false, false, (cudaStream_t)stream);
+}
+
+extern "C" int dr_dense_bwd(const float* x, const float* w, const float* y, const float* gy, int64_t M,
+                            int K, int N, int act, float* gz_ws, float* gx, float* gw, float* gb,
+                            void* stream) {
+  DR_REQUIRE(x && w && gy && gw, DR_EINVAL, "dr_dense_bwd: null pointer");
+  DR_REQUIRE(M >= 0 && K >= 1 && N >= 1, DR_EINVAL, "dr_dense_bwd: bad shape");
+  DR_REQUIRE(act >= DR_ACT_NONE && act <= DR_ACT_TANH, DR_EINVAL, "dr_dense_bwd: unknown activation %d", act);
+  DR_REQUIRE(act == DR_ACT_NONE || (y && gz_ws), DR_EINVAL, "dr_dense_bwd: activation needs y and gz_ws");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (gb) DR_CUDA_CALL(cudaMemsetAsync(gb, 0, sizeof(float) * N, st));
+  if (M == 0) {
+    DR_CUDA_CALL(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)K * N, st));
+    return DR_OK;
+  }
+  const float* gz = gy;
+  if (act != DR_ACT_NONE || gb) {
+    const int64_t rpc = rows_per_cta_for(M);
+    const int64_t ctas = (M + rpc - 1) / rpc;
+    actgrad_colsum_kernel<<<(unsigned)ctas, dim3(32, 8), 0, st>>>(gy, y, act, M, N, rpc, gz_ws, gb);
+    DR_CUDA_LAUNCH_CHECK("actgrad_colsum");
+    if (act != DR_ACT_NONE) gz = gz_ws;
+  }
+  if (gx) {
+    GemmArgs a = mk(gz, w, gx, M, K, N, N, N, K, EPI_STORE);   // gx[M,K] = gz[M,N] @ W^T
+    if (int rc = gemm_launch(a, false, true, st)) return rc;
+  }
+  return gemm_xt_g(x, gz, gw, M, K, N, st);
+}
+
+extern "C" int dr_cross_fwd(const float* x0, const float* x, const float* w, const float* uk, const float* vk,
+                            const float* b, float alpha, int64_t B, int d, int r, float* xu_ws, float* u_out,
+                            float* y, void* stream) {
+  DR_REQUIRE(x0 && x && y, DR_EINVAL, "dr_cross_fwd: null pointer");
+  DR_REQUIRE(B >= 0 && d >= 1 && r >= 0, DR_EINVAL, "dr_cross_fwd: bad shape");
+  DR_REQUIRE(alpha >= 0.f, DR_EINVAL, "dr_cross_fwd: diag scale must be non-negative, got %g", (double)alpha);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (r == 0) {
+    DR_REQUIRE(w, DR_EINVAL, "dr_cross_fwd: full-rank kernel W is NULL");
+    GemmArgs a = mk(x, w, y, B, d, d, d, d, d, EPI_CROSS);
+    a.bias = b; a.alpha = alpha; a.aux0 = x0; a.aux1 = x; a.out2 = u_out;
+    return gemm_launch(a, false, false, st);
+  }
+  DR_REQUIRE(uk && vk && xu_ws, DR_EINVAL, "dr_cross_fwd: low-rank needs U, V and xu_ws");
+  GemmArgs a1 = mk(x, uk, xu_ws, B, r, d, d, r, r, EPI_STORE);
+  if (int rc = gemm_launch(a1, false, false, st)) return rc;
+  GemmArgs a2 = mk(xu_ws, vk, y, B, d, r, r, d, d, EPI_CROSS);
+  a2.bias = b; a2.alpha = alpha; a2.aux0 = x0; a2.aux1 = x; a2.out2 = u_out;
+  return gemm_launch(a2, false, false, st);
+}
+
+extern "C" int dr_cross_bwd(const float* x0, const float* x, const float* w, const float* uk, const float* vk,
+                            float alpha, const float* u_saved, const float* xu_saved, const float* g, int64_t B,
+                            int d, int r, float* h_ws, float* t_ws, float* gx0, float* gx, float* gw,
+                            float* guk, float* gvk, float* gb, void* stream) {
+  DR_REQUIRE(x0 && x && g && h_ws && gx, DR_EINVAL, "dr_cross_bwd: null pointer");
+  DR_REQUIRE(B >= 0 && d >= 1 && r >= 0, DR_EINVAL, "dr_cross_bwd: bad shape");
+  DR_REQUIRE(!gx0 || u_saved, DR_EINVAL, "dr_cross_bwd: gx0 requested but u_saved is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (gb) DR_CUDA_CALL(cudaMemsetAsync(gb, 0, sizeof(float) * d, st));
+  if (B == 0) return DR_OK;
+  {
+    const int64_t rpc = rows_per_cta_for(B);
+    const int64_t ctas = (B + rpc - 1) / rpc;
+    cross_bwd_prologue_kernel<<<(unsigned)ctas, dim3(32, 8), 0, st>>>(g, x0, u_saved, B, d, rpc, h_ws, gx0, gb);
+    DR_CUDA_LAUNCH_CHECK("cross_bwd_prologue");
+  }
+  if (r == 0) {
+    DR_REQUIRE(w && gw, DR_EINVAL, "dr_cross_bwd: full-rank needs W and gW");
+    GemmArgs a = mk(h_ws, w, gx, B, d, d, d, d, d, EPI_CROSS_DX);   // gx = h @ W^T + alpha*h + g
+    a.alpha = alpha; a.aux0 = h_ws; a.aux1 = g;
+    if (int rc = gemm_launch(a, false, true, st)) return rc;
+    return gemm_xt_g(x, h_ws, gw, B, d, d, st);
+  }
+  DR_REQUIRE(uk && vk && guk && gvk && xu_saved && t_ws, DR_EINVAL, "dr_cross_bwd: low-rank operands missing");
+  if (int rc = gemm_xt_g(xu_saved, h_ws, gvk, B, r, d, st)) return rc;             // gV = (xU)^T h
+  GemmArgs a1 = mk(h_ws, vk, t_ws, B, r, d, d, d, r, EPI_STORE);                   // t = h @ V^T
+  if (int rc = gemm_launch(a1, false, true, st)) return rc;
+  if (int rc = gemm_xt_g(x, t_ws, guk, B, d, r, st)) return rc;                    // gU = x^T t
+  GemmArgs a2 = mk(t_ws, uk, gx, B, d, r, r, r, d, EPI_CROSS_DX);                  // gx = t @ U^T + ...
+  a2.alpha = alpha; a2.aux0 = h_ws; a2.aux1 = g;
+  return gemm_launch(a2, false, true, st);
+}
+
+extern "C" int dr_scores_fwd(const float* q, const float* c, const float* p, const int64_t* cand_ids,
+                             int64_t nq, int64_t nc, int D, float* scores, void* stream) {
+  DR_REQUIRE(q && c && scores, DR_EINVAL, "dr_scores_fwd: null pointer");
+  DR_REQUIRE(nq >= 0 && nc >= 1 && D >= 1, DR_EINVAL, "dr_scores_fwd: bad shape");
+  GemmArgs a = mk(q, c, scores, nq, nc, D, D, D, nc, EPI_SCORES);
+  a.bias = p; a.cand_ids = cand_ids;
+  return gemm_launch(a, false, true, (cudaStream_t)stream);
+}

@@ -1,0 +1,466 @@
+// Rows E + L + F of SURVEY.md section 8(a): the fused multi-slot embedding gather, first-order
+// term and FM second-order interaction (forward), and the backward whose embedding
+// gradient is a warp-aggregated vector-atomic scatter-add.  HBM-bandwidth bound.
+//
+// Reference semantics restated (never executed here):
+//   keras/models/ranking/fm.py:23-37   FM.call          linear + 0.5*sum((sum e)^2 - sum e^2)
+//   keras/models/ranking/deepfm.py:36-46  per-column DenseFeatures -> stack/concat
+//   estimator/models/feature_interaction/fm.py:10-26,41-56
+//
+// Thread mapping (both kernels).  A row of D fp32 is D/4 128-bit chunks; LPR = the power of
+// two >= D/4 lanes own one chunk each, so the LPR lanes of a "lane group" read one whole
+// row with one LDG.128 each (D=16: 4 lanes x 16 B = one 64 B row = two 32 B sectors).  A
+// warp holds G = 32/LPR lane groups; a lane group walks the S slots of ONE example, keeping
+// sum_s e and sum_s e^2 for its chunk in registers, so the FM reduction needs no memory
+// traffic at all and only log2(LPR) shuffles at the very end.  The ids of the warp's G
+// examples are one contiguous G*S block of the [B,S] id matrix: they are fetched with
+// coalesced loads into a per-warp shared-memory slice (no block barrier in the main loop).
+// Each lane then has up to U independent 16 B row loads in flight.
+#include "common.cuh"
+
+namespace dr {
+
+int g_tune_embed_fwd_unroll = 0;      // 0 = default per LPR
+int g_tune_embed_bwd_unroll = 0;
+int g_tune_embed_block = 256;         // threads per CTA
+int g_tune_embed_ctas_per_sm = 0;     // 0 = as many as fit (2048 threads / SM)
+int g_tune_embed_bwd_agg = 1;         // warp-aggregate duplicate ids before the atomics
+
+struct EmbedFwdParams {
+  const float* const* table_ptrs;
+  const float* const* lin_ptrs;
+  const int64_t* rows;
+  const float* single_table;   // S == 1 fast form (dr_gather_fwd); table_ptrs == nullptr
+  int64_t single_rows;
+  const void* ids;
+  const float* bias;
+  int64_t B;
+  int S, D;
+  float* out_stack;
+  float* out_sum;
+  float* out_logit;
+};
+
+struct EmbedBwdParams {
+  const void* ids;
+  const int64_t* rows;
+  int64_t single_rows;
+  const float* stack;
+  const float* sum_e;
+  const float* g_logit;
+  const float* g_stack;
+  int64_t B;
+  int S, D;
+  float* const* grad_table_ptrs;
+  float* const* grad_lin_ptrs;
+  float* single_grad;
+  float* g_bias;
+  float scale;
+};
+
+// shared memory carve-up: [S] table ptr | [S] lin ptr | [S] rows | per-warp id slices
+__host__ __device__ inline size_t embed_smem_bytes(int S, int warps, int G, int id_bytes) {
+  size_t hdr = (size_t)S * (sizeof(void*) * 2 + sizeof(int64_t));
+  size_t ids = (size_t)warps * G * S * id_bytes;
+  return hdr + ((ids + 15) & ~(size_t)15);
+}
+
+template <int LPR, typename IdT, int U>
+__global__ void __launch_bounds__(512) embed_fm_fwd_kernel(const EmbedFwdParams p) {
+  constexpr int G = 32 / LPR;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int S = p.S, D = p.D;
+  const float** s_tab = reinterpret_cast<const float**>(smem_raw);
+  const float** s_lin = s_tab + S;
+  int64_t* s_rows = reinterpret_cast<int64_t*>(s_lin + S);
+  const int warp_in_cta = threadIdx.x >> 5;
+  const int warps_per_cta = blockDim.x >> 5;
+  IdT* s_ids = reinterpret_cast<IdT*>(s_rows + S) + (size_t)warp_in_cta * G * S;
+
+  for (int i = threadIdx.x; i < S; i += blockDim.x) {
+    s_tab[i] = p.table_ptrs ? p.table_ptrs[i] : p.single_table;
+    s_lin[i] = p.lin_ptrs ? p.lin_ptrs[i] : nullptr;
+    s_rows[i] = p.rows ? p.rows[i] : p.single_rows;
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int c = lane % LPR;          // 16-byte chunk of the row this lane owns
+  const int g = lane / LPR;          // example (lane group) inside the warp tile
+  const bool chunk_ok = (c * 4) < D;
+  const bool has_lin = p.lin_ptrs != nullptr;
+  const float bias = p.bias ? __ldg(p.bias) : 0.f;
+  const IdT* __restrict__ ids = reinterpret_cast<const IdT*>(p.ids);
+
+  const int64_t ntiles = (p.B + G - 1) / G;
+  const int64_t warp0 = (int64_t)blockIdx.x * warps_per_cta + warp_in_cta;
+  const int64_t nwarps = (int64_t)gridDim.x * warps_per_cta;
+
+  for (int64_t tile = warp0; tile < ntiles; tile += nwarps) {
+    const int64_t b0 = tile * G;
+    const int nex = (int)min((int64_t)G, p.B - b0);
+    {  // coalesced id staging: G*S consecutive ids of the [B,S] matrix
+      const IdT* src = ids + b0 * S;
+      const int n = nex * S;
+      for (int i = lane; i < n; i += 32) s_ids[i] = __ldg(src + i);
+    }
+    __syncwarp();
+
+    const int64_t b = b0 + g;
+    const bool ex_ok = g < nex;
+    const IdT* my = s_ids + g * S;
+    float4 sum = f4_zero(), sq = f4_zero();
+    float* ostack = p.out_stack ? p.out_stack + ((size_t)b * S) * D + c * 4 : nullptr;
+
+    for (int s0 = 0; s0 < S; s0 += U) {
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int s = s0 + u;
+        v[u] = f4_zero();
+        if (s < S && ex_ok && chunk_ok) {
+          const int64_t id = (int64_t)my[s];
+          if ((uint64_t)id < (uint64_t)s_rows[s]) v[u] = ldg_nc_na(s_tab[s] + (size_t)id * D + c * 4);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int s = s0 + u;
+        if (s < S) {
+          sum.x += v[u].x; sum.y += v[u].y; sum.z += v[u].z; sum.w += v[u].w;
+          sq.x = fmaf(v[u].x, v[u].x, sq.x); sq.y = fmaf(v[u].y, v[u].y, sq.y);
+          sq.z = fmaf(v[u].z, v[u].z, sq.z); sq.w = fmaf(v[u].w, v[u].w, sq.w);
+          if (ostack && ex_ok && chunk_ok) stg4(ostack + (size_t)s * D, v[u]);
+        }
+      }
+    }
+
+    if (p.out_sum && ex_ok && chunk_ok) stg4(p.out_sum + (size_t)b * D + c * 4, sum);
+
+    if (p.out_logit) {
+      float lin = 0.f;
+      if (has_lin && ex_ok) {
+        for (int s = c; s < S; s += LPR) {   // the LPR lanes split the S scalar gathers
+          const int64_t id = (int64_t)my[s];
+          if ((uint64_t)id < (uint64_t)s_rows[s]) lin += __ldg(s_lin[s] + id);
+        }
+      }
+      float t = (sum.x * sum.x - sq.x) + (sum.y * sum.y - sq.y) + (sum.z * sum.z - sq.z) +
+                (sum.w * sum.w - sq.w);
+      t = group_sum<LPR>(t);
+      lin = group_sum<LPR>(lin);
+      if (c == 0 && ex_ok) p.out_logit[b] = (bias + lin) + 0.5f * t;
+    }
+    __syncwarp();   // the id slice is overwritten by the next tile
+  }
+}
+
+template <int LPR, typename IdT, int U, bool AGG>
+__global__ void __launch_bounds__(512) embed_fm_bwd_kernel(const EmbedBwdParams p) {
+  constexpr int G = 32 / LPR;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ float s_bias_part[16];
+  const int S = p.S, D = p.D;
+  float** s_tab = reinterpret_cast<float**>(smem_raw);
+  float** s_lin = s_tab + S;
+  int64_t* s_rows = reinterpret_cast<int64_t*>(s_lin + S);
+  const int warp_in_cta = threadIdx.x >> 5;
+  const int warps_per_cta = blockDim.x >> 5;
+  IdT* s_ids = reinterpret_cast<IdT*>(s_rows + S) + (size_t)warp_in_cta * G * S;
+
+  for (int i = threadIdx.x; i < S; i += blockDim.x) {
+    s_tab[i] = p.grad_table_ptrs ? p.grad_table_ptrs[i] : p.single_grad;
+    s_lin[i] = p.grad_lin_ptrs ? p.grad_lin_ptrs[i] : nullptr;
+    s_rows[i] = p.rows ? p.rows[i] : p.single_rows;
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int c = lane % LPR;
+  const int g = lane / LPR;
+  const bool chunk_ok = (c * 4) < D;
+  const bool has_fm = p.g_logit != nullptr;
+  const bool has_gs = p.g_stack != nullptr;
+  const bool has_lin = p.grad_lin_ptrs != nullptr && has_fm;
+  const float scale = p.scale;
+  const IdT* __restrict__ ids = reinterpret_cast<const IdT*>(p.ids);
+
+  const int64_t ntiles = (p.B + G - 1) / G;
+  const int64_t warp0 = (int64_t)blockIdx.x * warps_per_cta + warp_in_cta;
+  const int64_t nwarps = (int64_t)gridDim.x * warps_per_cta;
+  float bias_acc = 0.f;
+
+  for (int64_t tile = warp0; tile < ntiles; tile += nwarps) {
+    const int64_t b0 = tile * G;
+    const int nex = (int)min((int64_t)G, p.B - b0);
+    {
+      const IdT* src = ids + b0 * S;
+      const int n = nex * S;
+      for (int i = lane; i < n; i += 32) s_ids[i] = __ldg(src + i);
+    }
+    __syncwarp();
+
+    const int64_t b = b0 + g;
+    const bool ex_ok = g < nex;
+    const IdT* my = s_ids + g * S;
+    const size_t row0 = ((size_t)b * S) * D + c * 4;
+    const float gl = (has_fm && ex_ok) ? __ldg(p.g_logit + b) : 0.f;
+    if (c == 0) bias_acc += gl;
+
+    float4 sum = f4_zero();
+    if (has_fm && ex_ok && chunk_ok) {
+      if (p.sum_e) {
+        sum = ldg4(p.sum_e + (size_t)b * D + c * 4);
+      } else {
+        for (int s = 0; s < S; ++s) sum = f4_add(sum, ldg4(p.stack + row0 + (size_t)s * D));
+      }
+    }
+
+    for (int s0 = 0; s0 < S; s0 += U) {
+      float4 e[U], gs[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int s = s0 + u;
+        e[u] = f4_zero();
+        gs[u] = f4_zero();
+        if (s < S && ex_ok && chunk_ok) {
+          if (has_fm) e[u] = ldg_nc_na(p.stack + row0 + (size_t)s * D);
+          if (has_gs) gs[u] = ldg_nc_na(p.g_stack + row0 + (size_t)s * D);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int s = s0 + u;
+        if (s >= S) break;     // warp-uniform
+        int64_t id = -1;
+        if (ex_ok) id = (int64_t)my[s];
+        const bool ok = ex_ok && chunk_ok && (uint64_t)id < (uint64_t)s_rows[s];
+        float4 d;
+        d.x = scale * fmaf(gl, sum.x - e[u].x, gs[u].x);
+        d.y = scale * fmaf(gl, sum.y - e[u].y, gs[u].y);
+        d.z = scale * fmaf(gl, sum.z - e[u].z, gs[u].z);
+        d.w = scale * fmaf(gl, sum.w - e[u].w, gs[u].w);
+        bool leader = true;
+        if (AGG && G > 1) {
+          // lanes that target the same 16 B of the same table row are merged: the lowest
+          // lane adds its peers' contributions and issues the single vector atomic.
+          const unsigned long long key =
+              ok ? (((unsigned long long)id << 5) | (unsigned)c) : (0x8000000000000000ull | (unsigned)lane);
+          const unsigned peers = __match_any_sync(0xffffffffu, key);
+          if (!__all_sync(0xffffffffu, peers == (1u << lane))) {
+#pragma unroll
+            for (int k = 1; k < G; ++k) {
+              const float4 o = f4_shfl_down(d, k * LPR);
+              const int src = lane + k * LPR;
+              if (src < 32 && ((peers >> src) & 1u)) d = f4_add(d, o);
+            }
+            leader = (__ffs(peers) - 1) == lane;
+          }
+        }
+        if (ok && leader) red_add_v4(s_tab[s] + (size_t)id * D + c * 4, d);
+      }
+    }
+
+    if (has_lin && ex_ok) {
+      const float gv = scale * gl;
+      for (int s = c; s < S; s += LPR) {
+        const int64_t id = (int64_t)my[s];
+        if ((uint64_t)id < (uint64_t)s_rows[s]) red_add_f32(s_lin[s] + id, gv);
+      }
+    }
+    __syncwarp();
+  }
+
+  if (p.g_bias && has_fm) {   // one atomic per CTA for the scalar bias gradient
+    bias_acc = group_sum<32>(bias_acc);
+    if (lane == 0) s_bias_part[warp_in_cta] = bias_acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int w = 0; w < warps_per_cta; ++w) t += s_bias_part[w];
+      red_add_f32(p.g_bias, scale * t);
+    }
+  }
+}
+
+// ---- host-side dispatch -----------------------------------------------------------------
+static int lpr_for(int D) {
+  int chunks = D / 4, l = 1;
+  while (l < chunks) l <<= 1;
+  return l;
+}
+
+struct LaunchGeom {
+  int threads, ctas;
+  size_t smem;
+};
+
+static LaunchGeom geom(int64_t B, int S, int LPR, int id_bytes) {
+  LaunchGeom lg;
+  lg.threads = g_tune_embed_block;
+  if (lg.threads != 128 && lg.threads != 256 && lg.threads != 512) lg.threads = 256;
+  const int warps = lg.threads / 32, G = 32 / LPR;
+  lg.smem = embed_smem_bytes(S, warps, G, id_bytes);
+  const int64_t ntiles = (B + G - 1) / G;
+  int64_t ctas = (ntiles + warps - 1) / warps;
+  int per_sm = 2048 / lg.threads;
+  if (g_tune_embed_ctas_per_sm > 0 && g_tune_embed_ctas_per_sm < per_sm) per_sm = g_tune_embed_ctas_per_sm;
+  const int64_t cap = (int64_t)kNumSMs * per_sm;
+  if (ctas > cap) ctas = cap;
+  if (ctas < 1) ctas = 1;
+  lg.ctas = (int)ctas;
+  return lg;
+}
+
+template <int LPR, typename IdT, int U>
+static int launch_fwd_u(const EmbedFwdParams& p, cudaStream_t st) {
+  LaunchGeom lg = geom(p.B, p.S, LPR, sizeof(IdT));
+  auto k = embed_fm_fwd_kernel<LPR, IdT, U>;
+  if (lg.smem > 48 * 1024) DR_CUDA_CALL(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lg.smem));
+  k<<<lg.ctas, lg.threads, lg.smem, st>>>(p);
+  DR_CUDA_LAUNCH_CHECK("embed_fm_fwd");
+  return DR_OK;
+}
+
+template <int LPR, typename IdT>
+static int launch_fwd(const EmbedFwdParams& p, cudaStream_t st) {
+  int U = g_tune_embed_fwd_unroll;
+  if (U <= 0) U = (LPR <= 8) ? 8 : 4;
+  switch (U) {
+    case 1: return launch_fwd_u<LPR, IdT, 1>(p, st);
+    case 2: return launch_fwd_u<LPR, IdT, 2>(p, st);
+    case 4: return launch_fwd_u<LPR, IdT, 4>(p, st);
+    case 13: return launch_fwd_u<LPR, IdT, 13>(p, st);
+    case 26: return launch_fwd_u<LPR, IdT, 26>(p, st);
+    default: return launch_fwd_u<LPR, IdT, 8>(p, st);
+  }
+}
+
+template <int LPR, typename IdT, int U>
+static int launch_bwd_u(const EmbedBwdParams& p, cudaStream_t st) {
+  LaunchGeom lg = geom(p.B, p.S, LPR, sizeof(IdT));
+  if (g_tune_embed_bwd_agg) {
+    auto k = embed_fm_bwd_kernel<LPR, IdT, U, true>;
+    if (lg.smem > 48 * 1024) DR_CUDA_CALL(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lg.smem));
+    k<<<lg.ctas, lg.threads, lg.smem, st>>>(p);
+  } else {
+    auto k = embed_fm_bwd_kernel<LPR, IdT, U, false>;
+    if (lg.smem > 48 * 1024) DR_CUDA_CALL(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lg.smem));
+    k<<<lg.ctas, lg.threads, lg.smem, st>>>(p);
+  }
+  DR_CUDA_LAUNCH_CHECK("embed_fm_bwd");
+  return DR_OK;
+}
+
+template <int LPR, typename IdT>
+static int launch_bwd(const EmbedBwdParams& p, cudaStream_t st) {
+  int U = g_tune_embed_bwd_unroll;
+  if (U <= 0) U = 4;
+  switch (U) {
+    case 1: return launch_bwd_u<LPR, IdT, 1>(p, st);
+    case 2: return launch_bwd_u<LPR, IdT, 2>(p, st);
+    case 8: return launch_bwd_u<LPR, IdT, 8>(p, st);
+    default: return launch_bwd_u<LPR, IdT, 4>(p, st);
+  }
+}
+
+#define DR_DISPATCH_LPR(FN, P, ST)                                      \
+  do {                                                                  \
+    const int lpr__ = lpr_for((P).D);                                   \
+    if (id_bytes == 8) {                                                \
+      switch (lpr__) {                                                  \
+        case 1: return FN<1, int64_t>(P, ST);                           \
+        case 2: return FN<2, int64_t>(P, ST);                           \
+        case 4: return FN<4, int64_t>(P, ST);                           \
+        case 8: return FN<8, int64_t>(P, ST);                           \
+        case 16: return FN<16, int64_t>(P, ST);                         \
+        default: return FN<32, int64_t>(P, ST);                         \
+      }                                                                 \
+    } else {                                                            \
+      switch (lpr__) {                                                  \
+        case 1: return FN<1, int32_t>(P, ST);                           \
+        case 2: return FN<2, int32_t>(P, ST);                           \
+        case 4: return FN<4, int32_t>(P, ST);                           \
+        case 8: return FN<8, int32_t>(P, ST);                           \
+        case 16: return FN<16, int32_t>(P, ST);                         \
+        default: return FN<32, int32_t>(P, ST);                         \
+      }                                                                 \
+    }                                                                   \
+  } while (0)
+
+static int check_dims(const char* fn, int64_t B, int S, int D, int id_bytes) {
+  DR_REQUIRE(B >= 0, DR_EINVAL, "%s: B=%lld < 0", fn, (long long)B);
+  DR_REQUIRE(S >= 1 && S <= 4096, DR_EINVAL, "%s: S=%d outside [1,4096]", fn, S);
+  DR_REQUIRE(D >= 4 && D <= 128 && (D % 4) == 0, DR_EINVAL,
+             "%s: D=%d unsupported (need D %% 4 == 0 and 4 <= D <= 128)", fn, D);
+  DR_REQUIRE(id_bytes == 8 || id_bytes == 4, DR_EINVAL, "%s: id_bytes=%d (need 4 or 8)", fn, id_bytes);
+  return DR_OK;
+}
+
+}  // namespace dr
+
+using namespace dr;
+
+extern "C" int dr_embed_fm_fwd(const float* const* table_ptrs, const float* const* lin_ptrs,
+                               const int64_t* rows, const void* ids, int id_bytes, const float* bias,
+                               int64_t B, int S, int D, float* out_stack, float* out_sum,
+                               float* out_logit, void* stream) {
+  if (int rc = check_dims("dr_embed_fm_fwd", B, S, D, id_bytes)) return rc;
+  DR_REQUIRE(table_ptrs && rows && ids, DR_EINVAL, "dr_embed_fm_fwd: null table_ptrs/rows/ids");
+  DR_REQUIRE(out_stack || out_logit || out_sum, DR_EINVAL, "dr_embed_fm_fwd: no output requested");
+  DR_REQUIRE(!out_stack || aligned16(out_stack), DR_EALIGN, "dr_embed_fm_fwd: out_stack not 16-B aligned");
+  DR_REQUIRE(!out_sum || aligned16(out_sum), DR_EALIGN, "dr_embed_fm_fwd: out_sum not 16-B aligned");
+  if (B == 0) return DR_OK;
+  EmbedFwdParams p{};
+  p.table_ptrs = table_ptrs; p.lin_ptrs = lin_ptrs; p.rows = rows; p.ids = ids; p.bias = bias;
+  p.B = B; p.S = S; p.D = D; p.out_stack = out_stack; p.out_sum = out_sum; p.out_logit = out_logit;
+  cudaStream_t st = (cudaStream_t)stream;
+  DR_DISPATCH_LPR(launch_fwd, p, st);
+}
+
+extern "C" int dr_embed_fm_bwd(const void* ids, int id_bytes, const int64_t* rows, const float* stack,
+                               const float* sum_e, const float* g_logit, const float* g_stack,
+                               int64_t B, int S, int D, float* const* grad_table_ptrs,
+                               float* const* grad_lin_ptrs, float* g_bias, float scale, void* stream) {
+  if (int rc = check_dims("dr_embed_fm_bwd", B, S, D, id_bytes)) return rc;
+  DR_REQUIRE(ids && rows && grad_table_ptrs, DR_EINVAL, "dr_embed_fm_bwd: null ids/rows/grad_table_ptrs");
+  DR_REQUIRE(g_logit || g_stack, DR_EINVAL, "dr_embed_fm_bwd: both g_logit and g_stack are NULL");
+  DR_REQUIRE(!g_logit || stack, DR_EINVAL, "dr_embed_fm_bwd: g_logit given but stack is NULL");
+  DR_REQUIRE(!stack || aligned16(stack), DR_EALIGN, "dr_embed_fm_bwd: stack not 16-B aligned");
+  DR_REQUIRE(!g_stack || aligned16(g_stack), DR_EALIGN, "dr_embed_fm_bwd: g_stack not 16-B aligned");
+  DR_REQUIRE(!sum_e || aligned16(sum_e), DR_EALIGN, "dr_embed_fm_bwd: sum_e not 16-B aligned");
+  if (B == 0) return DR_OK;
+  EmbedBwdParams p{};
+  p.ids = ids; p.rows = rows; p.stack = stack; p.sum_e = sum_e; p.g_logit = g_logit; p.g_stack = g_stack;
+  p.B = B; p.S = S; p.D = D; p.grad_table_ptrs = grad_table_ptrs; p.grad_lin_ptrs = grad_lin_ptrs;
+  p.g_bias = g_bias; p.scale = scale;
+  cudaStream_t st = (cudaStream_t)stream;
+  DR_DISPATCH_LPR(launch_bwd, p, st);
+}
+
+extern "C" int dr_gather_fwd(const float* table, int64_t rows, const void* ids, int id_bytes, int64_t n,
+                             int D, float* out, void* stream) {
+  if (int rc = check_dims("dr_gather_fwd", n, 1, D, id_bytes)) return rc;
+  DR_REQUIRE(table && ids && out, DR_EINVAL, "dr_gather_fwd: null pointer");
+  DR_REQUIRE(rows >= 0, DR_EINVAL, "dr_gather_fwd: rows < 0");
+  DR_REQUIRE(aligned16(table) && aligned16(out), DR_EALIGN, "dr_gather_fwd: table/out not 16-B aligned");
+  if (n == 0) return DR_OK;
+  EmbedFwdParams p{};
+  p.single_table = table; p.single_rows = rows; p.ids = ids; p.B = n; p.S = 1; p.D = D; p.out_stack = out;
+  cudaStream_t st = (cudaStream_t)stream;
+  DR_DISPATCH_LPR(launch_fwd, p, st);
+}
+
+extern "C" int dr_scatter_add(float* grad_table, int64_t rows, const void* ids, int id_bytes, int64_t n,
+                              int D, const float* g, float scale, void* stream) {
+  if (int rc = check_dims("dr_scatter_add", n, 1, D, id_bytes)) return rc;
+  DR_REQUIRE(grad_table && ids && g, DR_EINVAL, "dr_scatter_add: null pointer");
+  DR_REQUIRE(rows >= 0, DR_EINVAL, "dr_scatter_add: rows < 0");
+  DR_REQUIRE(aligned16(grad_table) && aligned16(g), DR_EALIGN, "dr_scatter_add: table/g not 16-B aligned");
+  if (n == 0) return DR_OK;
+  EmbedBwdParams p{};
+  p.ids = ids; p.single_rows = rows; p.g_stack = g; p.B = n; p.S = 1; p.D = D; p.single_grad = grad_table;
+  p.scale = scale;
+  cudaStream_t st = (cudaStream_t)stream;
+  DR_DISPATCH_LPR(launch_bwd, p, st);
+}

@@ -1,0 +1,366 @@
+"""torch.autograd.Function wrappers over the C-ABI (include/deeprec_b200.h).
+
+PyTorch is plumbing here: it owns device memory and streams and gives the layers an autograd
+graph.  All arithmetic happens in libdeeprec_b200.so.  Every function raises if its inputs are
+not CUDA fp32 tensors -- there is no CPU or eager-PyTorch fallback on this path.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import check
+
+ACT_CODES = {None: 0, "linear": 0, "relu": 1, "sigmoid": 2, "tanh": 3}
+
+
+def act_code(act) -> int:
+    if callable(act):
+        act = getattr(act, "__name__", str(act))
+    if act not in ACT_CODES:
+        raise ValueError(f"unsupported activation {act!r}; supported: {sorted(k for k in ACT_CODES if k)}")
+    return ACT_CODES[act]
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise _lib.DeepRecError(f"{name} is on {t.device}: the hot path runs on CUDA only (no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name}: expected float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def _ids(t: torch.Tensor, name: str = "ids") -> torch.Tensor:
+    if not t.is_cuda:
+        raise _lib.DeepRecError(f"{name} is on {t.device}: the hot path runs on CUDA only (no CPU fallback)")
+    if t.dtype not in (torch.int64, torch.int32):
+        raise TypeError(f"{name}: expected int64 or int32 ids, got {t.dtype}")
+    return t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------
+# Rows E + L + F: fused multi-slot gather + linear + FM
+# ------------------------------------------------------------------------------------------
+class EmbedFM(torch.autograd.Function):
+    """stack, logit = EmbedFM(ids, weight_arena, linear_arena, bias, meta).
+
+    `meta` carries the device pointer arrays (table_ptrs, lin_ptrs, rows) of the collection.
+    Backward either scatter-adds into dense .grad buffers (meta.sparse_lr is None) or applies
+    the fused sparse SGD update in place (meta.sparse_lr = lr) and returns no table gradient.
+    """
+
+    @staticmethod
+    def forward(ctx, ids, weight, linear, bias, meta, want_logit: bool):
+        lib = _lib.load()
+        ids = _ids(ids)
+        B, S = ids.shape
+        D = meta.dim
+        stack = torch.empty((B, S, D), device=weight.device, dtype=torch.float32)
+        sum_e = torch.empty((B, D), device=weight.device, dtype=torch.float32) if want_logit else None
+        logit = torch.empty((B,), device=weight.device, dtype=torch.float32) if want_logit else None
+        tp, lp, rows = meta.pointers(weight, linear)
+        check(lib.dr_embed_fm_fwd(tp.data_ptr(), lp.data_ptr() if (want_logit and linear is not None) else None,
+                                  rows.data_ptr(), ids.data_ptr(), ids.element_size(),
+                                  _ptr(bias) if want_logit else None, B, S, D,
+                                  stack.data_ptr(), _ptr(sum_e), _ptr(logit), _stream()), "dr_embed_fm_fwd")
+        ctx.meta = meta
+        ctx.want_logit = want_logit
+        ctx.has_linear = linear is not None
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(ids, stack, sum_e, weight, linear, bias)
+        if want_logit:
+            return stack, logit
+        dummy = stack.new_zeros((0,))
+        ctx.mark_non_differentiable(dummy)
+        return stack, dummy
+
+    @staticmethod
+    def backward(ctx, g_stack, g_logit):
+        lib = _lib.load()
+        ids, stack, sum_e, weight, linear, bias = ctx.saved_tensors
+        meta = ctx.meta
+        B, S = ids.shape
+        D = meta.dim
+        want_logit = ctx.want_logit
+        g_stack = None if g_stack is None else _f32(g_stack, "g_stack")
+        g_logit = _f32(g_logit, "g_logit") if (want_logit and g_logit is not None) else None
+        if g_stack is None and g_logit is None:
+            return None, None, None, None, None, None
+        fused = meta.sparse_lr is not None
+        if fused:
+            gw, gl, gb = weight, linear, bias
+            scale = -float(meta.sparse_lr)
+            tp, lp, rows = meta.pointers(weight, linear)
+        else:
+            gw = torch.zeros_like(weight)
+            gl = torch.zeros_like(linear) if (linear is not None and g_logit is not None) else None
+            gb = torch.zeros_like(bias) if (bias is not None and g_logit is not None) else None
+            scale = 1.0
+            tp, lp, rows = meta.pointers(gw, gl, cache=False)
+        with torch.no_grad():
+            check(lib.dr_embed_fm_bwd(ids.data_ptr(), ids.element_size(), rows.data_ptr(),
+                                      stack.data_ptr(), _ptr(sum_e), _ptr(g_logit), _ptr(g_stack),
+                                      B, S, D, tp.data_ptr(),
+                                      lp.data_ptr() if (gl is not None and g_logit is not None) else None,
+                                      _ptr(gb) if g_logit is not None else None, scale, _stream()),
+                  "dr_embed_fm_bwd")
+        if fused:
+            return None, None, None, None, None, None
+        return None, gw, gl, gb, None, None
+
+
+class Gather(torch.autograd.Function):
+    """rows = table[ids] for one table (two-tower user / item tower); OOV id -> zero row."""
+
+    @staticmethod
+    def forward(ctx, table, ids, sparse_lr):
+        lib = _lib.load()
+        table = _f32(table, "table")
+        ids = _ids(ids)
+        n = ids.numel()
+        D = table.shape[1]
+        out = torch.empty((n, D), device=table.device, dtype=torch.float32)
+        check(lib.dr_gather_fwd(table.data_ptr(), table.shape[0], ids.data_ptr(), ids.element_size(), n, D,
+                                out.data_ptr(), _stream()), "dr_gather_fwd")
+        ctx.save_for_backward(table, ids)
+        ctx.sparse_lr = sparse_lr
+        return out.view(*ids.shape, D)
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        table, ids = ctx.saved_tensors
+        g = _f32(g, "g").view(-1, table.shape[1])
+        fused = ctx.sparse_lr is not None
+        tgt = table if fused else torch.zeros_like(table)
+        with torch.no_grad():
+            check(lib.dr_scatter_add(tgt.data_ptr(), table.shape[0], ids.data_ptr(), ids.element_size(),
+                                     ids.numel(), table.shape[1], g.data_ptr(),
+                                     -float(ctx.sparse_lr) if fused else 1.0, _stream()), "dr_scatter_add")
+        return (None if fused else tgt), None, None
+
+
+# ------------------------------------------------------------------------------------------
+# Row F standalone
+# ------------------------------------------------------------------------------------------
+class FMInteraction(torch.autograd.Function):
+    """0.5 * sum_d((sum_s x)^2 - sum_s x^2), keepdims -> [B, 1]."""
+
+    @staticmethod
+    def forward(ctx, x):
+        lib = _lib.load()
+        x = _f32(x, "x")
+        if x.dim() != 3:
+            raise ValueError("The rank of `x` should be 3. Got rank = {}.".format(x.dim()))
+        B, S, D = x.shape
+        out = torch.empty((B,), device=x.device, dtype=torch.float32)
+        check(lib.dr_fm_fwd(x.data_ptr(), B, S, D, out.data_ptr(), _stream()), "dr_fm_fwd")
+        ctx.save_for_backward(x)
+        return out.view(B, 1)
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        (x,) = ctx.saved_tensors
+        B, S, D = x.shape
+        g = _f32(g, "g").reshape(B)
+        gx = torch.empty_like(x)
+        check(lib.dr_fm_bwd(x.data_ptr(), g.data_ptr(), B, S, D, gx.data_ptr(), _stream()), "dr_fm_bwd")
+        return gx
+
+
+# ------------------------------------------------------------------------------------------
+# Row D: Dense
+# ------------------------------------------------------------------------------------------
+class DenseFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, act: int):
+        lib = _lib.load()
+        x = _f32(x, "x")
+        w = _f32(w, "kernel")
+        b = None if b is None else _f32(b, "bias")
+        lead = x.shape[:-1]
+        K = x.shape[-1]
+        x2 = x.reshape(-1, K)
+        M = x2.shape[0]
+        if w.shape[0] != K:
+            raise ValueError(f"Dense: input dim {K} does not match kernel {tuple(w.shape)}")
+        N = w.shape[1]
+        y = torch.empty((M, N), device=x.device, dtype=torch.float32)
+        check(lib.dr_dense_fwd(x2.data_ptr(), w.data_ptr(), _ptr(b), M, K, N, act, y.data_ptr(), _stream()),
+              "dr_dense_fwd")
+        ctx.act = act
+        ctx.has_bias = b is not None
+        ctx.save_for_backward(x2, w, y)
+        ctx.lead = lead
+        return y.view(*lead, N)
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.load()
+        x2, w, y = ctx.saved_tensors
+        M, K = x2.shape
+        N = w.shape[1]
+        gy = _f32(gy, "gy").reshape(M, N)
+        need_x = ctx.needs_input_grad[0]
+        gz_ws = torch.empty_like(gy) if ctx.act != 0 else None
+        gx = torch.empty((M, K), device=gy.device, dtype=torch.float32) if need_x else None
+        gw = torch.empty_like(w)
+        gb = torch.empty((N,), device=gy.device, dtype=torch.float32) if ctx.has_bias else None
+        check(lib.dr_dense_bwd(x2.data_ptr(), w.data_ptr(), y.data_ptr(), gy.data_ptr(), M, K, N, ctx.act,
+                               _ptr(gz_ws), _ptr(gx), gw.data_ptr(), _ptr(gb), _stream()), "dr_dense_bwd")
+        return (gx.view(*ctx.lead, K) if need_x else None), gw, gb, None
+
+
+# ------------------------------------------------------------------------------------------
+# Row X: Cross
+# ------------------------------------------------------------------------------------------
+class CrossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x0, x, w, uk, vk, b, alpha: float, same: bool):
+        lib = _lib.load()
+        x0 = _f32(x0, "x0")
+        x = x0 if same else _f32(x, "x")
+        d = x0.shape[-1]
+        lead = x0.shape[:-1]
+        x0_2 = x0.reshape(-1, d)
+        x_2 = x.reshape(-1, d)
+        B = x0_2.shape[0]
+        r = 0 if w is not None else uk.shape[1]
+        y = torch.empty((B, d), device=x0.device, dtype=torch.float32)
+        u = torch.empty((B, d), device=x0.device, dtype=torch.float32)
+        xu = torch.empty((B, r), device=x0.device, dtype=torch.float32) if r else None
+        check(lib.dr_cross_fwd(x0_2.data_ptr(), x_2.data_ptr(), _ptr(w), _ptr(uk), _ptr(vk), _ptr(b),
+                               float(alpha), B, d, r, _ptr(xu), u.data_ptr(), y.data_ptr(), _stream()),
+              "dr_cross_fwd")
+        ctx.alpha = float(alpha)
+        ctx.same = same
+        ctx.r = r
+        ctx.lead = lead
+        ctx.save_for_backward(x0_2, x_2, w, uk, vk, b, u, xu)
+        return y.view(*lead, d)
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        x0, x, w, uk, vk, b, u, xu = ctx.saved_tensors
+        B, d = x0.shape
+        r = ctx.r
+        g = _f32(g, "g").reshape(B, d)
+        dev = g.device
+        h = torch.empty((B, d), device=dev, dtype=torch.float32)
+        t = torch.empty((B, r), device=dev, dtype=torch.float32) if r else None
+        gx0 = torch.empty((B, d), device=dev, dtype=torch.float32)
+        gx = torch.empty((B, d), device=dev, dtype=torch.float32)
+        gw = torch.empty_like(w) if w is not None else None
+        guk = torch.empty_like(uk) if uk is not None else None
+        gvk = torch.empty_like(vk) if vk is not None else None
+        gb = torch.empty_like(b) if b is not None else None
+        check(lib.dr_cross_bwd(x0.data_ptr(), x.data_ptr(), _ptr(w), _ptr(uk), _ptr(vk), ctx.alpha,
+                               u.data_ptr(), _ptr(xu), g.data_ptr(), B, d, r, h.data_ptr(), _ptr(t),
+                               gx0.data_ptr(), gx.data_ptr(), _ptr(gw), _ptr(guk), _ptr(gvk), _ptr(gb),
+                               _stream()), "dr_cross_bwd")
+        if ctx.same:
+            gx0 = gx0 + gx
+            gx = None
+        else:
+            gx = gx.view(*ctx.lead, d)
+        return gx0.view(*ctx.lead, d), gx, gw, guk, gvk, gb, None, None
+
+
+# ------------------------------------------------------------------------------------------
+# Row R: in-batch softmax
+# ------------------------------------------------------------------------------------------
+class InBatchSoftmax(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, c, sample_weight, sampling_prob, cand_ids, inv_tau: float):
+        lib = _lib.load()
+        q = _f32(q, "query_embeddings")
+        c = _f32(c, "candidate_embeddings")
+        if q.dim() != 2 or c.dim() != 2 or q.shape[1] != c.shape[1]:
+            raise ValueError(f"Retrieval: embeddings must be [nq,D] and [nc,D], got {tuple(q.shape)} {tuple(c.shape)}")
+        nq, D = q.shape
+        nc = c.shape[0]
+        w = None if sample_weight is None else _f32(sample_weight, "sample_weight").reshape(nq)
+        p = None if sampling_prob is None else _f32(sampling_prob, "candidate_sampling_probability").reshape(nc)
+        ids = None
+        if cand_ids is not None:
+            ids = cand_ids.to(torch.int64).contiguous().reshape(nc)
+        lse = torch.empty((nq,), device=q.device, dtype=torch.float32)
+        loss = torch.empty((1,), device=q.device, dtype=torch.float32)
+        check(lib.dr_inbatch_softmax_fwd(q.data_ptr(), c.data_ptr(), _ptr(w), _ptr(p), _ptr(ids), float(inv_tau),
+                                         nq, nc, D, lse.data_ptr(), loss.data_ptr(), _stream()),
+              "dr_inbatch_softmax_fwd")
+        ctx.inv_tau = float(inv_tau)
+        ctx.save_for_backward(q, c, w, p, ids, lse)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, gloss):
+        lib = _lib.load()
+        q, c, w, p, ids, lse = ctx.saved_tensors
+        nq, D = q.shape
+        nc = c.shape[0]
+        gl = _f32(gloss, "gloss").reshape(1)
+        gq = torch.empty_like(q)
+        gc = torch.empty_like(c)
+        check(lib.dr_inbatch_softmax_bwd(q.data_ptr(), c.data_ptr(), _ptr(w), _ptr(p), _ptr(ids), ctx.inv_tau,
+                                         nq, nc, D, lse.data_ptr(), gl.data_ptr(), gq.data_ptr(), gc.data_ptr(),
+                                         _stream()), "dr_inbatch_softmax_bwd")
+        return gq, gc, None, None, None, None
+
+
+def scores(q, c, sampling_prob=None, cand_ids=None) -> torch.Tensor:
+    """Materialised [nq, nc] logits with R1/R2 corrections (no temperature); not differentiable."""
+    lib = _lib.load()
+    q = _f32(q, "q")
+    c = _f32(c, "c")
+    nq, D = q.shape
+    nc = c.shape[0]
+    p = None if sampling_prob is None else _f32(sampling_prob, "p").reshape(nc)
+    ids = None if cand_ids is None else cand_ids.to(torch.int64).contiguous().reshape(nc)
+    out = torch.empty((nq, nc), device=q.device, dtype=torch.float32)
+    check(lib.dr_scores_fwd(q.data_ptr(), c.data_ptr(), _ptr(p), _ptr(ids), nq, nc, D, out.data_ptr(), _stream()),
+          "dr_scores_fwd")
+    return out
+
+
+def hard_negative_topk(logits: torch.Tensor, k: int):
+    lib = _lib.load()
+    logits = _f32(logits, "logits")
+    nq, nc = logits.shape
+    out_l = torch.empty((nq, k), device=logits.device, dtype=torch.float32)
+    out_y = torch.empty((nq, k), device=logits.device, dtype=torch.float32)
+    out_i = torch.empty((nq, k), device=logits.device, dtype=torch.int32)
+    check(lib.dr_hard_negative_topk(logits.data_ptr(), nq, nc, k, out_l.data_ptr(), out_y.data_ptr(),
+                                    out_i.data_ptr(), _stream()), "dr_hard_negative_topk")
+    return out_l, out_y, out_i
+
+
+def bce_with_logits(z: torch.Tensor, y: torch.Tensor):
+    """(loss[1], grad_z[B], prob[B]) of mean binary cross-entropy on logits, one kernel."""
+    lib = _lib.load()
+    z = _f32(z, "logits").reshape(-1)
+    y = _f32(y, "labels").reshape(-1)
+    B = z.numel()
+    prob = torch.empty_like(z)
+    gz = torch.empty_like(z)
+    loss = torch.empty((1,), device=z.device, dtype=torch.float32)
+    check(lib.dr_bce_logits_fwd_bwd(z.data_ptr(), y.data_ptr(), B, prob.data_ptr(), loss.data_ptr(), gz.data_ptr(),
+                                    _stream()), "dr_bce_logits_fwd_bwd")
+    return loss, gz, prob
+
+
+def sgd_step_(p: torch.Tensor, g: torch.Tensor, lr: float) -> None:
+    lib = _lib.load()
+    check(lib.dr_sgd_step(p.data_ptr(), g.data_ptr(), p.numel(), float(lr), _stream()), "dr_sgd_step")

@@ -1,0 +1,209 @@
+/*
+ * deeprec_b200.h -- C-ABI of the B200-native hot path of deep_recommenders.
+ *
+ * One shared library (libdeeprec_b200.so), extern "C", plain pointers and sizes,
+ * no torch / C++ types.  The reference (LongmaoTeamTf/deep_recommenders) has no FFI at
+ * all: its "operator API" is the tf.keras Layer protocol and every op below is what a
+ * TensorFlow custom op for that layer's call()/gradient would bind.  Each entry cites the
+ * reference lines it replaces (paths relative to the reference repo root).
+ *
+ * Conventions (all entries):
+ *   - return 0 on success; <0 = argument rejected on the host BEFORE any launch
+ *     (DR_EINVAL ...); >0 = cudaError_t passed through.  dr_last_error() returns a
+ *     thread-local, human-readable message for the last non-zero return.
+ *   - every pointer is a DEVICE pointer owned by the caller (outputs and workspaces
+ *     included) unless the comment says "host".  The library allocates nothing.
+ *   - every compute entry takes the cudaStream_t to enqueue on (passed as void*), never
+ *     synchronises, never touches the default stream, keeps no global mutable state.
+ *   - tensors are row-major contiguous fp32; ids are int64 (id_bytes=8) or int32 (4).
+ *   - an id outside [0, rows) (TensorFlow's OOV id -1 included) contributes a zero row
+ *     and is never dereferenced.
+ */
+#ifndef DEEPREC_B200_H_
+#define DEEPREC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DR_OK 0
+#define DR_EINVAL (-1)     /* null pointer / bad size / unsupported D            */
+#define DR_EALIGN (-2)     /* a row base or tensor base is not 16-byte aligned   */
+#define DR_ENOTSUP (-3)    /* valid request this build does not implement        */
+
+/* activation codes (tf.keras.layers.Dense(activation=...)) */
+#define DR_ACT_NONE 0
+#define DR_ACT_RELU 1
+#define DR_ACT_SIGMOID 2
+#define DR_ACT_TANH 3
+
+/* ABI version (major*10000 + minor*100 + patch) and last error string. */
+int dr_version(void);
+const char* dr_last_error(void);
+/* Number of kernels this library has launched since load (process-wide, for bench.py). */
+uint64_t dr_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Row E + L + F fused: multi-slot embedding gather + first-order term + FM second order.
+ *   replaces: keras/models/ranking/fm.py:23-37,54-63 ; deepfm.py:36-46 (DenseFeatures per
+ *             column -> tf.stack -> FM.call) ; estimator/models/feature_interaction/
+ *             fm.py:10-26,41-56.
+ *   table_ptrs[S] : device array of S device pointers, table s is [rows[s], D] fp32,
+ *                   every base 16-B aligned.  D % 4 == 0, 4 <= D <= 128.
+ *   lin_ptrs[S]   : device array of S device pointers to [rows[s]] fp32 first-order
+ *                   weights; NULL = no first-order term.
+ *   rows[S]       : device int64.
+ *   ids           : [B, S] int64 / int32 (id_bytes).
+ *   bias          : device [1] or NULL.
+ *   out_stack     : [B, S, D] (== the [B, S*D] concat) or NULL (FM-only, no stack write).
+ *   out_sum       : [B, D] sum over slots (saved for backward) or NULL.
+ *   out_logit     : [B] = bias + sum_s lin_s[id_s] + 0.5*sum_d((sum_s e)^2 - sum_s e^2),
+ *                   or NULL (pure multi-slot gather).
+ * ------------------------------------------------------------------------------------- */
+int dr_embed_fm_fwd(const float* const* table_ptrs, const float* const* lin_ptrs,
+                    const int64_t* rows, const void* ids, int id_bytes, const float* bias,
+                    int64_t B, int S, int D,
+                    float* out_stack, float* out_sum, float* out_logit, void* stream);
+
+/* Backward of the above fused with the sparse update ("IndexedSlices" scatter-add):
+ *   dE[b,s,:] = g_logit[b] * (sum_e[b,:] - stack[b,s,:]) + g_stack[b,s,:]
+ *   grad_table s [id] += scale * dE      (vector red.global.add, warp-aggregated)
+ *   grad_lin   s [id] += scale * g_logit[b]
+ *   g_bias[0]         += scale * sum_b g_logit[b]
+ * scale = 1 with zeroed grad buffers gives the dense gradient TF autodiff would produce;
+ * scale = -lr with grad_* aliasing the parameters is a fused sparse SGD step.
+ * g_logit / g_stack / grad_lin_ptrs / g_bias / sum_e may be NULL (sum_e == NULL makes the
+ * kernel re-reduce the stack).  stack is required when g_logit != NULL.
+ */
+int dr_embed_fm_bwd(const void* ids, int id_bytes, const int64_t* rows,
+                    const float* stack, const float* sum_e,
+                    const float* g_logit, const float* g_stack,
+                    int64_t B, int S, int D,
+                    float* const* grad_table_ptrs, float* const* grad_lin_ptrs, float* g_bias,
+                    float scale, void* stream);
+
+/* Plain single-table gather / scatter-add (two-tower user & item towers).
+ *   replaces: tf.keras.layers.DenseFeatures(embedding_column) on one column
+ *             (keras/models/ranking/fm.py:47-51).  D % 4 == 0, 4 <= D <= 128.      */
+int dr_gather_fwd(const float* table, int64_t rows, const void* ids, int id_bytes,
+                  int64_t n, int D, float* out, void* stream);
+int dr_scatter_add(float* grad_table, int64_t rows, const void* ids, int id_bytes,
+                   int64_t n, int D, const float* g, float scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Row F standalone: FM second-order on a dense [B, S, D] tensor (any S, D >= 1).
+ *   replaces: keras/models/ranking/fm.py:28-35 ; estimator/.../fm.py:22-26.
+ *   out[b] = 0.5 * sum_d((sum_s x)^2 - sum_s x^2);  gx = g[b] * (sum_s x - x).
+ * ------------------------------------------------------------------------------------- */
+int dr_fm_fwd(const float* x, int64_t B, int S, int D, float* out, void* stream);
+int dr_fm_bwd(const float* x, const float* g, int64_t B, int S, int D, float* gx, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Row D: Dense layer  y = act(x @ W + b),  x [M,K], W [K,N] (Keras kernel layout), b [N].
+ *   replaces: tf.keras.layers.Dense in keras/models/ranking/deepfm.py:30-34, fm.py:16-20;
+ *             tf.layers.dense in estimator/models/feature_interaction/dnn.py:17-29.
+ *   fp32 accumulate, fp32-accurate products (no single-pass TF32/BF16).
+ * backward: gz = gy * act'(y) ; gx = gz @ W^T (NULL = skip) ; gw = x^T @ gz ; gb = colsum(gz).
+ *   gz_ws: [M,N] workspace (may alias gy if the caller no longer needs gy).  gw and gb
+ *   are OVERWRITTEN (not accumulated).
+ * ------------------------------------------------------------------------------------- */
+int dr_dense_fwd(const float* x, const float* w, const float* b, int64_t M, int K, int N,
+                 int act, float* y, void* stream);
+int dr_dense_bwd(const float* x, const float* w, const float* y, const float* gy,
+                 int64_t M, int K, int N, int act,
+                 float* gz_ws, float* gx, float* gw, float* gb, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Row X: Cross layer (DCN-v2 matrix form).
+ *   replaces: keras/models/ranking/dcn.py:70-88 (call) with build() :35-68.
+ *   full rank (r == 0):  u = x @ W + b + alpha*x        W [d,d]
+ *   low rank  (r  > 0):  u = (x @ U) @ V + b + alpha*x  U [d,r] (no bias), V [r,d]
+ *   y = x0 * u + x ;  u is saved ([B,d]) for backward.  b may be NULL (use_bias=False).
+ *   xu_ws: [B,r] workspace (low rank only; saved for backward).
+ * backward (g = dL/dy, h = g*x0):
+ *   gx0 = g*u ; gx = h @ W^T + alpha*h + g ; gW = x^T @ h ; gb = colsum(h)
+ *   (low rank: gV = (xU)^T @ h ; t = h @ V^T ; gU = x^T @ t ; gx = t @ U^T + alpha*h + g)
+ *   When the caller passed the same tensor as x0 and x it adds gx0 + gx itself.
+ *   h_ws [B,d], t_ws [B,r] workspaces.  gW/gU/gV/gb are OVERWRITTEN.
+ * ------------------------------------------------------------------------------------- */
+int dr_cross_fwd(const float* x0, const float* x, const float* w, const float* uk,
+                 const float* vk, const float* b, float alpha, int64_t B, int d, int r,
+                 float* xu_ws, float* u_out, float* y, void* stream);
+int dr_cross_bwd(const float* x0, const float* x, const float* w, const float* uk,
+                 const float* vk, float alpha, const float* u_saved, const float* xu_saved,
+                 const float* g, int64_t B, int d, int r,
+                 float* h_ws, float* t_ws, float* gx0, float* gx,
+                 float* gw, float* guk, float* gvk, float* gb, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Row R (+R1, R2): in-batch softmax loss of the two-tower Retrieval task, fused
+ *   Q @ C^T + online log-sum-exp; the [nq, nc] score matrix is never materialised.
+ *   replaces: keras/models/retrieval/sbcnm.py:120-151 (Retrieval.call), :78-86
+ *             (SamplingProbabilityCorrection), :52-75 (RemoveAccidentalNegative).
+ *   s_ij = (q_i . c_j - log p_j + dup_ij * MIN_FLOAT) * inv_tau,
+ *          dup_ij = [cand_ids_j == cand_ids_i] - [i == j],  MIN_FLOAT = FLT_MIN_ish/100
+ *   loss = sum_i w_i * (logsumexp_j s_ij - s_ii)      (CategoricalCrossentropy, SUM)
+ *   Q [nq,D], C [nc,D], nq <= nc (labels = eye(nq,nc)); w [nq] or NULL; p [nc] or NULL;
+ *   cand_ids [nc] int64 or NULL; lse_out [nq] saved for backward; loss_out [1] OVERWRITTEN.
+ * backward: G_ij = gl * w_i * (softmax(s)_ij - [i==j]) * inv_tau ; gQ = G @ C ; gC = G^T @ Q
+ *   (gQ, gC OVERWRITTEN; gloss [1] device scalar = upstream gradient of the loss).
+ * ------------------------------------------------------------------------------------- */
+int dr_inbatch_softmax_fwd(const float* q, const float* c, const float* w, const float* p,
+                           const int64_t* cand_ids, float inv_tau, int64_t nq, int64_t nc, int D,
+                           float* lse_out, float* loss_out, void* stream);
+int dr_inbatch_softmax_bwd(const float* q, const float* c, const float* w, const float* p,
+                           const int64_t* cand_ids, float inv_tau, int64_t nq, int64_t nc, int D,
+                           const float* lse, const float* gloss,
+                           float* gq, float* gc, void* stream);
+
+/* Materialised score matrix with the same corrections (needed by HardNegativeMining and
+ * by metrics): scores [nq,nc] = (Q @ C^T - log p + dup*MIN_FLOAT) (no temperature).       */
+int dr_scores_fwd(const float* q, const float* c, const float* p, const int64_t* cand_ids,
+                  int64_t nq, int64_t nc, int D, float* scores, void* stream);
+
+/* Row R3: HardNegativeMining (sbcnm.py:33-49): per row, indices of the k largest of
+ *   logits + labels*MAX_FLOAT (labels = eye) ; emits gathered logits [nq,k], labels [nq,k]
+ *   and the chosen column indices [nq,k] (int32).  Order inside a row is by descending
+ *   score (TF: sorted=False => unspecified).                                              */
+int dr_hard_negative_topk(const float* logits, int64_t nq, int64_t nc, int k,
+                          float* out_logits, float* out_labels, int32_t* out_idx, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Row-sharded tables: owner(r) = r mod G, local row = r div G.
+ *   dr_shard_bucket_ids: groups the flat id list [n] (n = B*S, slot = index % S) by owner.
+ *     global row = slot_offsets[s] + id (all S tables share one row space; slot_offsets and
+ *     rows may be NULL = ids are already global rows); an id outside [0, rows[s]) becomes
+ *     row -1 (owner 0, local id -1 => zero vector at the owner).
+ *     Writes send_counts [G] (int64), perm [n] (int32: position in owner-grouped order ->
+ *     original flat position) and local_ids [n] (int64, row div G, in grouped order).
+ *     cursor_ws: [G] int64 scratch.  Order inside one owner's group is unspecified.
+ *   The exchange itself (ids out, vectors back) is an NCCL all-to-all issued by the host
+ *   through torch.distributed; dr_unpermute_rows restores [n, D] rows to flat order
+ *   (out[perm[i]] = in[i]) and dr_permute_rows is its transpose (out[i] = in[perm[i]]).
+ * ------------------------------------------------------------------------------------- */
+int dr_shard_bucket_ids(const void* ids, int id_bytes, int64_t n, int S,
+                        const int64_t* slot_offsets, const int64_t* rows, int G,
+                        int64_t* send_counts, int64_t* cursor_ws, int32_t* perm,
+                        int64_t* local_ids, void* stream);
+int dr_permute_rows(const float* in, const int32_t* perm, int64_t n, int D, float* out, void* stream);
+int dr_unpermute_rows(const float* in, const int32_t* perm, int64_t n, int D, float* out, void* stream);
+
+/* Fused SGD for dense parameters: p -= lr * g  (n elements). */
+int dr_sgd_step(float* p, const float* g, int64_t n, float lr, void* stream);
+/* Binary cross-entropy on logits, mean over B (tf.keras.losses.binary_crossentropy on
+ * sigmoid outputs == this on logits), and its gradient wrt the logits:
+ *   loss[0] = mean_b( max(z,0) - z*y + log1p(exp(-|z|)) ) ; gz[b] = (sigmoid(z)-y)/B.
+ *   prob_out [B] (sigmoid) may be NULL.                                                   */
+int dr_bce_logits_fwd_bwd(const float* z, const float* y, int64_t B,
+                          float* prob_out, float* loss_out, float* gz, void* stream);
+
+/* Developer hook (not reference-facing): set a kernel tuning knob by name, e.g.
+ * "embed_fwd_unroll", "embed_block", "embed_bwd_agg", "gemm_splitk".                     */
+int dr_tune_set(const char* key, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPREC_B200_H_ */

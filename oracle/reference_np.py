@@ -1,0 +1,275 @@
+"""ORACLE -- test infrastructure only.  Nothing under deep_recommenders_b200/ may import this.
+
+CPU restatement, in numpy, of the arithmetic on the hot path of
+LongmaoTeamTf/deep_recommenders (paths below are relative to the reference repo root).
+The reference is pure Python over TensorFlow and TensorFlow is not installed in this
+environment (nor on the GPU box), so the reference itself cannot execute; each function
+below follows the cited reference lines op for op, with TensorFlow's documented op semantics
+(tf.reduce_sum / tf.pow / Dense = x @ W[in,out] + b / embedding lookup with OOV -> zeros /
+CategoricalCrossentropy(from_logits, SUM)) filled in.
+
+How it is pinned (see oracle/README.md and tests/test_oracle.py):
+  * the reference's own known-answer and property tests are ported onto it
+    (tests/keras/test_dcn.py:16-23, test_fm.py:17-26, test_sbcnm.py:16-55,
+     tests/estimator/test_fm.py:18-26);
+  * the reference's *own source files* are executed under a numpy-backed `tensorflow`
+    stand-in (oracle/tf_shim) to generate tests/golden/*.npz, and the oracle must reproduce
+    those bit-for-bit in float64 / to 1e-6 in float32;
+  * every analytic backward here is checked against torch-CPU autograd of the forward.
+Parity UNPINNED by the reference (it has no test for them): embedding-lookup values, all
+gradients, Retrieval.call, SamplingProbabilityCorrection.  For those the pin is the shim run
+and the float64 twin only.
+
+Every function takes ``dtype`` (np.float32 = the parity target, np.float64 = error budget).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+MAX_FLOAT = np.finfo(np.float32).max / 100.0     # keras/models/retrieval/sbcnm.py:9
+MIN_FLOAT = np.finfo(np.float32).min / 100.0     # keras/models/retrieval/sbcnm.py:10
+
+
+# ------------------------------------------------------------------------------------------
+# Row E: embedding lookup.  keras fm.py:47-51,57-61 / deepfm.py:25-28,39-43 build one
+# DenseFeatures(embedding_column) per key; estimator fm.py:48-52 uses input_layer.  For a
+# single-valued id this is a row gather; id -1 (OOV) or out of range -> zero vector.
+# ------------------------------------------------------------------------------------------
+def embedding_lookup(table: np.ndarray, ids: np.ndarray) -> np.ndarray:
+    ids = np.asarray(ids, dtype=np.int64)
+    ok = (ids >= 0) & (ids < table.shape[0])
+    out = np.zeros(ids.shape + (table.shape[1],), dtype=table.dtype)
+    out[ok] = table[ids[ok]]
+    return out
+
+
+def stack_embeddings(tables, ids: np.ndarray) -> np.ndarray:
+    """tf.stack([lookup_s(ids[:, s]) for s], axis=1) -> [B,S,D]   (deepfm.py:39-44)."""
+    return np.stack([embedding_lookup(t, ids[:, s]) for s, t in enumerate(tables)], axis=1)
+
+
+# Row L: first-order term.  keras fm.py:16-20,26: Dense(1)(multi_hot) with a [sum N, 1] kernel
+# == sum_s w_s[id_s] + b (OOV -> all-zero indicator row -> contributes 0).
+def linear_term(lin_weights, bias, ids: np.ndarray, dtype=np.float32) -> np.ndarray:
+    ids = np.asarray(ids, dtype=np.int64)
+    out = np.zeros((ids.shape[0],), dtype=dtype)
+    for s, w in enumerate(lin_weights):
+        col = ids[:, s]
+        ok = (col >= 0) & (col < w.shape[0])
+        v = np.zeros(col.shape, dtype=dtype)
+        v[ok] = w[col[ok]].astype(dtype)
+        out = out + v
+    return (out + dtype(bias)).reshape(-1, 1)
+
+
+# Row F: FM second order.  keras fm.py:28-35 (tf.pow(.,2)) == estimator fm.py:22-26 (tf.square).
+def fm_second_order(x: np.ndarray, dtype=np.float32) -> np.ndarray:
+    if x.ndim != 3:
+        raise ValueError("The rank of `x` should be 3. Got rank = {}.".format(x.ndim))   # estimator fm.py:19-20
+    x = x.astype(dtype)
+    x_sum = np.sum(x, axis=1)                                  # fm.py:28
+    x_square_sum = np.sum(np.power(x, 2), axis=1)              # fm.py:29
+    return (dtype(0.5) * np.sum(np.power(x_sum, 2) - x_square_sum, axis=1, keepdims=True)).astype(dtype)  # :31-35
+
+
+def fm_second_order_grad(x: np.ndarray, g: np.ndarray, dtype=np.float32) -> np.ndarray:
+    """d/dx of the above times upstream g [B,1]:  g * (sum_s x - x)."""
+    x = x.astype(dtype)
+    return (g.reshape(-1, 1, 1).astype(dtype) * (np.sum(x, axis=1, keepdims=True) - x)).astype(dtype)
+
+
+def fm_logit(tables, lin_weights, bias, ids, dtype=np.float32):
+    """FM.call(sparse, stack) = linear + interaction (keras fm.py:37; estimator fm.py:56)."""
+    stack = stack_embeddings(tables, ids)
+    return linear_term(lin_weights, bias, ids, dtype) + fm_second_order(stack, dtype), stack
+
+
+def sigmoid(z, dtype=np.float32):
+    z = z.astype(dtype)
+    return (1.0 / (1.0 + np.exp(-z))).astype(dtype)
+
+
+# Row D: Dense / DNN tower.  keras deepfm.py:30-34 ; estimator dnn.py:17-29.
+def act(z, name):
+    if name in (None, "linear"):
+        return z
+    if name == "relu":
+        return np.maximum(z, 0)
+    if name == "sigmoid":
+        return 1.0 / (1.0 + np.exp(-z))
+    if name == "tanh":
+        return np.tanh(z)
+    raise ValueError(name)
+
+
+def dense(x, w, b=None, activation=None, dtype=np.float32):
+    z = x.astype(dtype) @ w.astype(dtype)
+    if b is not None:
+        z = z + b.astype(dtype)
+    return act(z, activation).astype(dtype)
+
+
+def dnn(x, weights, biases, activation="relu", dtype=np.float32):
+    """[Dense(u, act) ...] + [Dense(last)] : activation on all but the last layer."""
+    h = x
+    hs = [x]
+    for i, (w, b) in enumerate(zip(weights, biases)):
+        h = dense(h, w, b, activation if i < len(weights) - 1 else None, dtype)
+        hs.append(h)
+    return h, hs
+
+
+def dense_grad(x, w, y, gy, activation=None, dtype=np.float32):
+    """(gx, gw, gb) of y = act(x@w+b) given upstream gy."""
+    x, w, y, gy = (a.astype(dtype) for a in (x, w, y, gy))
+    if activation == "relu":
+        gz = gy * (y > 0)
+    elif activation == "sigmoid":
+        gz = gy * y * (1 - y)
+    elif activation == "tanh":
+        gz = gy * (1 - y * y)
+    else:
+        gz = gy
+    return gz @ w.T, x.T @ gz, gz.sum(axis=0)
+
+
+# Model assembly (row M).  keras deepfm.py:36-47.
+def deepfm_forward(tables, lin_weights, bias, dnn_w, dnn_b, ids, activation="relu", dtype=np.float32):
+    fm_out, stack = fm_logit(tables, lin_weights, bias, ids, dtype)
+    concat = stack.reshape(stack.shape[0], -1)                 # tf.concat(embeddings, axis=1)  deepfm.py:45
+    deep, hs = dnn(concat, dnn_w, dnn_b, activation, dtype)    # deepfm.py:30-34,46
+    logits = fm_out + deep
+    return sigmoid(logits, dtype), logits, stack, hs           # deepfm.py:47
+
+
+# Row X: Cross.  keras dcn.py:70-88.
+def cross(x0, x=None, w=None, b=None, u=None, v=None, diag_scale=0.0, dtype=np.float32):
+    if x is None:
+        x = x0                                                  # dcn.py:72-73
+    if x0.shape[-1] != x.shape[-1]:
+        raise ValueError("`x0` and `x` dim mismatch. Got `x0` dim = {} and `x` dim = {}".format(
+            x0.shape[-1], x.shape[-1]))                         # dcn.py:75-78
+    x0 = x0.astype(dtype)
+    x = x.astype(dtype)
+    if w is not None:
+        prod = x @ w.astype(dtype)                              # dcn.py:80-81
+    else:
+        prod = (x @ u.astype(dtype)) @ v.astype(dtype)          # dcn.py:83
+    if b is not None:
+        prod = prod + b.astype(dtype)
+    if diag_scale:
+        prod = prod + dtype(diag_scale) * x                     # dcn.py:85-86
+    return (x0 * prod + x).astype(dtype), prod                  # dcn.py:88
+
+
+def cross_grad(x0, x, g, w=None, u=None, v=None, b=None, diag_scale=0.0, dtype=np.float32):
+    """Analytic backward of `cross`.  Returns dict of gradients."""
+    x0, x, g = (a.astype(dtype) for a in (x0, x, g))
+    _, prod = cross(x0, x, w, b, u, v, diag_scale, dtype)
+    h = g * x0
+    out = {"gx0": g * prod, "gb": h.sum(axis=0)}
+    if w is not None:
+        out["gw"] = x.T @ h
+        out["gx"] = h @ w.astype(dtype).T + dtype(diag_scale) * h + g
+    else:
+        xu = x @ u.astype(dtype)
+        t = h @ v.astype(dtype).T
+        out["gv"] = xu.T @ h
+        out["gu"] = x.T @ t
+        out["gx"] = t @ u.astype(dtype).T + dtype(diag_scale) * h + g
+    return out
+
+
+# Rows R, R1, R2, R3: two-tower task.  keras/models/retrieval/sbcnm.py.
+def gather_elements_along_row(data, column_indices):           # sbcnm.py:15-30
+    assert data.shape[0] == column_indices.shape[0]
+    return np.take_along_axis(data, column_indices, axis=1)
+
+
+def hard_negative_mining(logits, labels, num_hard_negatives):  # sbcnm.py:33-49
+    num_sampled = min(num_hard_negatives + 1, logits.shape[1])
+    masked = logits + labels * np.float32(MAX_FLOAT)
+    # tf.nn.top_k(sorted=False): any order; we use descending value, ties -> lower index
+    idx = np.argsort(-masked, axis=1, kind="stable")[:, :num_sampled]
+    return gather_elements_along_row(logits, idx), gather_elements_along_row(labels, idx), idx
+
+
+def remove_accidental_negative(logits, labels, identifiers):   # sbcnm.py:52-75
+    identifiers = np.asarray(identifiers).reshape(-1, 1)
+    positive_indices = np.argmax(labels, axis=1)
+    positive_identifier = identifiers[positive_indices]        # [B,1]
+    duplicate = (positive_identifier == identifiers.T).astype(labels.dtype)
+    duplicate = duplicate - labels
+    return logits + duplicate * np.float32(MIN_FLOAT)
+
+
+def sampling_probability_correction(logits, p):                # sbcnm.py:78-86
+    return logits - np.log(p).astype(logits.dtype)
+
+
+def categorical_crossentropy_sum(labels, scores, sample_weight=None, dtype=np.float32):
+    """tf.keras.losses.CategoricalCrossentropy(from_logits=True, reduction=SUM) (sbcnm.py:100-102)."""
+    s = scores.astype(dtype)
+    m = s.max(axis=1, keepdims=True)
+    lse = m + np.log(np.exp(s - m).sum(axis=1, keepdims=True))
+    per_row = -(labels.astype(dtype) * (s - lse)).sum(axis=1)
+    if sample_weight is not None:
+        per_row = per_row * np.asarray(sample_weight, dtype=dtype).reshape(-1)
+    return dtype(per_row.sum())
+
+
+def retrieval_loss(q, c, sample_weight=None, candidate_sampling_probability=None, candidate_ids=None,
+                   temperature=None, num_hard_negatives=None, dtype=np.float32):
+    """Retrieval.call (sbcnm.py:120-151) with the *intended* semantics of its three optional
+    branches (:136-146 are broken in the reference; the helper layers define the intent)."""
+    scores = q.astype(dtype) @ c.astype(dtype).T                # :129
+    labels = np.eye(scores.shape[0], scores.shape[1], dtype=dtype)   # :134
+    if candidate_sampling_probability is not None:
+        scores = sampling_probability_correction(scores, np.asarray(candidate_sampling_probability, dtype=dtype))
+    if candidate_ids is not None:
+        scores = remove_accidental_negative(scores, labels, candidate_ids).astype(dtype)
+    if num_hard_negatives is not None:
+        scores, labels, _ = hard_negative_mining(scores, labels, num_hard_negatives)
+    if temperature is not None:
+        scores = scores / dtype(temperature)                    # :148-149
+    return categorical_crossentropy_sum(labels, scores, sample_weight, dtype), scores, labels
+
+
+def retrieval_grad(q, c, sample_weight=None, candidate_sampling_probability=None, candidate_ids=None,
+                   temperature=None, dtype=np.float64):
+    """(gq, gc) of the no-hard-negative loss: G = w_i (softmax - eye) / tau ; gq = G c ; gc = G^T q."""
+    _, scores, labels = retrieval_loss(q, c, sample_weight, candidate_sampling_probability, candidate_ids,
+                                       temperature, None, dtype)
+    s = scores.astype(dtype)
+    p = np.exp(s - s.max(axis=1, keepdims=True))
+    p = p / p.sum(axis=1, keepdims=True)
+    G = p - labels
+    if sample_weight is not None:
+        G = G * np.asarray(sample_weight, dtype=dtype).reshape(-1, 1)
+    if temperature is not None:
+        G = G / dtype(temperature)
+    return G @ c.astype(dtype), G.T @ q.astype(dtype)
+
+
+# Backward of the fused embedding + linear + FM block (SURVEY.md 8a rows E/L/F backward).
+def embed_fm_grad(tables_rows, ids, stack, g_logit, g_stack, dtype=np.float64):
+    """Dense gradients TF autodiff + IndexedSlices densification would give.
+    Returns (grad_tables list, grad_lin list, grad_bias)."""
+    ids = np.asarray(ids, dtype=np.int64)
+    B, S, D = stack.shape
+    st = stack.astype(dtype)
+    gl = np.zeros((B,), dtype) if g_logit is None else np.asarray(g_logit, dtype).reshape(B)
+    dE = gl[:, None, None] * (st.sum(axis=1, keepdims=True) - st)
+    if g_stack is not None:
+        dE = dE + np.asarray(g_stack, dtype).reshape(B, S, D)
+    gts, gls = [], []
+    for s, rows in enumerate(tables_rows):
+        gt = np.zeros((rows, D), dtype)
+        glin = np.zeros((rows,), dtype)
+        col = ids[:, s]
+        ok = (col >= 0) & (col < rows)
+        np.add.at(gt, col[ok], dE[ok, s, :])
+        np.add.at(glin, col[ok], gl[ok])
+        gts.append(gt)
+        gls.append(glin)
+    return gts, gls, dtype(gl.sum())

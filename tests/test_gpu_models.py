@@ -1,0 +1,131 @@
+"""Row M (model assembly) on the GPU: the reference's model-level tests ported
+(tests/keras/test_fm.py:67-107, tests/keras/test_deepfm.py:16-56: two hash-bucket(100) columns,
+dim 16, train, predict, save / load round trip with get_config equality and assertAllEqual on the
+predictions), plus parity of the whole DeepFM forward against the oracle."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_np as R
+
+pytestmark = pytest.mark.gpu
+
+
+def build_columns():
+    from deep_recommenders_b200 import feature_column as fc
+    user_id = fc.categorical_column_with_hash_bucket("user_id", 100)
+    movie_id = fc.categorical_column_with_hash_bucket("movie_id", 100)
+    base = [user_id, movie_id]
+    return [fc.indicator_column(c) for c in base], [fc.embedding_column(c, dimension=16) for c in base]
+
+
+def collection_arrays(coll):
+    tables = [coll.table(s).detach().cpu().numpy() for s in range(coll.num_slots)]
+    lins = [coll.linear_of(s).detach().cpu().numpy() for s in range(coll.num_slots)]
+    return tables, lins, float(coll.bias)
+
+
+def test_deepfm_forward_matches_oracle():
+    from deep_recommenders.keras.models.ranking import DeepFM
+    from deep_recommenders_b200 import feature_column as fc
+    cols = [fc.categorical_column_with_identity(f"c{i}", 50 + i) for i in range(6)]
+    model = DeepFM([fc.indicator_column(c) for c in cols], [fc.embedding_column(c, 16) for c in cols],
+                   dnn_units_size=[64, 32], seed=3, device="cuda")
+    with torch.no_grad():
+        model.embeddings.linear.normal_(0, 0.1)
+        model.embeddings.bias.fill_(0.1)
+    rng = np.random.default_rng(0)
+    ids = np.stack([rng.integers(-1, 50 + i, 300) for i in range(6)], axis=1).astype(np.int64)
+    inputs = {f"c{i}": torch.from_numpy(ids[:, i]).cuda() for i in range(6)}
+    prob = model(inputs)
+    assert prob.shape == (300, 1)
+    tables, lins, bias = collection_arrays(model.embeddings)
+    ws = [l.kernel.detach().cpu().numpy() for l in model._dnn.layers]
+    bs = [l.bias.detach().cpu().numpy() for l in model._dnn.layers]
+    ref_prob, ref_logits, _, _ = R.deepfm_forward(tables, lins, bias, ws, bs, ids, "relu", np.float64)
+    assert np.allclose(prob.detach().cpu().numpy(), ref_prob, rtol=1e-5, atol=1e-6)
+    assert np.allclose(model.logits(inputs).detach().cpu().numpy(), ref_logits, rtol=1e-5, atol=2e-5)
+    assert set(model.get_config()) >= {"dnn_units_size", "dnn_activation"}
+
+
+@pytest.mark.parametrize("which", ["fm", "deepfm"])
+def test_ref_model_train_predict_save_load(which):
+    from deep_recommenders.keras.models.ranking import DeepFM, FactorizationMachine
+    ind, emb = build_columns()
+    mk = (lambda: FactorizationMachine(ind, emb, seed=1, device="cuda")) if which == "fm" else \
+         (lambda: DeepFM(ind, emb, dnn_units_size=[10, 5], seed=1, device="cuda"))
+    model = mk()
+    feats = {"user_id": np.asarray([["1"]] * 1000), "movie_id": np.asarray([["2"]] * 1000)}
+    labels = torch.zeros(1000, 1, device="cuda")                 # np.random.randint(0, 1) is always 0
+    model(feats)                                                 # build lazily-created layers
+    opt = torch.optim.Adam(model.parameters())
+    first = None
+    for _ in range(20):
+        opt.zero_grad()
+        p = model(feats)
+        loss = torch.nn.functional.binary_cross_entropy(p, labels)
+        loss.backward()
+        opt.step()
+        first = first if first is not None else float(loss)
+    assert float(loss) < first
+    test_data = {"user_id": np.asarray([["1"], ["2"]]), "movie_id": np.asarray([["1"], ["2"]])}
+    pred = model.predict(test_data)
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "model.pt")
+        model.save(path)
+        blob = torch.load(path, weights_only=False)
+        loaded = mk()
+        loaded(test_data)
+        loaded.load_state_dict(blob["state"])
+        loaded_pred = loaded.predict(test_data)
+    assert model.get_config() == loaded.get_config()
+    assert torch.equal(pred, loaded_pred)                         # assertAllEqual
+
+
+def test_estimator_twins():
+    from deep_recommenders.estimator.models.feature_interaction import FM, dnn
+    from deep_recommenders.estimator.models.ranking.deepfm import DeepFM
+    ind, emb = build_columns()
+    feats = {"user_id": np.asarray(["7", "8", "9"]), "movie_id": np.asarray(["1", "2", "3"])}
+    fm = FM(ind, emb, seed=0, device="cuda")
+    out = fm(feats)
+    assert out.shape == (3, 1) and len(fm.embeddings) == 2 and fm.embeddings[0].shape == (3, 16)
+    y = dnn(torch.randn(5, 8, device="cuda"), [4, 2], name="t")
+    assert y.shape == (5, 2)
+    with pytest.raises(TypeError):
+        dnn(torch.randn(5, 8, device="cuda"), [4, 2], batch_normalization=True)
+    p = DeepFM(ind, emb, [8, 4], seed=0, device="cuda")(feats)
+    assert p.shape == (3, 1) and float(p.min()) > 0 and float(p.max()) < 1
+
+
+def test_dcn_and_two_tower_train_step():
+    from deep_recommenders.keras.layers import DCN, TwoTower
+    model = DCN([100] * 6, 8, num_cross=2, dnn_units=[32, 16], seed=0, device="cuda")
+    ids = torch.randint(0, 100, (64, 6), device="cuda")
+    y = torch.randint(0, 2, (64, 1), device="cuda").float()
+    z = model.logits(ids)
+    params = list(model.parameters())
+    opt = torch.optim.SGD(params, lr=0.1)
+    l0 = None
+    for _ in range(30):
+        opt.zero_grad()
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(model.logits(ids), y)
+        loss.backward()
+        opt.step()
+        l0 = l0 if l0 is not None else float(loss)
+    assert float(loss) < l0
+    tt = TwoTower(500, 800, dim=32, temperature=0.5, seed=0, device="cuda")
+    u = torch.randint(0, 500, (128,), device="cuda")
+    i = torch.randint(0, 800, (128,), device="cuda")
+    opt = torch.optim.SGD(tt.parameters(), lr=0.05)
+    l0 = None
+    for _ in range(20):
+        opt.zero_grad()
+        loss = tt(u, i, remove_accidental_hits=True)
+        loss.backward()
+        opt.step()
+        l0 = l0 if l0 is not None else float(loss)
+    assert float(loss) < l0
