@@ -1,0 +1,263 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native hot path (contract: see DESIGN.md section 6).
+
+    python bench.py --gpus 1 --steps K --warmup W            # our arm
+    python bench.py --impl reference --steps K --warmup W     # CPU restatement of the reference path
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W
+
+Metric (BASELINE.json): examples/sec (fwd+bwd) DeepFM batch=65536.  Workload at N=1 = config C2:
+26 categorical slots x 1M-row tables, D=16, batch 65536, DNN [256,32]->1, synthetic uniform ids,
+one step = forward + backward + SGD update (row-sparse on the tables, dense on the tower).
+A step never skips work: every kernel of fwd, bwd and the optimizer runs inside the timed region.
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "examples/sec (fwd+bwd) DeepFM batch=65536"
+C2 = dict(slots=26, rows=1_000_000, dim=16, batch=65536, dnn=[256, 32])
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi sampler running during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU path (restated in torch-CPU: TensorFlow is not in this image)."""
+    import torch
+    from oracle.torch_cpu import DeepFMCPU
+    torch.manual_seed(0)
+    cores = torch.get_num_threads()
+    rows = [C2["rows"]] * C2["slots"]
+    B = C2["batch"]
+    model = DeepFMCPU(rows, C2["dim"], C2["dnn"], seed=0)
+    g = torch.Generator().manual_seed(1)
+    pool = [(torch.randint(0, C2["rows"], (B, C2["slots"]), generator=g),
+             torch.randint(0, 2, (B,), generator=g).float()) for _ in range(2)]
+    for i in range(max(1, args.warmup)):
+        model.train_step(*pool[i % 2], 0.01)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        model.train_step(*pool[i % 2], 0.01)
+    dt = time.perf_counter() - t0
+    v = B * args.steps / dt
+    sample = f"{args.steps} full train steps (fwd+bwd+SGD) at B={B}, torch-CPU restatement of the reference path"
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "examples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": v, "unit": "examples/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "examples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "CPU restatement of the reference path (torch-CPU), not TensorFlow: TF is not installed in this image"}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n):
+    return {"workload": f"C2 DeepFM: {C2['slots']} slots x {C2['rows']} rows, D={C2['dim']}, batch {C2['batch']} per GPU, "
+                        f"DNN {C2['dnn']}->1, BCE, SGD (row-sparse tables + dense tower)",
+            "global_batch": C2["batch"] * n, "parallelism": "single GPU" if n == 1 else f"row-sharded tables x{n} + data-parallel tower",
+            "l2": "inputs larger than L2: 2.1 GB of tables, id batches and activations rotate through a pool",
+            "ids": "uniform int64"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank == 0:
+            run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from deep_recommenders_b200 import _lib, feature_column as fc
+    from deep_recommenders_b200.keras.models.ranking import DeepFM
+    from deep_recommenders_b200.training import DeepFMTrainStep
+
+    B, S, D = C2["batch"], C2["slots"], C2["dim"]
+    cols = [fc.categorical_column_with_identity(f"C{i}", C2["rows"]) for i in range(S)]
+    if world > 1:
+        from deep_recommenders_b200.sharded import ShardedDeepFMTrainStep
+        trainer = ShardedDeepFMTrainStep(cols, D, C2["dnn"], batch_size=B, lr=0.01, seed=1, device=dev).capture()
+    else:
+        model = DeepFM([fc.indicator_column(c) for c in cols], [fc.embedding_column(c, D) for c in cols],
+                       dnn_units_size=C2["dnn"], seed=1, device=dev, sparse_lr=0.01)
+        trainer = DeepFMTrainStep(model, batch_size=B, lr=0.01).capture()
+
+    # synthetic MovieLens-shaped batches: pool resident in HBM (value) and in pinned host memory (e2e)
+    NP = 8
+    gen = torch.Generator(device=dev).manual_seed(100 + rank)
+    ids_pool = [torch.randint(0, C2["rows"], (B, S), device=dev, generator=gen) for _ in range(NP)]
+    lab_pool = [torch.randint(0, 2, (B,), device=dev, generator=gen).float() for _ in range(NP)]
+    host_ids = [t.cpu().pin_memory() for t in ids_pool]
+    host_lab = [t.cpu().pin_memory() for t in lab_pool]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t)
+        return ms
+
+    # ---- device-resident timed region ------------------------------------------------------------
+    for i in range(args.warmup):
+        trainer.step(ids_pool[i % NP], lab_pool[i % NP])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            trainer.step(ids_pool[i % NP], lab_pool[i % NP])
+        e1.record()
+        barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    value = B * world * args.steps / (ms * 1e-3)
+    final_loss = float(trainer.loss.item())
+
+    # ---- end-to-end: host buffers in, loss out, copies inside the timed region --------------------
+    for i in range(args.warmup):
+        trainer.train_step_host(host_ids[i % NP], host_lab[i % NP], host_ids[(i + 1) % NP], host_lab[(i + 1) % NP])
+    trainer._staged = None
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        trainer.train_step_host(host_ids[i % NP], host_lab[i % NP], host_ids[(i + 1) % NP], host_lab[(i + 1) % NP])
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e = {"value": B * world * args.steps / (ms_e2e * 1e-3), "unit": "examples/s",
+           "h2d_bytes_per_step": (host_ids[0].numel() * host_ids[0].element_size() + host_lab[0].numel() * 4) * world,
+           "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the headline kernel (fused gather+FM forward), timed live with CUDA events ----
+    peaks, peak_kind = measured_peaks()
+    roof, shares = trainer.profile_kernels(ids_pool, lab_pool, iters=max(10, args.steps))
+    alg_bytes = B * (S * (8 + 4 * D + 4) + 4 * S * D + 4 * D + 4)      # ids + rows + w + stack + sum_e + logit
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "embed_fwd_traffic.json")))["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    fwd_s = roof["embed_fm_fwd_ms"] * 1e-3
+    roofline = {"kernel": "embed_fm_fwd_kernel (fused 26-slot gather + first-order + FM)", "bound": "hbm",
+                "achieved": alg_bytes / fwd_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": alg_bytes / fwd_s / 1e9 / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_kind,
+                "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": fwd_s * 1e6}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle.torch_cpu import time_deepfm_cpu
+        r = time_deepfm_cpu([C2["rows"]] * S, D, C2["dnn"], B, steps=8, warmup=1, max_seconds=25.0)
+        cpu = {"value": r["examples_per_sec"], "unit": "examples/s", "cores": r["cores"], "kind": "port",
+               "sample": f"{r['steps']} full train steps at B={B} (torch-CPU restatement of the reference path, "
+                         f"not TensorFlow), host has {os.cpu_count()} logical CPUs"}
+
+    line = {"metric": METRIC, "value": value, "unit": "examples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(trainer.launches_per_step * args.steps),
+            "launches_per_step": int(trainer.launches_per_step), "roofline": roofline, "kernel_ms": shares,
+            "cpu_baseline": cpu, "final_loss": final_loss,
+            "cuda_graph": trainer.graph is not None}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -28,8 +28,8 @@ _SIGS = {
     "dr_last_error": [],
     "dr_launch_count": [],
     "dr_tune_set": [C.c_char_p, _i],
-    "dr_embed_fm_fwd": [_p, _p, _p, _p, _i, _p, _i64, _i, _i, _p, _p, _p, _p],
-    "dr_embed_fm_bwd": [_p, _i, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _f, _p],
+    "dr_embed_fm_fwd": [_p, _p, _p, _p, _i, _p, _i64, _i, _i, _i64, _i64, _p, _p, _p, _p],
+    "dr_embed_fm_bwd": [_p, _i, _p, _p, _p, _p, _p, _i64, _i, _i, _i64, _i64, _p, _p, _p, _f, _p],
     "dr_gather_fwd": [_p, _i64, _p, _i, _i64, _i, _p, _p],
     "dr_scatter_add": [_p, _i64, _p, _i, _i64, _i, _p, _f, _p],
     "dr_fm_fwd": [_p, _i64, _i, _i, _p, _p],
@@ -46,7 +46,7 @@ _SIGS = {
     "dr_permute_rows": [_p, _p, _i64, _i, _p, _p],
     "dr_unpermute_rows": [_p, _p, _i64, _i, _p, _p],
     "dr_sgd_step": [_p, _p, _i64, _f, _p],
-    "dr_bce_logits_fwd_bwd": [_p, _p, _i64, _p, _p, _p, _p],
+    "dr_bce_logits_fwd_bwd": [_p, _p, _p, _i64, _p, _p, _p, _p],
 }
 _RESTYPES = {"dr_last_error": C.c_char_p, "dr_launch_count": C.c_uint64}
 

@@ -36,6 +36,8 @@ struct EmbedFwdParams {
   const float* bias;
   int64_t B;
   int S, D;
+  int64_t row_stride;   // floats between consecutive rows of a table (>= D)
+  int64_t lin_stride;   // floats between consecutive first-order weights (>= 1)
   float* out_stack;
   float* out_sum;
   float* out_logit;
@@ -56,6 +58,8 @@ struct EmbedBwdParams {
   float* single_grad;
   float* g_bias;
   float scale;
+  int64_t row_stride;
+  int64_t lin_stride;
 };
 
 // shared memory carve-up: [S] table ptr | [S] lin ptr | [S] rows | per-warp id slices
@@ -120,7 +124,7 @@ __global__ void __launch_bounds__(512) embed_fm_fwd_kernel(const EmbedFwdParams 
         v[u] = f4_zero();
         if (s < S && ex_ok && chunk_ok) {
           const int64_t id = (int64_t)my[s];
-          if ((uint64_t)id < (uint64_t)s_rows[s]) v[u] = ldg_nc_na(s_tab[s] + (size_t)id * D + c * 4);
+          if ((uint64_t)id < (uint64_t)s_rows[s]) v[u] = ldg_nc_na(s_tab[s] + (size_t)id * p.row_stride + c * 4);
         }
       }
 #pragma unroll
@@ -142,7 +146,7 @@ __global__ void __launch_bounds__(512) embed_fm_fwd_kernel(const EmbedFwdParams 
       if (has_lin && ex_ok) {
         for (int s = c; s < S; s += LPR) {   // the LPR lanes split the S scalar gathers
           const int64_t id = (int64_t)my[s];
-          if ((uint64_t)id < (uint64_t)s_rows[s]) lin += __ldg(s_lin[s] + id);
+          if ((uint64_t)id < (uint64_t)s_rows[s]) lin += __ldg(s_lin[s] + (size_t)id * p.lin_stride);
         }
       }
       float t = (sum.x * sum.x - sq.x) + (sum.y * sum.y - sq.y) + (sum.z * sum.z - sq.z) +
@@ -257,7 +261,7 @@ __global__ void __launch_bounds__(512) embed_fm_bwd_kernel(const EmbedBwdParams 
             leader = (__ffs(peers) - 1) == lane;
           }
         }
-        if (ok && leader) red_add_v4(s_tab[s] + (size_t)id * D + c * 4, d);
+        if (ok && leader) red_add_v4(s_tab[s] + (size_t)id * p.row_stride + c * 4, d);
       }
     }
 
@@ -265,7 +269,7 @@ __global__ void __launch_bounds__(512) embed_fm_bwd_kernel(const EmbedBwdParams 
       const float gv = scale * gl;
       for (int s = c; s < S; s += LPR) {
         const int64_t id = (int64_t)my[s];
-        if ((uint64_t)id < (uint64_t)s_rows[s]) red_add_f32(s_lin[s] + id, gv);
+        if ((uint64_t)id < (uint64_t)s_rows[s]) red_add_f32(s_lin[s] + (size_t)id * p.lin_stride, gv);
       }
     }
     __syncwarp();
@@ -403,25 +407,32 @@ using namespace dr;
 
 extern "C" int dr_embed_fm_fwd(const float* const* table_ptrs, const float* const* lin_ptrs,
                                const int64_t* rows, const void* ids, int id_bytes, const float* bias,
-                               int64_t B, int S, int D, float* out_stack, float* out_sum,
-                               float* out_logit, void* stream) {
+                               int64_t B, int S, int D, int64_t row_stride, int64_t lin_stride,
+                               float* out_stack, float* out_sum, float* out_logit, void* stream) {
   if (int rc = check_dims("dr_embed_fm_fwd", B, S, D, id_bytes)) return rc;
   DR_REQUIRE(table_ptrs && rows && ids, DR_EINVAL, "dr_embed_fm_fwd: null table_ptrs/rows/ids");
   DR_REQUIRE(out_stack || out_logit || out_sum, DR_EINVAL, "dr_embed_fm_fwd: no output requested");
+  if (row_stride == 0) row_stride = D;
+  if (lin_stride == 0) lin_stride = 1;
+  DR_REQUIRE(row_stride >= D && row_stride % 4 == 0, DR_EINVAL,
+             "dr_embed_fm_fwd: row_stride=%lld must be >= D and a multiple of 4", (long long)row_stride);
+  DR_REQUIRE(lin_stride >= 1, DR_EINVAL, "dr_embed_fm_fwd: lin_stride=%lld < 1", (long long)lin_stride);
   DR_REQUIRE(!out_stack || aligned16(out_stack), DR_EALIGN, "dr_embed_fm_fwd: out_stack not 16-B aligned");
   DR_REQUIRE(!out_sum || aligned16(out_sum), DR_EALIGN, "dr_embed_fm_fwd: out_sum not 16-B aligned");
   if (B == 0) return DR_OK;
   EmbedFwdParams p{};
   p.table_ptrs = table_ptrs; p.lin_ptrs = lin_ptrs; p.rows = rows; p.ids = ids; p.bias = bias;
   p.B = B; p.S = S; p.D = D; p.out_stack = out_stack; p.out_sum = out_sum; p.out_logit = out_logit;
+  p.row_stride = row_stride; p.lin_stride = lin_stride;
   cudaStream_t st = (cudaStream_t)stream;
   DR_DISPATCH_LPR(launch_fwd, p, st);
 }
 
 extern "C" int dr_embed_fm_bwd(const void* ids, int id_bytes, const int64_t* rows, const float* stack,
                                const float* sum_e, const float* g_logit, const float* g_stack,
-                               int64_t B, int S, int D, float* const* grad_table_ptrs,
-                               float* const* grad_lin_ptrs, float* g_bias, float scale, void* stream) {
+                               int64_t B, int S, int D, int64_t row_stride, int64_t lin_stride,
+                               float* const* grad_table_ptrs, float* const* grad_lin_ptrs, float* g_bias,
+                               float scale, void* stream) {
   if (int rc = check_dims("dr_embed_fm_bwd", B, S, D, id_bytes)) return rc;
   DR_REQUIRE(ids && rows && grad_table_ptrs, DR_EINVAL, "dr_embed_fm_bwd: null ids/rows/grad_table_ptrs");
   DR_REQUIRE(g_logit || g_stack, DR_EINVAL, "dr_embed_fm_bwd: both g_logit and g_stack are NULL");
@@ -429,11 +440,15 @@ extern "C" int dr_embed_fm_bwd(const void* ids, int id_bytes, const int64_t* row
   DR_REQUIRE(!stack || aligned16(stack), DR_EALIGN, "dr_embed_fm_bwd: stack not 16-B aligned");
   DR_REQUIRE(!g_stack || aligned16(g_stack), DR_EALIGN, "dr_embed_fm_bwd: g_stack not 16-B aligned");
   DR_REQUIRE(!sum_e || aligned16(sum_e), DR_EALIGN, "dr_embed_fm_bwd: sum_e not 16-B aligned");
+  if (row_stride == 0) row_stride = D;
+  if (lin_stride == 0) lin_stride = 1;
+  DR_REQUIRE(row_stride >= D && row_stride % 4 == 0 && lin_stride >= 1, DR_EINVAL,
+             "dr_embed_fm_bwd: bad strides row=%lld lin=%lld", (long long)row_stride, (long long)lin_stride);
   if (B == 0) return DR_OK;
   EmbedBwdParams p{};
   p.ids = ids; p.rows = rows; p.stack = stack; p.sum_e = sum_e; p.g_logit = g_logit; p.g_stack = g_stack;
   p.B = B; p.S = S; p.D = D; p.grad_table_ptrs = grad_table_ptrs; p.grad_lin_ptrs = grad_lin_ptrs;
-  p.g_bias = g_bias; p.scale = scale;
+  p.g_bias = g_bias; p.scale = scale; p.row_stride = row_stride; p.lin_stride = lin_stride;
   cudaStream_t st = (cudaStream_t)stream;
   DR_DISPATCH_LPR(launch_bwd, p, st);
 }
@@ -447,6 +462,7 @@ extern "C" int dr_gather_fwd(const float* table, int64_t rows, const void* ids, 
   if (n == 0) return DR_OK;
   EmbedFwdParams p{};
   p.single_table = table; p.single_rows = rows; p.ids = ids; p.B = n; p.S = 1; p.D = D; p.out_stack = out;
+  p.row_stride = D; p.lin_stride = 1;
   cudaStream_t st = (cudaStream_t)stream;
   DR_DISPATCH_LPR(launch_fwd, p, st);
 }
@@ -460,7 +476,7 @@ extern "C" int dr_scatter_add(float* grad_table, int64_t rows, const void* ids, 
   if (n == 0) return DR_OK;
   EmbedBwdParams p{};
   p.ids = ids; p.single_rows = rows; p.g_stack = g; p.B = n; p.S = 1; p.D = D; p.single_grad = grad_table;
-  p.scale = scale;
+  p.scale = scale; p.row_stride = D; p.lin_stride = 1;
   cudaStream_t st = (cudaStream_t)stream;
   DR_DISPATCH_LPR(launch_bwd, p, st);
 }

@@ -82,14 +82,14 @@ __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, i
 }
 
 // BCE on logits (mean) + gradient.  loss accumulated with one atomic per CTA.
-__global__ void __launch_bounds__(256) bce_kernel(const float* __restrict__ z, const float* __restrict__ y,
+__global__ void __launch_bounds__(256) bce_kernel(const float* __restrict__ z, const float* __restrict__ z_add, const float* __restrict__ y,
                                                    int64_t B, float invB, float* __restrict__ prob,
                                                    float* __restrict__ loss, float* __restrict__ gz) {
   __shared__ float part[8];
   float acc = 0.f;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += stride) {
-    const float zi = z[i], yi = y[i];
+    const float zi = z[i] + (z_add ? z_add[i] : 0.f), yi = y[i];
     const float pr = 1.f / (1.f + expf(-zi));
     acc += fmaxf(zi, 0.f) - zi * yi + log1pf(expf(-fabsf(zi)));
     if (prob) prob[i] = pr;
@@ -145,14 +145,14 @@ extern "C" int dr_sgd_step(float* p, const float* g, int64_t n, float lr, void* 
   return DR_OK;
 }
 
-extern "C" int dr_bce_logits_fwd_bwd(const float* z, const float* y, int64_t B, float* prob_out,
+extern "C" int dr_bce_logits_fwd_bwd(const float* z, const float* z_add, const float* y, int64_t B, float* prob_out,
                                      float* loss_out, float* gz, void* stream) {
   DR_REQUIRE(z && y && loss_out && B >= 1, DR_EINVAL, "dr_bce_logits_fwd_bwd: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   DR_CUDA_CALL(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
   int64_t ctas = (B + 255) / 256;
   if (ctas > kNumSMs * 4) ctas = kNumSMs * 4;
-  bce_kernel<<<(int)ctas, 256, 0, st>>>(z, y, B, 1.f / (float)B, prob_out, loss_out, gz);
+  bce_kernel<<<(int)ctas, 256, 0, st>>>(z, z_add, y, B, 1.f / (float)B, prob_out, loss_out, gz);
   DR_CUDA_LAUNCH_CHECK("dr_bce_logits_fwd_bwd");
   return DR_OK;
 }

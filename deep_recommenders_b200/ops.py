@@ -69,13 +69,14 @@ class EmbedFM(torch.autograd.Function):
         sum_e = torch.empty((B, D), device=weight.device, dtype=torch.float32) if want_logit else None
         logit = torch.empty((B,), device=weight.device, dtype=torch.float32) if want_logit else None
         tp, lp, rows = meta.pointers(weight, linear)
-        check(lib.dr_embed_fm_fwd(tp.data_ptr(), lp.data_ptr() if (want_logit and linear is not None) else None,
+        has_lin = want_logit and meta.with_linear
+        check(lib.dr_embed_fm_fwd(tp.data_ptr(), lp.data_ptr() if has_lin else None,
                                   rows.data_ptr(), ids.data_ptr(), ids.element_size(),
-                                  _ptr(bias) if want_logit else None, B, S, D,
+                                  _ptr(bias) if want_logit else None, B, S, D, meta.row_stride, meta.lin_stride,
                                   stack.data_ptr(), _ptr(sum_e), _ptr(logit), _stream()), "dr_embed_fm_fwd")
         ctx.meta = meta
         ctx.want_logit = want_logit
-        ctx.has_linear = linear is not None
+        ctx.has_lin = has_lin
         ctx.has_bias = bias is not None
         ctx.save_for_backward(ids, stack, sum_e, weight, linear, bias)
         if want_logit:
@@ -107,11 +108,12 @@ class EmbedFM(torch.autograd.Function):
             gb = torch.zeros_like(bias) if (bias is not None and g_logit is not None) else None
             scale = 1.0
             tp, lp, rows = meta.pointers(gw, gl, cache=False)
+        lin_grad = ctx.has_lin and g_logit is not None
         with torch.no_grad():
             check(lib.dr_embed_fm_bwd(ids.data_ptr(), ids.element_size(), rows.data_ptr(),
                                       stack.data_ptr(), _ptr(sum_e), _ptr(g_logit), _ptr(g_stack),
-                                      B, S, D, tp.data_ptr(),
-                                      lp.data_ptr() if (gl is not None and g_logit is not None) else None,
+                                      B, S, D, meta.row_stride, meta.lin_stride, tp.data_ptr(),
+                                      lp.data_ptr() if lin_grad else None,
                                       _ptr(gb) if g_logit is not None else None, scale, _stream()),
                   "dr_embed_fm_bwd")
         if fused:
@@ -347,16 +349,17 @@ def hard_negative_topk(logits: torch.Tensor, k: int):
     return out_l, out_y, out_i
 
 
-def bce_with_logits(z: torch.Tensor, y: torch.Tensor):
-    """(loss[1], grad_z[B], prob[B]) of mean binary cross-entropy on logits, one kernel."""
+def bce_with_logits(z: torch.Tensor, y: torch.Tensor, z_add: torch.Tensor = None):
+    """(loss[1], grad_z[B], prob[B]) of mean binary cross-entropy on logits z (+ z_add), one kernel."""
     lib = _lib.load()
     z = _f32(z, "logits").reshape(-1)
+    z_add = None if z_add is None else _f32(z_add, "z_add").reshape(-1)
     y = _f32(y, "labels").reshape(-1)
     B = z.numel()
     prob = torch.empty_like(z)
     gz = torch.empty_like(z)
     loss = torch.empty((1,), device=z.device, dtype=torch.float32)
-    check(lib.dr_bce_logits_fwd_bwd(z.data_ptr(), y.data_ptr(), B, prob.data_ptr(), loss.data_ptr(), gz.data_ptr(),
+    check(lib.dr_bce_logits_fwd_bwd(z.data_ptr(), _ptr(z_add), y.data_ptr(), B, prob.data_ptr(), loss.data_ptr(), gz.data_ptr(),
                                     _stream()), "dr_bce_logits_fwd_bwd")
     return loss, gz, prob
 

@@ -1,0 +1,226 @@
+"""Whole-step training drivers for the hot path: forward + backward + optimizer of a DeepFM
+model (reference: examples/train_deepfm_on_movielens_keras.py:38-54 -- compile(BCE, optimizer)
++ fit) as one CUDA-graph replay of hand-written kernels.
+
+`DeepFMTrainStep(model, lr)` takes a `deep_recommenders.keras.models.ranking.DeepFM` and runs
+
+   ids [B,S] -> dr_embed_fm_fwd -> Dense(relu)... -> Dense(1) -> BCE(fm_logit + dnn_logit)
+             -> dr_dense_bwd x L -> dr_embed_fm_bwd (fused sparse SGD, scale = -lr)
+             -> dr_sgd_step on the flat dense-parameter buffer
+
+with every buffer preallocated, so the step is capturable in a CUDA graph (no allocator calls,
+no host sync).  The optimizer is plain SGD: row-sparse for the tables (only the rows a batch
+touches are read-modify-written), dense for the tower.  (The reference examples use Adam; a
+fused sparse Adam is the first "next" item of SURVEY.md section 8f.)
+
+`train_step_host` is the end-to-end entry: ids / labels arrive in (pinned) HOST memory, are
+copied H2D on a side stream one batch ahead (double buffered), and the loss is read back D2H.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+
+from . import _lib, ops
+from ._lib import check
+
+
+class DeepFMTrainStep:
+    def __init__(self, model, batch_size: int, lr: float = 0.01, id_dtype=torch.int64, use_graph: bool = True):
+        self.lib = _lib.load()
+        self.model = model
+        coll = model.embeddings
+        self.coll = coll
+        self.B, self.S, self.D = int(batch_size), coll.num_slots, coll.dim
+        self.lr = float(lr)
+        dev = coll.weight.device
+        if dev.type != "cuda":
+            raise _lib.DeepRecError("DeepFMTrainStep needs the model on a CUDA device (no CPU fallback)")
+        self.dev = dev
+        # make sure the lazily built Dense layers exist, then move the tower into ONE flat buffer
+        layers = list(model._dnn.layers)
+        in_dim = self.S * self.D
+        for l in layers:
+            if not l.built:
+                l.build((self.B, in_dim), device=dev)
+            in_dim = l.units
+        self.layers = layers
+        sizes = []
+        for l in layers:
+            sizes += [l.kernel.numel(), l.bias.numel() if l.bias is not None else 0]
+        total = sum(sizes)
+        self.flat = torch.empty(total, device=dev, dtype=torch.float32)
+        self.gflat = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.w: List[torch.Tensor] = []
+        self.b: List[Optional[torch.Tensor]] = []
+        self.gw: List[torch.Tensor] = []
+        self.gb: List[Optional[torch.Tensor]] = []
+        o = 0
+        with torch.no_grad():
+            for l in layers:
+                n = l.kernel.numel()
+                self.flat[o:o + n].copy_(l.kernel.reshape(-1))
+                l.kernel.data = self.flat[o:o + n].view_as(l.kernel)     # parameters alias the flat buffer
+                self.w.append(l.kernel.data)
+                self.gw.append(self.gflat[o:o + n].view_as(l.kernel))
+                o += n
+                if l.bias is not None:
+                    n = l.bias.numel()
+                    self.flat[o:o + n].copy_(l.bias)
+                    l.bias.data = self.flat[o:o + n]
+                    self.b.append(l.bias.data)
+                    self.gb.append(self.gflat[o:o + n])
+                    o += n
+                else:
+                    self.b.append(None)
+                    self.gb.append(None)
+        B, S, D = self.B, self.S, self.D
+        f = dict(device=dev, dtype=torch.float32)
+        self.ids = torch.zeros((B, S), device=dev, dtype=id_dtype)
+        self.labels = torch.zeros((B,), **f)
+        self.stack = torch.empty((B, S, D), **f)
+        self.sum_e = torch.empty((B, D), **f)
+        self.fm_logit = torch.empty((B,), **f)
+        self.acts = [torch.empty((B, l.units), **f) for l in layers]
+        self.g_acts = [torch.empty((B, l.units), **f) for l in layers]       # dL/d(output of layer i)
+        self.gz_ws = [torch.empty((B, l.units), **f) if l._act != 0 else None for l in layers]
+        self.g_stack = torch.empty((B, S, D), **f)
+        self.loss = torch.zeros((1,), **f)
+        self.prob = torch.empty((B,), **f)
+        self.tp, self.lp, self.rows = coll.pointers(coll.weight, coll.linear)
+        self.graph = None
+        self.use_graph = use_graph
+        self._copy_stream = torch.cuda.Stream(device=dev)
+        self._staged = None
+        self.launches_per_step = None
+
+    # ---- the step, as raw C-ABI calls on the current stream ------------------------------------
+    def _enqueue(self, mark=None):
+        """`mark(label)` (optional) is called after each kernel group; profile_kernels uses it to
+        drop a CUDA event on the launching stream between groups."""
+        lib, st = self.lib, torch.cuda.current_stream().cuda_stream
+        B, S, D = self.B, self.S, self.D
+        c = self.coll
+        mark = mark or (lambda label: None)
+        mark("start")
+        check(lib.dr_embed_fm_fwd(self.tp.data_ptr(), self.lp.data_ptr(), self.rows.data_ptr(), self.ids.data_ptr(),
+                                  self.ids.element_size(), c.bias.data_ptr(), B, S, D, c.row_stride, c.lin_stride,
+                                  self.stack.data_ptr(),
+                                  self.sum_e.data_ptr(), self.fm_logit.data_ptr(), st), "dr_embed_fm_fwd")
+        mark("embed_fm_fwd")
+        x = self.stack
+        K = S * D
+        for i, l in enumerate(self.layers):
+            check(lib.dr_dense_fwd(x.data_ptr(), self.w[i].data_ptr(), ops._ptr(self.b[i]), B, K, l.units, l._act,
+                                   self.acts[i].data_ptr(), st), "dr_dense_fwd")
+            x, K = self.acts[i], l.units
+            mark(f"dense_fwd_{i}")
+        gz = self.g_acts[-1]                                   # [B,1]: dL/dlogit
+        check(lib.dr_bce_logits_fwd_bwd(self.acts[-1].data_ptr(), self.fm_logit.data_ptr(), self.labels.data_ptr(), B,
+                                        self.prob.data_ptr(), self.loss.data_ptr(), gz.data_ptr(), st), "dr_bce")
+        mark("bce")
+        for i in range(len(self.layers) - 1, -1, -1):
+            l = self.layers[i]
+            xin = self.stack if i == 0 else self.acts[i - 1]
+            Kin = S * D if i == 0 else self.layers[i - 1].units
+            gx = self.g_stack if i == 0 else self.g_acts[i - 1]
+            check(lib.dr_dense_bwd(xin.data_ptr(), self.w[i].data_ptr(), self.acts[i].data_ptr(),
+                                   self.g_acts[i].data_ptr(), B, Kin, l.units, l._act, ops._ptr(self.gz_ws[i]),
+                                   gx.data_ptr(), self.gw[i].data_ptr(), ops._ptr(self.gb[i]), st), "dr_dense_bwd")
+            mark(f"dense_bwd_{i}")
+        check(lib.dr_embed_fm_bwd(self.ids.data_ptr(), self.ids.element_size(), self.rows.data_ptr(),
+                                  self.stack.data_ptr(), self.sum_e.data_ptr(), gz.data_ptr(), self.g_stack.data_ptr(),
+                                  B, S, D, c.row_stride, c.lin_stride, self.tp.data_ptr(), self.lp.data_ptr(),
+                                  c.bias.data_ptr(), -self.lr, st),
+              "dr_embed_fm_bwd")
+        mark("embed_fm_bwd")
+        check(lib.dr_sgd_step(self.flat.data_ptr(), self.gflat.data_ptr(), self.flat.numel(), self.lr, st), "dr_sgd_step")
+        mark("sgd")
+
+    def profile_kernels(self, ids_pool, labels_pool, iters: int = 10):
+        """Eager (non-graph) passes with a CUDA event on the launching stream between kernel groups.
+        Returns ({"embed_fm_fwd_ms": ...}, {label: mean ms}) -- the live per-kernel timing bench.py
+        reports in `roofline` and `kernel_ms`."""
+        sums, count = {}, 0
+        for it in range(iters + 2):
+            self.ids.copy_(ids_pool[it % len(ids_pool)], non_blocking=True)
+            self.labels.copy_(labels_pool[it % len(labels_pool)].reshape(-1), non_blocking=True)
+            evs = []
+
+            def mark(label):
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                evs.append((label, e))
+
+            self._enqueue(mark)
+            torch.cuda.synchronize()
+            if it < 2:
+                continue
+            count += 1
+            for (l0, e0), (l1, e1) in zip(evs[:-1], evs[1:]):
+                sums[l1] = sums.get(l1, 0.0) + e0.elapsed_time(e1)
+        shares = {k: v / count for k, v in sums.items()}
+        return {"embed_fm_fwd_ms": shares["embed_fm_fwd"]}, shares
+
+    def capture(self):
+        """Warm up (sets kernel attributes) then record the step into a CUDA graph."""
+        n0 = _lib.launch_count()
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._enqueue()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.launches_per_step = _lib.launch_count() - n0
+        if self.use_graph:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue()
+            self.graph = g
+        return self
+
+    def run(self):
+        """One step on whatever is in self.ids / self.labels (device resident)."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._enqueue()
+
+    def step(self, ids: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        """Device-resident inputs: copy into the static buffers (D2D) and run. Returns loss[1]."""
+        self.ids.copy_(ids, non_blocking=True)
+        self.labels.copy_(labels.reshape(-1), non_blocking=True)
+        self.run()
+        return self.loss
+
+    # ---- end-to-end: host buffers in, loss out ---------------------------------------------------
+    def stage_host(self, ids_host: torch.Tensor, labels_host: torch.Tensor):
+        """Start the H2D copy of the NEXT batch on the copy stream into the spare device buffers."""
+        if not hasattr(self, "_spare"):
+            self._spare = (torch.empty_like(self.ids), torch.empty_like(self.labels))
+        with torch.cuda.stream(self._copy_stream):
+            self._spare[0].copy_(ids_host, non_blocking=True)
+            self._spare[1].copy_(labels_host.reshape(-1), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        self._staged = ev
+
+    def train_step_host(self, ids_host, labels_host, next_ids_host=None, next_labels_host=None) -> float:
+        """Public end-to-end step.  ids/labels are HOST tensors (pinned for async copies).  If the
+        caller passes the next batch too, its H2D copy overlaps this step's kernels."""
+        cur = torch.cuda.current_stream()
+        if self._staged is None:
+            self.stage_host(ids_host, labels_host)
+        cur.wait_event(self._staged)
+        # swap staged buffers into the static ones the graph reads (D2D, 13.6 MB at C2)
+        self.ids.copy_(self._spare[0], non_blocking=True)
+        self.labels.copy_(self._spare[1], non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(cur)
+        self._staged = None
+        if next_ids_host is not None:
+            self._copy_stream.wait_event(done)
+            self.stage_host(next_ids_host, next_labels_host)
+        self.run()
+        return float(self.loss.item())          # D2H read of the step's result (synchronises)

@@ -50,10 +50,13 @@ uint64_t dr_launch_count(void);
  *   replaces: keras/models/ranking/fm.py:23-37,54-63 ; deepfm.py:36-46 (DenseFeatures per
  *             column -> tf.stack -> FM.call) ; estimator/models/feature_interaction/
  *             fm.py:10-26,41-56.
- *   table_ptrs[S] : device array of S device pointers, table s is [rows[s], D] fp32,
- *                   every base 16-B aligned.  D % 4 == 0, 4 <= D <= 128.
- *   lin_ptrs[S]   : device array of S device pointers to [rows[s]] fp32 first-order
- *                   weights; NULL = no first-order term.
+ *   table_ptrs[S] : device array of S device pointers, table s is [rows[s], D] fp32 with
+ *                   row_stride floats between rows (0 = D; >= D, multiple of 4), every row
+ *                   base 16-B aligned.  D % 4 == 0, 4 <= D <= 128.
+ *   lin_ptrs[S]   : device array of S device pointers to the first-order weights, weight of
+ *                   id i at lin_ptrs[s][i * lin_stride] (0 = 1); NULL = no first-order term.
+ *                   The strides let the host co-locate a row's first-order weight with its
+ *                   embedding vector (row = [D floats | w | pad]) so one DRAM page serves both.
  *   rows[S]       : device int64.
  *   ids           : [B, S] int64 / int32 (id_bytes).
  *   bias          : device [1] or NULL.
@@ -64,7 +67,7 @@ uint64_t dr_launch_count(void);
  * ------------------------------------------------------------------------------------- */
 int dr_embed_fm_fwd(const float* const* table_ptrs, const float* const* lin_ptrs,
                     const int64_t* rows, const void* ids, int id_bytes, const float* bias,
-                    int64_t B, int S, int D,
+                    int64_t B, int S, int D, int64_t row_stride, int64_t lin_stride,
                     float* out_stack, float* out_sum, float* out_logit, void* stream);
 
 /* Backward of the above fused with the sparse update ("IndexedSlices" scatter-add):
@@ -80,7 +83,7 @@ int dr_embed_fm_fwd(const float* const* table_ptrs, const float* const* lin_ptrs
 int dr_embed_fm_bwd(const void* ids, int id_bytes, const int64_t* rows,
                     const float* stack, const float* sum_e,
                     const float* g_logit, const float* g_stack,
-                    int64_t B, int S, int D,
+                    int64_t B, int S, int D, int64_t row_stride, int64_t lin_stride,
                     float* const* grad_table_ptrs, float* const* grad_lin_ptrs, float* g_bias,
                     float scale, void* stream);
 
@@ -193,10 +196,11 @@ int dr_unpermute_rows(const float* in, const int32_t* perm, int64_t n, int D, fl
 /* Fused SGD for dense parameters: p -= lr * g  (n elements). */
 int dr_sgd_step(float* p, const float* g, int64_t n, float lr, void* stream);
 /* Binary cross-entropy on logits, mean over B (tf.keras.losses.binary_crossentropy on
- * sigmoid outputs == this on logits), and its gradient wrt the logits:
+ * sigmoid outputs == this on logits), and its gradient wrt the logits.  The logit is
+ * z[b] + z_add[b] (z_add may be NULL): DeepFM's  fm_logit + dnn_logit  (deepfm.py:46-47).
  *   loss[0] = mean_b( max(z,0) - z*y + log1p(exp(-|z|)) ) ; gz[b] = (sigmoid(z)-y)/B.
- *   prob_out [B] (sigmoid) may be NULL.                                                   */
-int dr_bce_logits_fwd_bwd(const float* z, const float* y, int64_t B,
+ *   prob_out [B] (sigmoid) and gz may be NULL.                                            */
+int dr_bce_logits_fwd_bwd(const float* z, const float* z_add, const float* y, int64_t B,
                           float* prob_out, float* loss_out, float* gz, void* stream);
 
 /* Developer hook (not reference-facing): set a kernel tuning knob by name, e.g.

@@ -29,13 +29,13 @@ def make_problem(B, rows, D, seed=0, oov_frac=0.0, id_dtype=np.int64, zipf=False
     return tables, lins, bias, ids.astype(id_dtype)
 
 
-def to_collection(tables, lins, bias, sparse_lr=None):
+def to_collection(tables, lins, bias, sparse_lr=None, layout="fused"):
     from deep_recommenders_b200.embedding import EmbeddingCollection
     coll = EmbeddingCollection([t.shape[0] for t in tables], tables[0].shape[1], device="cuda", init="empty",
-                               sparse_lr=sparse_lr)
+                               sparse_lr=sparse_lr, layout=layout)
     with torch.no_grad():
-        coll.weight.copy_(torch.from_numpy(np.concatenate(tables, 0)))
-        coll.linear.copy_(torch.from_numpy(np.concatenate(lins, 0)))
+        coll.emb_view().copy_(torch.from_numpy(np.concatenate(tables, 0)))
+        coll.lin_view().copy_(torch.from_numpy(np.concatenate(lins, 0)))
         coll.bias.fill_(float(bias))
     return coll
 
@@ -62,11 +62,12 @@ CASES = [
 
 
 @pytest.mark.parametrize("B,rows,D", CASES)
-@pytest.mark.parametrize("id_dtype", [np.int64, np.int32])
-def test_forward_parity(B, rows, D, id_dtype):
+@pytest.mark.parametrize("id_dtype,layout", [(np.int64, "fused"), (np.int32, "fused"), (np.int64, "split")])
+def test_forward_parity(B, rows, D, id_dtype, layout):
     tables, lins, bias, ids = make_problem(B, rows, D, seed=B + D, oov_frac=0.1, id_dtype=id_dtype)
-    coll = to_collection(tables, lins, bias)
-    stack, logit = coll(torch.from_numpy(ids).cuda())
+    coll = to_collection(tables, lins, bias, layout=layout)
+    with torch.no_grad():
+        stack, logit = coll(torch.from_numpy(ids).cuda())
     torch.cuda.synchronize()
     ref_stack = R.stack_embeddings(tables, ids)
     # a gather is a copy: bit-exact
@@ -83,7 +84,8 @@ def test_forward_parity(B, rows, D, id_dtype):
 def test_forward_empty_batch():
     tables, lins, bias, ids = make_problem(4, [10, 10], 16)
     coll = to_collection(tables, lins, bias)
-    stack, logit = coll(torch.zeros((0, 2), dtype=torch.int64, device="cuda"))
+    with torch.no_grad():
+        stack, logit = coll(torch.zeros((0, 2), dtype=torch.int64, device="cuda"))
     assert stack.shape == (0, 2, 16) and logit.shape == (0,)
 
 
@@ -91,7 +93,8 @@ def test_all_oov_gives_bias_only():
     tables, lins, bias, _ = make_problem(8, [10, 10, 10], 16)
     coll = to_collection(tables, lins, bias)
     ids = torch.full((8, 3), -1, dtype=torch.int64, device="cuda")
-    stack, logit = coll(ids)
+    with torch.no_grad():
+        stack, logit = coll(ids)
     assert float(stack.abs().max()) == 0.0
     assert np.allclose(logit.cpu().numpy(), float(bias))
 
@@ -122,13 +125,13 @@ BWD_CASES = [
 
 
 @pytest.mark.parametrize("B,rows,D", BWD_CASES)
-@pytest.mark.parametrize("agg", [1, 0])
-def test_backward_parity(B, rows, D, agg):
+@pytest.mark.parametrize("agg,layout", [(1, "fused"), (0, "fused"), (1, "split")])
+def test_backward_parity(B, rows, D, agg, layout):
     from deep_recommenders_b200 import _lib
     _lib.tune("embed_bwd_agg", agg)
     try:
         tables, lins, bias, ids = make_problem(B, rows, D, seed=7 * B + D, oov_frac=0.05)
-        coll = to_collection(tables, lins, bias)
+        coll = to_collection(tables, lins, bias, layout=layout)
         rng = np.random.default_rng(1)
         g_logit = rng.standard_normal(B).astype(np.float32)
         g_stack = rng.standard_normal((B, len(rows), D)).astype(np.float32)
@@ -142,15 +145,18 @@ def test_backward_parity(B, rows, D, agg):
         st64 = ref_stack.astype(np.float64)
         absdE = np.abs(g_logit)[:, None, None] * (np.abs(st64.sum(1, keepdims=True)) + np.abs(st64)) + np.abs(g_stack)
         scale_t, _, _ = R.embed_fm_grad([t.shape[0] for t in tables], ids, ref_stack * 0, None, absdE, np.float64)
-        gw = coll.weight.grad.cpu().numpy().astype(np.float64)
+        cgw, cgl, cgb = coll.grads()
+        gw = cgw.cpu().numpy().astype(np.float64)
         ref = np.concatenate(gts, 0)
         sc = np.concatenate(scale_t, 0)
         assert (np.abs(gw - ref) <= 1e-5 * sc + 1e-7).all(), np.abs(gw - ref).max()
-        gl = coll.linear.grad.cpu().numpy().astype(np.float64)
+        gl = cgl.cpu().numpy().astype(np.float64)
         refl = np.concatenate(gls, 0)
         _, scl, _ = R.embed_fm_grad([t.shape[0] for t in tables], ids, ref_stack, np.abs(g_logit), None, np.float64)
         assert (np.abs(gl - refl) <= 1e-5 * np.concatenate(scl, 0) + 1e-7).all()
-        assert abs(float(coll.bias.grad) - gb) <= 1e-5 * np.abs(g_logit).sum() + 1e-7
+        assert abs(float(cgb) - gb) <= 1e-5 * np.abs(g_logit).sum() + 1e-7
+        if layout == "fused":
+            assert float(coll.weight.grad[:, D + 1:].abs().max()) == 0.0      # pad lanes untouched
     finally:
         _lib.tune("embed_bwd_agg", 1)
 
@@ -165,11 +171,12 @@ def test_backward_same_id_1000_times():
     torch.cuda.synchronize()
     ref_stack = R.stack_embeddings(tables, ids)
     gts, gls, gb = R.embed_fm_grad([100, 100], ids, ref_stack, np.ones(1000), None, np.float64)
-    gw = coll.weight.grad.cpu().numpy()
+    cgw, cgl, cgb = coll.grads()
+    gw = cgw.cpu().numpy()
     ref = np.concatenate(gts, 0)
     assert np.allclose(gw, ref, rtol=1e-5, atol=1e-5 * np.abs(ref).max())
-    assert np.allclose(coll.linear.grad.cpu().numpy(), np.concatenate(gls, 0), rtol=1e-6)
-    assert abs(float(coll.bias.grad) - 1000.0) < 1e-3
+    assert np.allclose(cgl.cpu().numpy(), np.concatenate(gls, 0), rtol=1e-6)
+    assert abs(float(cgb) - 1000.0) < 1e-3
 
 
 def test_fused_sparse_sgd_equals_dense_sgd():
@@ -184,12 +191,13 @@ def test_fused_sparse_sgd_equals_dense_sgd():
         ((logit * gvec).sum() + 0.5 * (stack * stack).sum()).backward()
     torch.cuda.synchronize()
     with torch.no_grad():
-        want_w = dense.weight - lr * dense.weight.grad
-        want_l = dense.linear - lr * dense.linear.grad
-        want_b = dense.bias - lr * dense.bias.grad
+        gw, gl, gb = dense.grads()
+        want_w = dense.emb_view() - lr * gw
+        want_l = dense.lin_view() - lr * gl
+        want_b = dense.bias - lr * gb
     assert fused.weight.grad is None
-    assert torch.allclose(fused.weight, want_w, rtol=1e-5, atol=1e-6)
-    assert torch.allclose(fused.linear, want_l, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(fused.emb_view(), want_w, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(fused.lin_view(), want_l, rtol=1e-5, atol=1e-6)
     assert torch.allclose(fused.bias, want_b, rtol=1e-5, atol=1e-6)
 
 
@@ -221,16 +229,18 @@ def test_full_size_c2_properties():
     B, S, D, rows = 65536, 26, 16, 1_000_000
     coll = EmbeddingCollection([rows] * S, D, device="cuda", seed=1)
     with torch.no_grad():
-        coll.linear.normal_(0, 0.1)
+        coll.lin_view().normal_(0, 0.1)
         coll.bias.fill_(0.25)
     gen = torch.Generator(device="cuda").manual_seed(0)
     ids = torch.randint(0, rows, (B, S), device="cuda", generator=gen)
-    stack, logit = coll(ids)
+    with torch.no_grad():
+        stack, logit = coll(ids)
     offs = (torch.arange(S, device="cuda") * rows).view(1, S)
     flat = (ids + offs).view(-1)
-    want = coll.weight.detach().index_select(0, flat).view(B, S, D)
+    picked = coll.weight.detach().index_select(0, flat)
+    want = picked[:, :D].contiguous().view(B, S, D)
     assert torch.equal(stack, want)
-    lin = coll.linear.detach().index_select(0, flat).view(B, S).double().sum(1)
+    lin = picked[:, D].view(B, S).double().sum(1)
     st = want.double()
     fm64 = 0.5 * ((st.sum(1) ** 2).sum(1) - (st ** 2).sum((1, 2)))
     ref = lin + fm64 + 0.25
@@ -244,6 +254,6 @@ def test_full_size_c2_properties():
     tp, lp, rws = coll.pointers(gw, None, cache=False)
     from deep_recommenders_b200 import _lib
     _lib.check(_lib.load().dr_embed_fm_bwd(ids.data_ptr(), 8, rws.data_ptr(), None, None, None, g.data_ptr(),
-                                           B, S, D, tp.data_ptr(), None, None, 1.0,
+                                           B, S, D, coll.row_stride, coll.lin_stride, tp.data_ptr(), None, None, 1.0,
                                            torch.cuda.current_stream().cuda_stream), "bwd")
     assert float(gw.sum()) == float(B * S * D)

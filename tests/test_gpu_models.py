@@ -35,7 +35,7 @@ def test_deepfm_forward_matches_oracle():
     model = DeepFM([fc.indicator_column(c) for c in cols], [fc.embedding_column(c, 16) for c in cols],
                    dnn_units_size=[64, 32], seed=3, device="cuda")
     with torch.no_grad():
-        model.embeddings.linear.normal_(0, 0.1)
+        model.embeddings.lin_view().normal_(0, 0.1)
         model.embeddings.bias.fill_(0.1)
     rng = np.random.default_rng(0)
     ids = np.stack([rng.integers(-1, 50 + i, 300) for i in range(6)], axis=1).astype(np.int64)

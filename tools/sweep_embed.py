@@ -43,7 +43,7 @@ def main():
     for D, idb in ((16, 8), (16, 4), (32, 8)):
         coll = EmbeddingCollection([rows] * S, D, device="cuda", seed=1)
         with torch.no_grad():
-            coll.linear.normal_(0, 0.1)
+            coll.lin_view().normal_(0, 0.1)
         gen = torch.Generator(device="cuda").manual_seed(0)
         NP = 6
         ids_pool = [torch.randint(0, rows, (B, S), device="cuda", generator=gen,
@@ -59,7 +59,7 @@ def main():
         def fwd(i):
             k = i % NP
             _lib.check(lib.dr_embed_fm_fwd(tp.data_ptr(), lp.data_ptr(), rws.data_ptr(), ids_pool[k].data_ptr(), idb,
-                                           coll.bias.data_ptr(), B, S, D, stacks[k].data_ptr(), sums[k].data_ptr(),
+                                           coll.bias.data_ptr(), B, S, D, coll.row_stride, coll.lin_stride, stacks[k].data_ptr(), sums[k].data_ptr(),
                                            logits[k].data_ptr(), st), "fwd")
 
         gl = torch.randn(B, device="cuda") * 1e-3
@@ -68,7 +68,7 @@ def main():
         def bwd(i):
             k = i % NP
             _lib.check(lib.dr_embed_fm_bwd(ids_pool[k].data_ptr(), idb, rws.data_ptr(), stacks[k].data_ptr(),
-                                           sums[k].data_ptr(), gl.data_ptr(), gs[k].data_ptr(), B, S, D,
+                                           sums[k].data_ptr(), gl.data_ptr(), gs[k].data_ptr(), B, S, D, coll.row_stride, coll.lin_stride,
                                            tp.data_ptr(), lp.data_ptr(), coll.bias.data_ptr(), -1e-6, st), "bwd")
 
         for block, unroll, cps in itertools.product((128, 256, 512), (2, 4, 8, 13, 26), (0,)):
