@@ -42,7 +42,7 @@ _SIGS = {
     "dr_inbatch_softmax_bwd": [_p, _p, _p, _p, _p, _f, _i64, _i64, _i, _p, _p, _p, _p, _p],
     "dr_scores_fwd": [_p, _p, _p, _p, _i64, _i64, _i, _p, _p],
     "dr_hard_negative_topk": [_p, _i64, _i64, _i, _p, _p, _p, _p],
-    "dr_shard_bucket_ids": [_p, _i, _i64, _i, _p, _p, _i, _p, _p, _p, _p, _p],
+    "dr_shard_bucket_ids": [_p, _i, _i64, _i, _p, _p, _i, _i64, _p, _p, _p, _p, _p],
     "dr_permute_rows": [_p, _p, _i64, _i, _p, _p],
     "dr_unpermute_rows": [_p, _p, _i64, _i, _p, _p],
     "dr_sgd_step": [_p, _p, _i64, _f, _p],

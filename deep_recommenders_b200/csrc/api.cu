@@ -38,6 +38,14 @@ extern "C" int dr_tune_set(const char* key, int value) {
   else if (!strcmp(key, "embed_bwd_agg")) g_tune_embed_bwd_agg = value;
   else if (!strcmp(key, "gemm_variant")) g_tune_gemm_variant = value;
   else if (!strcmp(key, "gemm_splitk")) g_tune_gemm_splitk = value;
+  else if (!strcmp(key, "l2_fetch_granularity")) {
+    // device-wide hint: how many bytes L2 fetches from HBM around a missing 32-B sector (32/64/128)
+    cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value);
+    if (e != cudaSuccess) {
+      set_error("dr_tune_set: cudaDeviceSetLimit(MaxL2FetchGranularity, %d): %s", value, cudaGetErrorString(e));
+      return (int)e;
+    }
+  }
   else {
     set_error("dr_tune_set: unknown key '%s'", key);
     return DR_EINVAL;

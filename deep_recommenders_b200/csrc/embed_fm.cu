@@ -252,9 +252,10 @@ __global__ void __launch_bounds__(512) embed_fm_bwd_kernel(const EmbedBwdParams 
               ok ? (((unsigned long long)id << 5) | (unsigned)c) : (0x8000000000000000ull | (unsigned)lane);
           const unsigned peers = __match_any_sync(0xffffffffu, key);
           if (!__all_sync(0xffffffffu, peers == (1u << lane))) {
+            const float4 d0 = d;   // shuffle the ORIGINAL contributions (d is being accumulated)
 #pragma unroll
             for (int k = 1; k < G; ++k) {
-              const float4 o = f4_shfl_down(d, k * LPR);
+              const float4 o = f4_shfl_down(d0, k * LPR);
               const int src = lane + k * LPR;
               if (src < 32 && ((peers >> src) & 1u)) d = f4_add(d, o);
             }
@@ -410,6 +411,7 @@ extern "C" int dr_embed_fm_fwd(const float* const* table_ptrs, const float* cons
                                int64_t B, int S, int D, int64_t row_stride, int64_t lin_stride,
                                float* out_stack, float* out_sum, float* out_logit, void* stream) {
   if (int rc = check_dims("dr_embed_fm_fwd", B, S, D, id_bytes)) return rc;
+  if (B == 0) return DR_OK;
   DR_REQUIRE(table_ptrs && rows && ids, DR_EINVAL, "dr_embed_fm_fwd: null table_ptrs/rows/ids");
   DR_REQUIRE(out_stack || out_logit || out_sum, DR_EINVAL, "dr_embed_fm_fwd: no output requested");
   if (row_stride == 0) row_stride = D;
@@ -434,6 +436,7 @@ extern "C" int dr_embed_fm_bwd(const void* ids, int id_bytes, const int64_t* row
                                float* const* grad_table_ptrs, float* const* grad_lin_ptrs, float* g_bias,
                                float scale, void* stream) {
   if (int rc = check_dims("dr_embed_fm_bwd", B, S, D, id_bytes)) return rc;
+  if (B == 0) return DR_OK;
   DR_REQUIRE(ids && rows && grad_table_ptrs, DR_EINVAL, "dr_embed_fm_bwd: null ids/rows/grad_table_ptrs");
   DR_REQUIRE(g_logit || g_stack, DR_EINVAL, "dr_embed_fm_bwd: both g_logit and g_stack are NULL");
   DR_REQUIRE(!g_logit || stack, DR_EINVAL, "dr_embed_fm_bwd: g_logit given but stack is NULL");
@@ -456,6 +459,7 @@ extern "C" int dr_embed_fm_bwd(const void* ids, int id_bytes, const int64_t* row
 extern "C" int dr_gather_fwd(const float* table, int64_t rows, const void* ids, int id_bytes, int64_t n,
                              int D, float* out, void* stream) {
   if (int rc = check_dims("dr_gather_fwd", n, 1, D, id_bytes)) return rc;
+  if (n == 0) return DR_OK;
   DR_REQUIRE(table && ids && out, DR_EINVAL, "dr_gather_fwd: null pointer");
   DR_REQUIRE(rows >= 0, DR_EINVAL, "dr_gather_fwd: rows < 0");
   DR_REQUIRE(aligned16(table) && aligned16(out), DR_EALIGN, "dr_gather_fwd: table/out not 16-B aligned");
@@ -470,6 +474,7 @@ extern "C" int dr_gather_fwd(const float* table, int64_t rows, const void* ids, 
 extern "C" int dr_scatter_add(float* grad_table, int64_t rows, const void* ids, int id_bytes, int64_t n,
                               int D, const float* g, float scale, void* stream) {
   if (int rc = check_dims("dr_scatter_add", n, 1, D, id_bytes)) return rc;
+  if (n == 0) return DR_OK;
   DR_REQUIRE(grad_table && ids && g, DR_EINVAL, "dr_scatter_add: null pointer");
   DR_REQUIRE(rows >= 0, DR_EINVAL, "dr_scatter_add: rows < 0");
   DR_REQUIRE(aligned16(grad_table) && aligned16(g), DR_EALIGN, "dr_scatter_add: table/g not 16-B aligned");

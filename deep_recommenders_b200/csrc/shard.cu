@@ -18,32 +18,17 @@ __device__ __forceinline__ int64_t global_row(const IdT* __restrict__ ids, int64
   return __ldg(slot_offsets + s) + id;
 }
 
+// One pass: every flat lookup i claims a slot in its owner's padded segment of the send buffer
+// (segment g = [g*cap, (g+1)*cap)), writes its local row id there and remembers the slot in
+// inv[i].  Slots are claimed with one atomic per distinct owner per warp (match.any aggregation).
+// A segment that would exceed cap raises the overflow flag (the lookup then reads slot -1 = zero row).
 template <typename IdT>
-__global__ void __launch_bounds__(256) shard_hist_kernel(const IdT* __restrict__ ids, int64_t n, int S,
-                                                          const int64_t* __restrict__ slot_offsets,
-                                                          const int64_t* __restrict__ rows, int G,
-                                                          unsigned long long* __restrict__ counts) {
-  __shared__ unsigned int h[64];
-  if (threadIdx.x < 64) h[threadIdx.x] = 0;
-  __syncthreads();
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const int64_t r = global_row(ids, i, S, slot_offsets, rows);
-    const int owner = r < 0 ? 0 : (int)(r % G);
-    atomicAdd(&h[owner], 1u);
-  }
-  __syncthreads();
-  if (threadIdx.x < G && h[threadIdx.x]) atomicAdd(counts + threadIdx.x, (unsigned long long)h[threadIdx.x]);
-}
-
-template <typename IdT>
-__global__ void __launch_bounds__(256) shard_scatter_kernel(const IdT* __restrict__ ids, int64_t n, int S,
-                                                             const int64_t* __restrict__ slot_offsets,
-                                                             const int64_t* __restrict__ rows, int G,
-                                                             const unsigned long long* __restrict__ counts,
-                                                             unsigned long long* __restrict__ cursor,
-                                                             int32_t* __restrict__ perm,
-                                                             int64_t* __restrict__ local_ids) {
+__global__ void __launch_bounds__(256) shard_bucket_kernel(const IdT* __restrict__ ids, int64_t n, int S,
+                                                            const int64_t* __restrict__ slot_offsets,
+                                                            const int64_t* __restrict__ rows, int G, int64_t cap,
+                                                            unsigned long long* __restrict__ cursor,
+                                                            int64_t* __restrict__ send_ids, int32_t* __restrict__ inv,
+                                                            int32_t* __restrict__ overflow) {
   const int lane = threadIdx.x & 31;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t nround = (n + stride - 1) / stride;
@@ -56,18 +41,21 @@ __global__ void __launch_bounds__(256) shard_scatter_kernel(const IdT* __restric
       r = global_row(ids, i, S, slot_offsets, rows);
       owner = r < 0 ? 0 : (int)(r % G);
     }
-    // warp-aggregated slot claim: one atomic per distinct owner per warp
     const unsigned peers = __match_any_sync(0xffffffffu, live ? owner : (64 + lane));
     unsigned long long base = 0;
     const int leader = __ffs(peers) - 1;
     if (live && lane == leader) base = atomicAdd(cursor + owner, (unsigned long long)__popc(peers));
     base = __shfl_sync(0xffffffffu, base, leader);
     if (live) {
-      unsigned long long start = 0;
-      for (int g = 0; g < owner; ++g) start += counts[g];
-      const unsigned long long pos = start + base + (unsigned long long)__popc(peers & ((1u << lane) - 1u));
-      perm[pos] = (int32_t)i;
-      local_ids[pos] = r < 0 ? -1 : r / G;
+      const unsigned long long pos = base + (unsigned long long)__popc(peers & ((1u << lane) - 1u));
+      if (pos < (unsigned long long)cap) {
+        const int64_t slot = (int64_t)owner * cap + (int64_t)pos;
+        send_ids[slot] = r < 0 ? -1 : r / G;
+        inv[i] = (int32_t)slot;
+      } else {
+        inv[i] = -1;
+        atomicExch(overflow, 1);
+      }
     }
   }
 }
@@ -84,6 +72,7 @@ __global__ void __launch_bounds__(256) permute_rows_kernel(const float* __restri
     const int64_t i = f / chunks;
     const int c = (int)(f % chunks);
     const int64_t j = __ldg(perm + i);
+    if (j < 0) continue;
     if (UNPERMUTE) stg4(out + (size_t)j * D + c * 4, ldg_nc_na(in + (size_t)i * D + c * 4));
     else stg4(out + (size_t)i * D + c * 4, ldg_nc_na(in + (size_t)j * D + c * 4));
   }
@@ -93,36 +82,32 @@ __global__ void __launch_bounds__(256) permute_rows_kernel(const float* __restri
 
 using namespace dr;
 
-// Full form used by the sharded collection (slot offsets + per-slot row counts).
 extern "C" int dr_shard_bucket_ids(const void* ids, int id_bytes, int64_t n, int S,
-                                      const int64_t* slot_offsets, const int64_t* rows, int G,
-                                      int64_t* send_counts, int64_t* cursor_ws, int32_t* perm,
-                                      int64_t* local_ids, void* stream) {
-  DR_REQUIRE(ids && send_counts && cursor_ws && perm && local_ids, DR_EINVAL, "dr_shard_bucket_ids: null pointer");
-  DR_REQUIRE(n >= 0 && n < (int64_t)1 << 31, DR_EINVAL, "dr_shard_bucket_ids: n=%lld out of range", (long long)n);
+                                   const int64_t* slot_offsets, const int64_t* rows, int G, int64_t cap,
+                                   int64_t* send_counts, int64_t* send_ids, int32_t* inv, int32_t* overflow,
+                                   void* stream) {
+  DR_REQUIRE(ids && send_counts && send_ids && inv && overflow, DR_EINVAL, "dr_shard_bucket_ids: null pointer");
+  DR_REQUIRE(n >= 0, DR_EINVAL, "dr_shard_bucket_ids: n=%lld < 0", (long long)n);
   DR_REQUIRE(G >= 1 && G <= 64, DR_EINVAL, "dr_shard_bucket_ids: G=%d outside [1,64]", G);
   DR_REQUIRE(S >= 1, DR_EINVAL, "dr_shard_bucket_ids: S=%d", S);
+  DR_REQUIRE(cap >= 1 && (int64_t)G * cap < ((int64_t)1 << 31), DR_EINVAL,
+             "dr_shard_bucket_ids: G*cap=%lld must fit int32", (long long)((int64_t)G * cap));
   DR_REQUIRE(id_bytes == 8 || id_bytes == 4, DR_EINVAL, "dr_shard_bucket_ids: id_bytes=%d", id_bytes);
   cudaStream_t st = (cudaStream_t)stream;
   DR_CUDA_CALL(cudaMemsetAsync(send_counts, 0, sizeof(int64_t) * G, st));
-  DR_CUDA_CALL(cudaMemsetAsync(cursor_ws, 0, sizeof(int64_t) * G, st));
+  DR_CUDA_CALL(cudaMemsetAsync(overflow, 0, sizeof(int32_t), st));
+  DR_CUDA_CALL(cudaMemsetAsync(send_ids, 0xFF, sizeof(int64_t) * (size_t)G * cap, st));   // all -1
   if (n == 0) return DR_OK;
   int64_t ctas = (n + 255) / 256;
   if (ctas > kNumSMs * 8) ctas = kNumSMs * 8;
-  auto* cnt = reinterpret_cast<unsigned long long*>(send_counts);
-  auto* cur = reinterpret_cast<unsigned long long*>(cursor_ws);
-  if (id_bytes == 8) {
-    shard_hist_kernel<int64_t><<<(unsigned)ctas, 256, 0, st>>>((const int64_t*)ids, n, S, slot_offsets, rows, G, cnt);
-    DR_CUDA_LAUNCH_CHECK("shard_hist");
-    shard_scatter_kernel<int64_t><<<(unsigned)ctas, 256, 0, st>>>((const int64_t*)ids, n, S, slot_offsets, rows, G,
-                                                                   cnt, cur, perm, local_ids);
-  } else {
-    shard_hist_kernel<int32_t><<<(unsigned)ctas, 256, 0, st>>>((const int32_t*)ids, n, S, slot_offsets, rows, G, cnt);
-    DR_CUDA_LAUNCH_CHECK("shard_hist");
-    shard_scatter_kernel<int32_t><<<(unsigned)ctas, 256, 0, st>>>((const int32_t*)ids, n, S, slot_offsets, rows, G,
-                                                                   cnt, cur, perm, local_ids);
-  }
-  DR_CUDA_LAUNCH_CHECK("shard_scatter");
+  auto* cur = reinterpret_cast<unsigned long long*>(send_counts);
+  if (id_bytes == 8)
+    shard_bucket_kernel<int64_t><<<(unsigned)ctas, 256, 0, st>>>((const int64_t*)ids, n, S, slot_offsets, rows, G, cap,
+                                                                  cur, send_ids, inv, overflow);
+  else
+    shard_bucket_kernel<int32_t><<<(unsigned)ctas, 256, 0, st>>>((const int32_t*)ids, n, S, slot_offsets, rows, G, cap,
+                                                                  cur, send_ids, inv, overflow);
+  DR_CUDA_LAUNCH_CHECK("shard_bucket");
   return DR_OK;
 }
 

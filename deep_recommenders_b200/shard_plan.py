@@ -1,0 +1,37 @@
+"""Pure-Python partition arithmetic of the row-sharded embedding tables.
+
+The reference is single-process; this is the B200 design: all S tables of a model share one
+global row space (row = slot_offset[s] + id), row r is owned by rank r mod G and stored at local
+index r div G.  Shared by the CUDA path (sharded.py) and the gloo CPU protocol tests.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+
+def slot_offsets(rows: Sequence[int]) -> List[int]:
+    out, o = [], 0
+    for r in rows:
+        out.append(o)
+        o += int(r)
+    return out
+
+
+def owner(row: int, world: int) -> int:
+    return row % world
+
+
+def local_row(row: int, world: int) -> int:
+    return row // world
+
+
+def local_rows(total_rows: int, rank: int, world: int) -> int:
+    """Number of global rows r in [0, total_rows) with r % world == rank."""
+    return (total_rows - rank + world - 1) // world if total_rows > rank else 0
+
+
+def capacity(n_lookups: int, world: int, slack: float = 0.25, floor: int = 1024) -> int:
+    """Per-destination slots of the padded equal-split exchange: mean + slack, at least `floor`
+    above the mean (uniform ids deviate by ~sqrt(n/G); the overflow flag catches skew)."""
+    mean = (n_lookups + world - 1) // world
+    return min(n_lookups, mean + max(floor, int(mean * slack))) if world > 1 else n_lookups

@@ -1,0 +1,261 @@
+"""Row-sharded embedding tables + data-parallel tower: the N>1 path.
+
+One process per GPU (torch.distributed, NCCL over NVLink/NVSwitch).  Global batch = world * B,
+each rank trains on its own B examples:
+
+  fwd  ids [B,S] --dr_shard_bucket_ids--> padded per-owner local row ids
+       all-to-all (ids out)            -> every owner gathers its rows  (dr_gather_fwd, fused
+                                          rows [emb | w | pad]: the first-order weight rides along)
+       all-to-all (vectors back)       -> dr_embed_fm_fwd with table = receive buffer, ids = inv:
+                                          un-permute + stack + first-order + FM in ONE kernel
+       DNN tower (replicated) -> BCE
+  bwd  tower backward -> dr_embed_fm_bwd packs per-lookup gradient rows into the send buffer
+       all-to-all (gradients out)      -> owners apply the row-sparse SGD update (dr_scatter_add)
+       all-reduce of the flat tower gradient (+ the FM bias gradient), then dr_sgd_step.
+
+The exchanges are equal-split (fixed capacity, -1 padded) so there is no host round trip for
+split sizes; an overflow flag set by the bucket kernel is checked after the step.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import _lib, ops, shard_plan
+from ._lib import check
+from .keras.layers.base import Dense
+
+
+class ShardedEmbedding:
+    """This rank's shard of the global row space, fused layout [local_rows, D+4]."""
+
+    def __init__(self, rows: Sequence[int], dim: int, rank: int, world: int, device, seed: Optional[int] = None):
+        if dim + 4 > 128:
+            raise NotImplementedError("sharded fused rows need D + 4 <= 128 in this round")
+        self.rows_list = [int(r) for r in rows]
+        self.dim, self.rank, self.world = int(dim), rank, world
+        self.vdim = self.dim + 4
+        self.total_rows = sum(self.rows_list)
+        self.local_rows = shard_plan.local_rows(self.total_rows, rank, world)
+        self.device = device
+        std = 1.0 / self.dim ** 0.5
+        w = torch.zeros((self.local_rows, self.vdim), dtype=torch.float32, device=device)
+        gen = torch.Generator(device=device).manual_seed((seed or 0) * 1000 + rank)
+        torch.nn.init.trunc_normal_(w[:, :self.dim], 0.0, std, -2 * std, 2 * std, generator=gen)
+        self.weight = w
+        self.slot_offsets = torch.tensor(shard_plan.slot_offsets(self.rows_list), dtype=torch.int64, device=device)
+        self.rows = torch.tensor(self.rows_list, dtype=torch.int64, device=device)
+
+
+class ShardedDeepFMTrainStep:
+    def __init__(self, columns, dim: int, dnn_units: Sequence[int], batch_size: int, lr: float = 0.01,
+                 seed: int = 0, device=None, group=None, use_graph: bool = False):
+        if not dist.is_initialized():
+            raise RuntimeError("ShardedDeepFMTrainStep needs an initialised torch.distributed process group")
+        self.lib = _lib.load()
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if dev.type != "cuda":
+            raise _lib.DeepRecError("the sharded hot path runs on CUDA only (no CPU fallback)")
+        self.dev = dev
+        rows = [c.num_buckets for c in columns]
+        self.B, self.S, self.D = int(batch_size), len(rows), int(dim)
+        self.lr = float(lr)
+        self.emb = ShardedEmbedding(rows, dim, self.rank, self.world, dev, seed)
+        B, S, D, G = self.B, self.S, self.D, self.world
+        self.n = B * S
+        self.cap = shard_plan.capacity(self.n, G)
+        V = self.emb.vdim
+        f = dict(device=dev, dtype=torch.float32)
+        # tower: identical initialisation on every rank (same seed), kept in one flat buffer; slot 0 = FM bias
+        layers: List[Dense] = [Dense(u, activation="relu", seed=seed + i) for i, u in enumerate(dnn_units)]
+        layers.append(Dense(1, seed=seed + len(dnn_units)))
+        in_dim = S * D
+        for l in layers:
+            l.build((B, in_dim), device=dev)
+            in_dim = l.units
+        self.layers = layers
+        total = 1 + sum(l.kernel.numel() + l.bias.numel() for l in layers)
+        self.flat = torch.zeros(total, **f)
+        self.gflat = torch.zeros(total, **f)
+        self.bias, self.g_bias = self.flat[0:1], self.gflat[0:1]
+        self.w, self.b, self.gw, self.gb = [], [], [], []
+        o = 1
+        with torch.no_grad():
+            for l in layers:
+                for src, dst_p, dst_g in ((l.kernel, self.w, self.gw), (l.bias, self.b, self.gb)):
+                    nel = src.numel()
+                    self.flat[o:o + nel].copy_(src.reshape(-1))
+                    src.data = self.flat[o:o + nel].view_as(src)
+                    dst_p.append(src.data)
+                    dst_g.append(self.gflat[o:o + nel].view_as(src))
+                    o += nel
+        # static buffers
+        self.ids = torch.zeros((B, S), device=dev, dtype=torch.int64)
+        self.labels = torch.zeros((B,), **f)
+        self.send_counts = torch.zeros((G,), device=dev, dtype=torch.int64)
+        self.send_ids = torch.empty((G * self.cap,), device=dev, dtype=torch.int64)
+        self.recv_ids = torch.empty((G * self.cap,), device=dev, dtype=torch.int64)
+        self.inv = torch.empty((self.n,), device=dev, dtype=torch.int32)
+        self.overflow = torch.zeros((1,), device=dev, dtype=torch.int32)
+        self.vec_send = torch.empty((G * self.cap, V), **f)      # rows gathered for the requesters
+        self.vec_recv = torch.empty((G * self.cap, V), **f)      # rows this rank asked for
+        self.grad_send = torch.empty((G * self.cap, V), **f)
+        self.grad_recv = torch.empty((G * self.cap, V), **f)
+        self.stack = torch.empty((B, S, D), **f)
+        self.sum_e = torch.empty((B, D), **f)
+        self.fm_logit = torch.empty((B,), **f)
+        self.acts = [torch.empty((B, l.units), **f) for l in layers]
+        self.g_acts = [torch.empty((B, l.units), **f) for l in layers]
+        self.gz_ws = [torch.empty((B, l.units), **f) if l._act != 0 else None for l in layers]
+        self.g_stack = torch.empty((B, S, D), **f)
+        self.loss = torch.zeros((1,), **f)
+        self.prob = torch.empty((B,), **f)
+        # "identity tables": the S slots all read the receive buffer (table base = vec_recv, rows = G*cap)
+        base = self.vec_recv.data_ptr()
+        self.tp = torch.full((S,), base, device=dev, dtype=torch.int64)
+        self.lp = torch.full((S,), base + D * 4, device=dev, dtype=torch.int64)
+        gbase = self.grad_send.data_ptr()
+        self.gtp = torch.full((S,), gbase, device=dev, dtype=torch.int64)
+        self.glp = torch.full((S,), gbase + D * 4, device=dev, dtype=torch.int64)
+        self.trows = torch.full((S,), G * self.cap, device=dev, dtype=torch.int64)
+        self.graph = None
+        self.launches_per_step = None
+        self._copy_stream = torch.cuda.Stream(device=dev)
+        self._staged = None
+
+    def _a2a(self, out, inp):
+        dist.all_to_all_single(out, inp, group=self.group)
+
+    def _enqueue(self, mark=None):
+        lib, st = self.lib, torch.cuda.current_stream().cuda_stream
+        B, S, D, G, V = self.B, self.S, self.D, self.world, self.emb.vdim
+        mark = mark or (lambda label: None)
+        mark("start")
+        check(lib.dr_shard_bucket_ids(self.ids.data_ptr(), 8, self.n, S, self.emb.slot_offsets.data_ptr(),
+                                      self.emb.rows.data_ptr(), G, self.cap, self.send_counts.data_ptr(),
+                                      self.send_ids.data_ptr(), self.inv.data_ptr(), self.overflow.data_ptr(), st),
+              "dr_shard_bucket_ids")
+        mark("bucket")
+        self._a2a(self.recv_ids, self.send_ids)
+        mark("a2a_ids")
+        check(lib.dr_gather_fwd(self.emb.weight.data_ptr(), self.emb.local_rows, self.recv_ids.data_ptr(), 8,
+                                G * self.cap, V, self.vec_send.data_ptr(), st), "dr_gather_fwd")
+        mark("owner_gather")
+        self._a2a(self.vec_recv, self.vec_send)
+        mark("a2a_vectors")
+        check(lib.dr_embed_fm_fwd(self.tp.data_ptr(), self.lp.data_ptr(), self.trows.data_ptr(), self.inv.data_ptr(), 4,
+                                  self.bias.data_ptr(), B, S, D, V, V, self.stack.data_ptr(), self.sum_e.data_ptr(),
+                                  self.fm_logit.data_ptr(), st), "dr_embed_fm_fwd")
+        mark("embed_fm_fwd")
+        x, K = self.stack, S * D
+        for i, l in enumerate(self.layers):
+            check(lib.dr_dense_fwd(x.data_ptr(), self.w[i].data_ptr(), self.b[i].data_ptr(), B, K, l.units, l._act,
+                                   self.acts[i].data_ptr(), st), "dr_dense_fwd")
+            x, K = self.acts[i], l.units
+            mark(f"dense_fwd_{i}")
+        gz = self.g_acts[-1]
+        check(lib.dr_bce_logits_fwd_bwd(self.acts[-1].data_ptr(), self.fm_logit.data_ptr(), self.labels.data_ptr(), B,
+                                        self.prob.data_ptr(), self.loss.data_ptr(), gz.data_ptr(), st), "dr_bce")
+        mark("bce")
+        for i in range(len(self.layers) - 1, -1, -1):
+            l = self.layers[i]
+            xin = self.stack if i == 0 else self.acts[i - 1]
+            Kin = S * D if i == 0 else self.layers[i - 1].units
+            gx = self.g_stack if i == 0 else self.g_acts[i - 1]
+            check(lib.dr_dense_bwd(xin.data_ptr(), self.w[i].data_ptr(), self.acts[i].data_ptr(),
+                                   self.g_acts[i].data_ptr(), B, Kin, l.units, l._act, ops._ptr(self.gz_ws[i]),
+                                   gx.data_ptr(), self.gw[i].data_ptr(), self.gb[i].data_ptr(), st), "dr_dense_bwd")
+            mark(f"dense_bwd_{i}")
+        # pack per-lookup gradient rows [dE | g_logit | 0 0 0] into the padded send buffer
+        self.grad_send.zero_()
+        self.g_bias.zero_()
+        check(lib.dr_embed_fm_bwd(self.inv.data_ptr(), 4, self.trows.data_ptr(), self.stack.data_ptr(),
+                                  self.sum_e.data_ptr(), gz.data_ptr(), self.g_stack.data_ptr(), B, S, D, V, V,
+                                  self.gtp.data_ptr(), self.glp.data_ptr(), self.g_bias.data_ptr(), 1.0, st),
+              "dr_embed_fm_bwd")
+        mark("embed_fm_bwd_pack")
+        self._a2a(self.grad_recv, self.grad_send)
+        mark("a2a_grads")
+        # owners: row-sparse SGD on the fused rows (mean over the GLOBAL batch: 1/world)
+        check(lib.dr_scatter_add(self.emb.weight.data_ptr(), self.emb.local_rows, self.recv_ids.data_ptr(), 8,
+                                 G * self.cap, V, self.grad_recv.data_ptr(), -self.lr / G, st), "dr_scatter_add")
+        mark("owner_scatter_sgd")
+        dist.all_reduce(self.gflat, group=self.group)
+        mark("allreduce_dense")
+        check(lib.dr_sgd_step(self.flat.data_ptr(), self.gflat.data_ptr(), self.flat.numel(), self.lr / G, st),
+              "dr_sgd_step")
+        mark("sgd")
+
+    def capture(self):
+        n0 = _lib.launch_count()
+        self._enqueue()
+        torch.cuda.synchronize()
+        self.launches_per_step = _lib.launch_count() - n0
+        self.check_overflow()
+        return self
+
+    def check_overflow(self):
+        if int(self.overflow.item()) != 0:
+            raise _lib.DeepRecError(f"shard exchange overflow: a destination needed more than cap={self.cap} slots; "
+                                    "raise shard_plan.capacity slack (skewed ids)")
+
+    def run(self):
+        self._enqueue()
+
+    def step(self, ids, labels):
+        self.ids.copy_(ids, non_blocking=True)
+        self.labels.copy_(labels.reshape(-1), non_blocking=True)
+        self.run()
+        return self.loss
+
+    def stage_host(self, ids_host, labels_host):
+        if not hasattr(self, "_spare"):
+            self._spare = (torch.empty_like(self.ids), torch.empty_like(self.labels))
+        with torch.cuda.stream(self._copy_stream):
+            self._spare[0].copy_(ids_host, non_blocking=True)
+            self._spare[1].copy_(labels_host.reshape(-1), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        self._staged = ev
+
+    def train_step_host(self, ids_host, labels_host, next_ids_host=None, next_labels_host=None) -> float:
+        cur = torch.cuda.current_stream()
+        if self._staged is None:
+            self.stage_host(ids_host, labels_host)
+        cur.wait_event(self._staged)
+        self.ids.copy_(self._spare[0], non_blocking=True)
+        self.labels.copy_(self._spare[1], non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(cur)
+        self._staged = None
+        if next_ids_host is not None:
+            self._copy_stream.wait_event(done)
+            self.stage_host(next_ids_host, next_labels_host)
+        self.run()
+        return float(self.loss.item())
+
+    def profile_kernels(self, ids_pool, labels_pool, iters: int = 10):
+        sums, count = {}, 0
+        for it in range(iters + 2):
+            self.ids.copy_(ids_pool[it % len(ids_pool)], non_blocking=True)
+            self.labels.copy_(labels_pool[it % len(labels_pool)].reshape(-1), non_blocking=True)
+            evs = []
+
+            def mark(label):
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                evs.append((label, e))
+
+            self._enqueue(mark)
+            torch.cuda.synchronize()
+            if it < 2:
+                continue
+            count += 1
+            for (l0, e0), (l1, e1) in zip(evs[:-1], evs[1:]):
+                sums[l1] = sums.get(l1, 0.0) + e0.elapsed_time(e1)
+        shares = {k: v / count for k, v in sums.items()}
+        return {"embed_fm_fwd_ms": shares["embed_fm_fwd"]}, shares

@@ -175,21 +175,27 @@ int dr_hard_negative_topk(const float* logits, int64_t nq, int64_t nc, int k,
 
 /* ---------------------------------------------------------------------------------------
  * Row-sharded tables: owner(r) = r mod G, local row = r div G.
- *   dr_shard_bucket_ids: groups the flat id list [n] (n = B*S, slot = index % S) by owner.
+ *   dr_shard_bucket_ids: one pass over the flat id list [n] (n = B*S, slot = index % S).
  *     global row = slot_offsets[s] + id (all S tables share one row space; slot_offsets and
  *     rows may be NULL = ids are already global rows); an id outside [0, rows[s]) becomes
  *     row -1 (owner 0, local id -1 => zero vector at the owner).
- *     Writes send_counts [G] (int64), perm [n] (int32: position in owner-grouped order ->
- *     original flat position) and local_ids [n] (int64, row div G, in grouped order).
- *     cursor_ws: [G] int64 scratch.  Order inside one owner's group is unspecified.
- *   The exchange itself (ids out, vectors back) is an NCCL all-to-all issued by the host
- *   through torch.distributed; dr_unpermute_rows restores [n, D] rows to flat order
- *   (out[perm[i]] = in[i]) and dr_permute_rows is its transpose (out[i] = in[perm[i]]).
+ *     The send buffer is PADDED to a fixed capacity so the exchange is an equal-split
+ *     all-to-all with no host synchronisation: segment g = send_ids[g*cap, (g+1)*cap) holds the
+ *     local row ids (row div G) destined to rank g, -1 in unused slots.  inv[i] = slot of
+ *     lookup i (-1 on overflow).  send_counts[G] = used slots per segment; overflow[0] = 1 if
+ *     some segment needed more than cap slots (the caller must then re-run with a larger cap).
+ *     Order inside a segment is unspecified.  Requires G*cap < 2^31.
+ *   The exchange (ids out, vectors back, gradients out) is an NCCL all-to-all issued by the
+ *   host through torch.distributed.  Because inv IS a gather index, the returned vectors are
+ *   consumed directly by dr_embed_fm_fwd (table = the receive buffer, ids = inv), which fuses
+ *   the un-permute with the FM reduction; dr_embed_fm_bwd with the same ids packs the
+ *   per-lookup gradients for the way back.  dr_permute_rows / dr_unpermute_rows are the plain
+ *   row shuffles (out[i] = in[perm[i]] / out[perm[i]] = in[i]; negative perm entries skipped).
  * ------------------------------------------------------------------------------------- */
 int dr_shard_bucket_ids(const void* ids, int id_bytes, int64_t n, int S,
-                        const int64_t* slot_offsets, const int64_t* rows, int G,
-                        int64_t* send_counts, int64_t* cursor_ws, int32_t* perm,
-                        int64_t* local_ids, void* stream);
+                        const int64_t* slot_offsets, const int64_t* rows, int G, int64_t cap,
+                        int64_t* send_counts, int64_t* send_ids, int32_t* inv, int32_t* overflow,
+                        void* stream);
 int dr_permute_rows(const float* in, const int32_t* perm, int64_t n, int D, float* out, void* stream);
 int dr_unpermute_rows(const float* in, const int32_t* perm, int64_t n, int D, float* out, void* stream);
 

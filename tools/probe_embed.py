@@ -42,9 +42,16 @@ def main():
     st = torch.cuda.current_stream().cuda_stream
     out = []
     NP = 6
-    for D, rows, layout, idb in ((16, 1_000_000, "fused", 8), (16, 1_000_000, "split", 8), (16, 1_000_000, "fused", 4),
-                                 (16, 20_000, "fused", 8), (32, 1_000_000, "fused", 8), (128, 200_000, "fused", 8)):
-        if ncu_mode and not (D == 16 and rows == 1_000_000 and layout == "fused" and idb == 8):
+    gran = 0
+    for a in sys.argv:
+        if a.startswith("--gran="):
+            gran = int(a.split("=")[1])
+    if gran:
+        _lib.tune("l2_fetch_granularity", gran)
+    for D, rows, layout, idb in ((16, 1_000_000, "fused", 8), (16, 1_000_000, "split", 8),
+                                 (16, 20_000, "split", 8), (32, 1_000_000, "fused", 8), (32, 1_000_000, "split", 8),
+                                 (128, 200_000, "split", 8)):
+        if ncu_mode and not (D == 16 and rows == 1_000_000 and layout == "split" and idb == 8):
             continue
         coll = EmbeddingCollection([rows] * S, D, device="cuda", seed=1, layout=layout)
         gen = torch.Generator(device="cuda").manual_seed(0)
@@ -96,14 +103,14 @@ def main():
             fwd(i)
         for name, (fn, nbytes) in exps.items():
             t = timeit(fn)
-            r = dict(exp=name, D=D, rows=rows, layout=layout, id_bytes=idb, us=round(t * 1e6, 2),
+            r = dict(exp=name, gran=gran, D=D, rows=rows, layout=layout, id_bytes=idb, us=round(t * 1e6, 2),
                      alg_gbs=round(nbytes / t / 1e9, 1), frac=round(nbytes / t / 1e9 / HBM, 4))
             print(json.dumps(r), flush=True)
             out.append(r)
         del coll, ids_pool, stacks, sums, gs
         torch.cuda.empty_cache()
     os.makedirs("gpurun_out", exist_ok=True)
-    json.dump(out, open("gpurun_out/probe_embed.json", "w"), indent=1)
+    json.dump(out, open(f"gpurun_out/probe_embed_g{gran}.json", "w"), indent=1)
 
 
 if __name__ == "__main__":
