@@ -28,6 +28,7 @@ _SIGS = {
     "dr_last_error": [],
     "dr_launch_count": [],
     "dr_tune_set": [C.c_char_p, _i],
+    "dr_set_workspace": [_p, C.c_uint64],
     "dr_embed_fm_fwd": [_p, _p, _p, _p, _i, _p, _i64, _i, _i, _i64, _i64, _p, _p, _p, _p],
     "dr_embed_fm_bwd": [_p, _i, _p, _p, _p, _p, _p, _i64, _i, _i, _i64, _i64, _p, _p, _p, _f, _p],
     "dr_gather_fwd": [_p, _i64, _p, _i, _i64, _i, _p, _p],
@@ -94,3 +95,26 @@ def launch_count() -> int:
 
 def tune(key: str, value: int) -> None:
     check(load().dr_tune_set(key.encode(), int(value)), "dr_tune_set")
+
+
+_workspace = None
+
+
+def set_workspace(nbytes: int, device=None):
+    """Allocate (through torch) and register the tensor-core GEMM scratch; 0 unregisters."""
+    global _workspace
+    import torch
+    if nbytes <= 0:
+        check(load().dr_set_workspace(None, 0), "dr_set_workspace")
+        _workspace = None
+        return None
+    if _workspace is None or _workspace.numel() < nbytes:
+        _workspace = torch.empty(int(nbytes), dtype=torch.uint8, device=device or "cuda")
+    check(load().dr_set_workspace(_workspace.data_ptr(), _workspace.numel()), "dr_set_workspace")
+    return _workspace
+
+
+def enable_tensor_core_gemm(workspace_bytes: int = 2 << 30, device=None) -> None:
+    """Route eligible GEMMs (Dense / Cross / scores) to the tcgen05 3xTF32 kernel."""
+    set_workspace(workspace_bytes, device)
+    tune("gemm_variant", 1)

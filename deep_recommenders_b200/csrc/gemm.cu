@@ -245,6 +245,7 @@ int gemm_launch(const GemmArgs& a0, bool ta, bool tb, cudaStream_t st) {
   if (a.splitk < 1) a.splitk = 1;
   DR_REQUIRE(a.splitk == 1 || a.epi == EPI_ATOMIC, DR_EINVAL, "gemm: split-K needs the atomic epilogue");
   DR_REQUIRE((a.N + 15) / 16 <= 65535, DR_EINVAL, "gemm: N=%lld too large for grid.y", (long long)a.N);
+  if (gemm_tc_eligible(a, ta, tb)) return gemm_tc_launch(a, ta, tb, st);
   const int64_t ktiles = (a.K + 15) / 16;
   if (a.splitk > ktiles) a.splitk = (int)ktiles;
   if (a.N > 64) return launch_cfg<128, 128, 16, 8, 8>(a, ta, tb, st);

@@ -44,4 +44,9 @@ extern int g_tune_gemm_splitk;
 // C = A * B with the given storage flags; picks the tile shape from N. Returns DR_* / cudaError.
 int gemm_launch(const GemmArgs& a, bool transA, bool transB, cudaStream_t st);
 
+// tcgen05 3xTF32 variant (gemm_tc.cu): used when g_tune_gemm_variant == 1, the shape is aligned
+// and the registered workspace (dr_set_workspace) can hold the hi/lo operand planes.
+bool gemm_tc_eligible(const GemmArgs& a, bool transA, bool transB);
+int gemm_tc_launch(const GemmArgs& a, bool transA, bool transB, cudaStream_t st);
+
 }  // namespace dr

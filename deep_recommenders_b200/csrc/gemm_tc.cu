@@ -1,0 +1,424 @@
+// Variant 1 of the fp32 GEMM core: tcgen05 (5th-gen tensor cores) with 3xTF32 split products.
+//
+//   C[M,N] = epilogue( A @ B ),   A = Ah + Al, B = Bh + Bl   (Ah = fp32 with the low 13 mantissa
+//   bits cleared = exactly representable in TF32, Al = A - Ah exactly),
+//   A @ B ~= Al@Bh + Ah@Bl + Ah@Bh      (the dropped Al@Bl term is ~2^-22 relative)
+// which restores fp32-level accuracy (the parity bar is 1e-5 relative, out of reach of single-pass
+// TF32/BF16) at 3 tensor-core products per k-step.  The hi/lo planes are produced by
+// split_tf32_kernel into caller-provided workspace (dr_set_workspace) and streamed by TMA.
+//
+// Structure (one 128 x BN output tile per CTA, 192 threads, sm_100a only):
+//   warp 0      TMA producer: cp.async.bulk.tensor (SWIZZLE_128B boxes) into a 3-stage smem ring,
+//               completion on "full" mbarriers (expect_tx)
+//   warp 1      TMEM allocator + MMA issuer: one elected lane issues tcgen05.mma.kind::tf32
+//               (M=128, N=BN, K=8) x 4 k-steps x 3 products per stage, accumulator in TMEM;
+//               tcgen05.commit releases the smem stage ("empty" mbarrier) and finally signals
+//               the epilogue ("tmem_full")
+//   warps 2-5   epilogue: tcgen05.ld (32 lanes x 32 columns per warp), fused epilogue (gemm.cuh
+//               Epi modes), vectorised global stores / split-K atomics
+// Operand majors: K-major (row-major [rows, K]) or MN-major ([K, rows] row-major) per operand;
+// both are canonical SWIZZLE_128B UMMA layouts (32 tf32 = 128 B per swizzle row).
+#include "gemm.cuh"
+#include <cuda.h>
+#include <float.h>
+
+namespace dr {
+
+// ---- workspace registered by the host (dr_set_workspace) ----------------------------------------
+static void* g_ws_ptr = nullptr;
+static size_t g_ws_bytes = 0;
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;          // 32 tf32 = 128 bytes = one SWIZZLE_128B row
+constexpr int TC_STAGES = 3;
+constexpr int TC_THREADS = 192;
+
+// ---- small PTX wrappers ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B, version 1.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;   // LayoutType::SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): TF32 x TF32 -> F32, dense.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool b_mn) {
+  return (1u << 4)                       // c_format = F32
+         | (2u << 7) | (2u << 10)        // a_format = b_format = TF32
+         | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16)
+         | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ x, int64_t n4,
+                                                          float* __restrict__ hi, float* __restrict__ lo) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    float4 h, l;
+    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+    reinterpret_cast<float4*>(hi)[i] = h;
+    reinterpret_cast<float4*>(lo)[i] = l;
+  }
+}
+
+__device__ __forceinline__ float epi_scalar_tc(const GemmArgs& a, float acc, int64_t m, int64_t n) {
+  const int64_t off = m * a.ldc + n;
+  switch (a.epi) {
+    case EPI_BIAS_ACT: return act_apply(acc + (a.bias ? __ldg(a.bias + n) : 0.f), a.act);
+    case EPI_ACTGRAD: return acc * act_grad_from_y(__ldg(a.aux0 + off), a.act);
+    case EPI_CROSS: {
+      const float x = __ldg(a.aux1 + off);
+      float u = acc + (a.bias ? __ldg(a.bias + n) : 0.f);
+      if (a.alpha != 0.f) u = u + a.alpha * x;
+      if (a.out2) a.out2[off] = u;
+      return __ldg(a.aux0 + off) * u + x;
+    }
+    case EPI_CROSS_DX: {
+      float v = acc + __ldg(a.aux1 + off);
+      if (a.alpha != 0.f) v += a.alpha * __ldg(a.aux0 + off);
+      return v;
+    }
+    case EPI_SCORES: {
+      float v = acc;
+      if (a.bias) v = v - logf(__ldg(a.bias + n));
+      if (a.cand_ids && m != n && m < a.N && __ldg(a.cand_ids + n) == __ldg(a.cand_ids + m))
+        v = v + (-FLT_MAX / 100.0f);
+      return v;
+    }
+    default: return acc;
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+               const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+               const GemmArgs a) {
+  constexpr int A_TILE = TC_BM * TC_BK * 4;   // 16 KB
+  constexpr int B_TILE = BN * TC_BK * 4;
+  constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], tmem_full_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t m0 = (int64_t)blockIdx.x * TC_BM;
+  const int64_t n0 = (int64_t)blockIdx.y * BN;
+  const int64_t kblocks = (a.K + TC_BK - 1) / TC_BK;
+  const int64_t per = (kblocks + a.splitk - 1) / a.splitk;
+  const int64_t kb0 = (int64_t)blockIdx.z * per;
+  const int64_t kb1 = min(kblocks, kb0 + per);
+  const int nkb = (int)max((int64_t)0, kb1 - kb0);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAh) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAl) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBh) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBl) : "memory");
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {   // TMEM: BN fp32 accumulator columns (power of two >= 32)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"((uint32_t)BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (nkb > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        // ===== TMA producer =====
+        for (int i = 0; i < nkb; ++i) {
+          const int s = i % TC_STAGES;
+          const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          mbar_expect_tx(&full_bar[s], (uint32_t)STAGE);
+          uint8_t* st = smem + (size_t)s * STAGE;
+          const int k = (int)((kb0 + i) * TC_BK);
+          if (!A_MN) {
+            tma_load_2d(st, &tmAh, &full_bar[s], k, (int)m0);
+            tma_load_2d(st + A_TILE, &tmAl, &full_bar[s], k, (int)m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < TC_BM / 32; ++j) {
+              tma_load_2d(st + j * 4096, &tmAh, &full_bar[s], (int)m0 + j * 32, k);
+              tma_load_2d(st + A_TILE + j * 4096, &tmAl, &full_bar[s], (int)m0 + j * 32, k);
+            }
+          }
+          if (!B_MN) {
+            tma_load_2d(st + 2 * A_TILE, &tmBh, &full_bar[s], k, (int)n0);
+            tma_load_2d(st + 2 * A_TILE + B_TILE, &tmBl, &full_bar[s], k, (int)n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 32; ++j) {
+              tma_load_2d(st + 2 * A_TILE + j * 4096, &tmBh, &full_bar[s], (int)n0 + j * 32, k);
+              tma_load_2d(st + 2 * A_TILE + B_TILE + j * 4096, &tmBl, &full_bar[s], (int)n0 + j * 32, k);
+            }
+          }
+        }
+      }
+      __syncwarp();
+    } else if (warp == 1) {
+      if (lane == 0) {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc = make_idesc(TC_BM, BN, A_MN, B_MN);
+        for (int i = 0; i < nkb; ++i) {
+          const int s = i % TC_STAGES;
+          const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * STAGE);
+          const uint32_t sb = sa + 2 * A_TILE;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; ++k) {
+            // K-major: step 8 tf32 = 32 B inside the 128-B swizzle row, 8-row groups 1024 B apart.
+            // MN-major: step 8 k-rows = 1024 B, MN atoms (32 elements) 4096 B apart.
+            const uint32_t a_off = A_MN ? (uint32_t)k * 1024u : (uint32_t)k * 32u;
+            const uint32_t b_off = B_MN ? (uint32_t)k * 1024u : (uint32_t)k * 32u;
+            const uint32_t a_lbo = A_MN ? 4096u : 16u, b_lbo = B_MN ? 4096u : 16u;
+            const uint64_t dAh = make_smem_desc(sa + a_off, a_lbo, 1024u);
+            const uint64_t dAl = make_smem_desc(sa + A_TILE + a_off, a_lbo, 1024u);
+            const uint64_t dBh = make_smem_desc(sb + b_off, b_lbo, 1024u);
+            const uint64_t dBl = make_smem_desc(sb + B_TILE + b_off, b_lbo, 1024u);
+            const uint32_t acc0 = (i > 0 || k > 0) ? 1u : 0u;
+            tc_mma_tf32(tmem_base, dAl, dBh, idesc, acc0);   // small cross terms first
+            tc_mma_tf32(tmem_base, dAh, dBl, idesc, 1u);
+            tc_mma_tf32(tmem_base, dAh, dBh, idesc, 1u);
+          }
+          tc_commit(&empty_bar[s]);          // smem stage reusable once these MMAs retire
+        }
+        tc_commit(&tmem_full_bar);           // accumulator complete
+      }
+      __syncwarp();
+    } else {
+      // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
+      mbar_wait(&tmem_full_bar, 0);
+      tc_fence_after();
+      const int q = warp & 3;
+      const int64_t m = m0 + q * 32 + lane;
+      const bool vec_ok = ((a.ldc & 3) == 0) && aligned16(a.C);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+        const int64_t nb = n0 + c * 32;
+        if (m < a.M && nb < a.N) {
+          if (a.epi == EPI_ATOMIC) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nb + j < a.N) red_add_f32(a.C + m * a.ldc + nb + j, __uint_as_float(r[j]));
+          } else if (vec_ok && nb + 31 < a.N) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 o;
+              o.x = epi_scalar_tc(a, __uint_as_float(r[j + 0]), m, nb + j + 0);
+              o.y = epi_scalar_tc(a, __uint_as_float(r[j + 1]), m, nb + j + 1);
+              o.z = epi_scalar_tc(a, __uint_as_float(r[j + 2]), m, nb + j + 2);
+              o.w = epi_scalar_tc(a, __uint_as_float(r[j + 3]), m, nb + j + 3);
+              *reinterpret_cast<float4*>(a.C + m * a.ldc + nb + j) = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nb + j < a.N) a.C[m * a.ldc + nb + j] = epi_scalar_tc(a, __uint_as_float(r[j]), m, nb + j);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+static int get_encode() {
+  if (g_encode) return DR_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+    set_error("gemm_tc: cuTensorMapEncodeTiled entry point not available (%s)", cudaGetErrorString(e));
+    return e != cudaSuccess ? (int)e : DR_ENOTSUP;
+  }
+  g_encode = (EncodeTiledFn)fn;
+  return DR_OK;
+}
+
+// 2-D fp32 tensor [outer, inner] (inner contiguous, pitch floats), box {32, box_outer}, SWIZZLE_128B.
+static int make_map(CUtensorMap* tm, const float* base, int64_t inner, int64_t outer, int64_t pitch, int box_outer) {
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch * 4};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("gemm_tc: cuTensorMapEncodeTiled failed (CUresult %d; inner=%lld outer=%lld pitch=%lld)", (int)r,
+              (long long)inner, (long long)outer, (long long)pitch);
+    return DR_EINVAL;
+  }
+  return DR_OK;
+}
+
+bool gemm_tc_eligible(const GemmArgs& a, bool ta, bool tb) {
+  if (g_tune_gemm_variant != 1) return false;
+  if (a.N < 96 || a.M < 64 || a.K < 32) return false;
+  if ((a.lda & 3) || (a.ldb & 3) || !aligned16(a.A) || !aligned16(a.B)) return false;
+  const size_t a_elems = (size_t)(ta ? a.K : a.M) * (size_t)a.lda;
+  const size_t b_elems = (size_t)(tb ? a.N : a.K) * (size_t)a.ldb;
+  if ((a_elems & 3) || (b_elems & 3)) return false;
+  const size_t need = (a_elems + b_elems) * 2 * sizeof(float) + 4096;
+  if (!g_ws_ptr || g_ws_bytes < need) return false;
+  if (a.M >= ((int64_t)1 << 31) || a.K >= ((int64_t)1 << 31)) return false;
+  return true;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_tc(const CUtensorMap* tms, const GemmArgs& a, cudaStream_t st) {
+  constexpr int STAGE = 2 * TC_BM * TC_BK * 4 + 2 * BN * TC_BK * 4;
+  const size_t smem = (size_t)TC_STAGES * STAGE + 1024;
+  auto k = gemm_tc_kernel<BN, A_MN, B_MN>;
+  DR_CUDA_CALL(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)((a.M + TC_BM - 1) / TC_BM), (unsigned)((a.N + BN - 1) / BN), (unsigned)a.splitk);
+  k<<<grid, TC_THREADS, smem, st>>>(tms[0], tms[1], tms[2], tms[3], a);
+  DR_CUDA_LAUNCH_CHECK("gemm_tc");
+  return DR_OK;
+}
+
+int gemm_tc_launch(const GemmArgs& a0, bool ta, bool tb, cudaStream_t st) {
+  GemmArgs a = a0;
+  if (int rc = get_encode()) return rc;
+  if (a.splitk < 1) a.splitk = 1;
+  const int64_t kblocks = (a.K + TC_BK - 1) / TC_BK;
+  if (a.splitk > kblocks) a.splitk = (int)kblocks;
+  // hi/lo planes in the registered workspace
+  const size_t a_elems = (size_t)(ta ? a.K : a.M) * (size_t)a.lda;
+  const size_t b_elems = (size_t)(tb ? a.N : a.K) * (size_t)a.ldb;
+  float* Ah = reinterpret_cast<float*>(g_ws_ptr);
+  float* Al = Ah + a_elems;
+  float* Bh = Al + a_elems;
+  float* Bl = Bh + b_elems;
+  auto split = [&](const float* x, size_t n, float* hi, float* lo) -> int {
+    int64_t n4 = (int64_t)(n / 4);
+    int64_t ctas = (n4 + 255) / 256;
+    if (ctas > kNumSMs * 8) ctas = kNumSMs * 8;
+    split_tf32_kernel<<<(unsigned)ctas, 256, 0, st>>>(x, n4, hi, lo);
+    DR_CUDA_LAUNCH_CHECK("split_tf32");
+    return DR_OK;
+  };
+  if (int rc = split(a.A, a_elems, Ah, Al)) return rc;
+  if (int rc = split(a.B, b_elems, Bh, Bl)) return rc;
+  // A(m,k): !ta -> stored [M,K] (K-major), ta -> stored [K,M] (MN-major)
+  // B(k,n): !tb -> stored [K,N] (MN-major), tb -> stored [N,K] (K-major)
+  const bool A_MN = ta, B_MN = !tb;
+  CUtensorMap tms[4];
+  if (!A_MN) {
+    if (int rc = make_map(&tms[0], Ah, a.K, a.M, a.lda, TC_BM)) return rc;
+    if (int rc = make_map(&tms[1], Al, a.K, a.M, a.lda, TC_BM)) return rc;
+  } else {
+    if (int rc = make_map(&tms[0], Ah, a.M, a.K, a.lda, TC_BK)) return rc;
+    if (int rc = make_map(&tms[1], Al, a.M, a.K, a.lda, TC_BK)) return rc;
+  }
+  constexpr int BN = 128;
+  if (!B_MN) {
+    if (int rc = make_map(&tms[2], Bh, a.K, a.N, a.ldb, BN)) return rc;
+    if (int rc = make_map(&tms[3], Bl, a.K, a.N, a.ldb, BN)) return rc;
+  } else {
+    if (int rc = make_map(&tms[2], Bh, a.N, a.K, a.ldb, TC_BK)) return rc;
+    if (int rc = make_map(&tms[3], Bl, a.N, a.K, a.ldb, TC_BK)) return rc;
+  }
+  if (!A_MN && B_MN) return launch_tc<BN, false, true>(tms, a, st);
+  if (!A_MN && !B_MN) return launch_tc<BN, false, false>(tms, a, st);
+  if (A_MN && B_MN) return launch_tc<BN, true, true>(tms, a, st);
+  return launch_tc<BN, true, false>(tms, a, st);
+}
+
+}  // namespace dr
+
+extern "C" int dr_set_workspace(void* ptr, uint64_t bytes) {
+  using namespace dr;
+  DR_REQUIRE(ptr == nullptr || aligned16(ptr), DR_EALIGN, "dr_set_workspace: pointer not 16-B aligned");
+  g_ws_ptr = ptr;
+  g_ws_bytes = ptr ? (size_t)bytes : 0;
+  return DR_OK;
+}

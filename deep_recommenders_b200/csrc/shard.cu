@@ -34,13 +34,17 @@ __global__ void __launch_bounds__(256) shard_bucket_kernel(const IdT* __restrict
   const int64_t nround = (n + stride - 1) / stride;
   for (int64_t it = 0; it < nround; ++it) {
     const int64_t i = it * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = i < n;
     int64_t r = -1;
     int owner = 0;
-    if (live) {
+    if (i < n) {
       r = global_row(ids, i, S, slot_offsets, rows);
-      owner = r < 0 ? 0 : (int)(r % G);
+      if (r < 0) {          // out-of-vocabulary: zero row, nothing to exchange
+        inv[i] = -1;
+      } else {
+        owner = (int)(r % G);
+      }
     }
+    const bool live = i < n && r >= 0;
     const unsigned peers = __match_any_sync(0xffffffffu, live ? owner : (64 + lane));
     unsigned long long base = 0;
     const int leader = __ffs(peers) - 1;
@@ -50,7 +54,7 @@ __global__ void __launch_bounds__(256) shard_bucket_kernel(const IdT* __restrict
       const unsigned long long pos = base + (unsigned long long)__popc(peers & ((1u << lane) - 1u));
       if (pos < (unsigned long long)cap) {
         const int64_t slot = (int64_t)owner * cap + (int64_t)pos;
-        send_ids[slot] = r < 0 ? -1 : r / G;
+        send_ids[slot] = r / G;
         inv[i] = (int32_t)slot;
       } else {
         inv[i] = -1;

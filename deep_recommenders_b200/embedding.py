@@ -5,15 +5,18 @@ Replaces the per-column ``tf.keras.layers.DenseFeatures(embedding_column)`` /
 ``DenseFeatures(indicator_columns) -> Dense(1)`` objects the reference builds
 (keras/models/ranking/fm.py:47-51, deepfm.py:24-28; estimator/.../fm.py:43-52).
 
-Layout in HBM (layout="fused", the default when the first-order term exists)
-  weight : [sum_s rows_s, D + 4] fp32   row = [ D embedding floats | w | 3 pad ]: the
-           first-order weight w of an id (the Dense(1, kernel_initializer="zeros") kernel entry
-           of the reference's multi-hot linear term) sits in the same DRAM page as its
-           embedding vector, so one random access serves both.  Row stride (D+4)*4 bytes is
-           a multiple of 16, so every row base is 16-B aligned for LDG.128.
-  bias   : [1]                          that Dense's bias.
-layout="split": weight [sum rows, D] and linear [sum rows] as two arrays (two random accesses
-per lookup).  Table s occupies rows [off_s, off_s + rows_s) in either layout.
+Layout in HBM (layout="fused", the default when the first-order term exists and D <= 28)
+  weight : [sum_s rows_s, 32] fp32   row = [ D embedding floats | w | pad ] in ONE 128-byte,
+           128-byte-aligned line: the first-order weight w of an id (the
+           Dense(1, kernel_initializer="zeros") kernel entry of the reference's multi-hot linear
+           term) travels in the same HBM line as its embedding vector.  Measured on B200
+           (profiles/): L2 fills from HBM in 128-B lines, so a 64-B row costs 128 B of DRAM traffic
+           anyway and a separate 4-B first-order gather costs another 128 B; fusing them halves the
+           random DRAM lines per lookup.
+  bias   : [1]                       that Dense's bias.
+layout="split": weight [sum rows, D] and linear [sum rows] as two arrays (two random lines per
+lookup; used for D >= 32 where the row already fills whole lines).  Table s occupies rows
+[off_s, off_s + rows_s) in either layout.
 The reference densifies the indicator columns into a [B, sum_s N_s] multi-hot and multiplies
 by a [sum N, 1] kernel (fm.py:16-20,26); the sparse gather-sum here is the same number.
 """
@@ -46,12 +49,14 @@ class EmbeddingCollection(nn.Module):
             offs.append(offs[-1] + r)
         self.total_rows = offs[-1]
         self.with_linear = bool(with_linear)
-        self.layout = layout or ("fused" if with_linear else "split")
+        self.layout = layout or ("fused" if (with_linear and self.dim + 1 <= 32) else "split")
         if self.layout not in ("fused", "split"):
             raise ValueError(f"unknown layout {self.layout!r}")
         if self.layout == "fused" and not with_linear:
             raise ValueError("layout='fused' needs with_linear=True")
-        self.row_stride = self.dim + 4 if self.layout == "fused" else self.dim
+        if self.layout == "fused" and self.dim + 1 > 32:
+            raise ValueError("layout='fused' packs [emb | w] into one 128-B line: needs D <= 28")
+        self.row_stride = 32 if self.layout == "fused" else self.dim
         self.lin_stride = self.row_stride if self.layout == "fused" else 1
         std = init_stddev if init_stddev is not None else 1.0 / math.sqrt(self.dim)
         w = torch.zeros((self.total_rows, self.row_stride), dtype=torch.float32, device=dev)

@@ -209,6 +209,12 @@ int dr_sgd_step(float* p, const float* g, int64_t n, float lr, void* stream);
 int dr_bce_logits_fwd_bwd(const float* z, const float* z_add, const float* y, int64_t B,
                           float* prob_out, float* loss_out, float* gz, void* stream);
 
+/* Scratch for the tensor-core GEMM variant (hi/lo TF32 operand planes).  The caller owns the
+ * buffer and keeps it alive until it registers another one (ptr = NULL unregisters).  One
+ * workspace per process: GEMM entry points that use it must not run concurrently on two
+ * streams.  Without a (large enough) workspace the FFMA variant is used.                  */
+int dr_set_workspace(void* ptr, uint64_t bytes);
+
 /* Developer hook (not reference-facing): set a kernel tuning knob by name, e.g.
  * "embed_fwd_unroll", "embed_block", "embed_bwd_agg", "gemm_splitk".                     */
 int dr_tune_set(const char* key, int value);

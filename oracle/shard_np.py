@@ -20,11 +20,13 @@ def bucket_ids(ids: np.ndarray, slot_offsets, rows, world: int, cap: int):
     counts = np.zeros((world,), np.int64)
     overflow = False
     for i in range(B * S):
+        if grow[i] < 0:          # out-of-vocabulary: zero row, nothing to exchange
+            continue
         g = owner[i]
         pos = counts[g]
         counts[g] += 1
         if pos < cap:
-            send[g * cap + pos] = -1 if grow[i] < 0 else grow[i] // world
+            send[g * cap + pos] = grow[i] // world
             inv[i] = g * cap + pos
         else:
             overflow = True

@@ -44,20 +44,25 @@ def test_world1_sharded_step_equals_single_gpu_step():
         ref = DeepFMTrainStep(model, batch_size=B, lr=0.05, use_graph=False)
         with torch.no_grad():
             sh.emb.weight[:, D].normal_(0, 0.1)
-            model.embeddings.weight.copy_(sh.emb.weight)
+            model.embeddings.emb_view().copy_(sh.emb.weight[:, :D])
+            model.embeddings.lin_view().copy_(sh.emb.weight[:, D])
             for i in range(len(ref.layers)):
                 ref.w[i].copy_(sh.w[i])
                 ref.b[i].copy_(sh.b[i])
         gen = torch.Generator(device="cuda").manual_seed(0)
         ids = torch.stack([torch.randint(-1, r + 1, (B,), device="cuda", generator=gen) for r in rows], dim=1)
         lab = torch.randint(0, 2, (B,), device="cuda", generator=gen).float()
-        for _ in range(3):
+        for it in range(3):
             l_sh = float(sh.step(ids, lab).item())
             l_ref = float(ref.step(ids, lab).item())
             sh.check_overflow()
             assert abs(l_sh - l_ref) <= 1e-5 * abs(l_ref) + 1e-6
-            assert torch.equal(sh.stack, ref.stack)                       # gathered rows bit-exact
-        assert torch.allclose(sh.emb.weight, model.embeddings.weight, rtol=1e-5, atol=1e-6)
+            if it == 0:
+                assert torch.equal(sh.stack, ref.stack)                   # gathered rows bit-exact
+            else:   # later steps differ by the (unordered) atomic summation of duplicate-id updates
+                assert torch.allclose(sh.stack, ref.stack, rtol=1e-5, atol=1e-6)
+        assert torch.allclose(sh.emb.weight[:, :D], model.embeddings.emb_view(), rtol=1e-5, atol=1e-6)
+        assert torch.allclose(sh.emb.weight[:, D], model.embeddings.lin_view(), rtol=1e-5, atol=1e-6)
         for i in range(len(ref.layers)):
             assert torch.allclose(sh.w[i], ref.w[i], rtol=1e-5, atol=1e-6)
         assert torch.allclose(sh.bias, model.embeddings.bias, rtol=1e-5, atol=1e-6)
@@ -74,7 +79,7 @@ def test_bucket_kernel_against_numpy_twin():
     B, S, G = 333, 3, 4
     ids = np.stack([rng.integers(-2, r + 2, B) for r in rows], axis=1).astype(np.int64)
     offs = shard_plan.slot_offsets(rows)
-    cap = shard_plan.capacity(B * S, G, slack=0.5, floor=16)
+    cap = shard_plan.capacity(B * S, G, slack=1.0, floor=16)
     t = lambda a, dt: torch.tensor(a, dtype=dt, device="cuda")
     idt = t(ids, torch.int64)
     counts = torch.zeros(G, dtype=torch.int64, device="cuda")
@@ -91,9 +96,12 @@ def test_bucket_kernel_against_numpy_twin():
     # order inside a segment is unspecified: compare the multiset per segment and the lookup -> id map
     for g in range(G):
         assert np.array_equal(np.sort(send[g * cap:(g + 1) * cap]), np.sort(rsend[g * cap:(g + 1) * cap]))
-    assert np.array_equal(send[inv], rsend[rinv])
-    assert np.array_equal(inv // cap, rinv // cap)
-    assert len(np.unique(inv)) == B * S
+    lv = rinv >= 0
+    assert np.array_equal(send[inv[lv]], rsend[rinv[lv]])
+    assert np.array_equal(inv[lv] // cap, rinv[lv] // cap)
+    live = rinv >= 0
+    assert np.array_equal(inv >= 0, live)
+    assert len(np.unique(inv[live])) == int(live.sum())
     # overflow is reported, not silently dropped
     _lib.check(lib.dr_shard_bucket_ids(idt.data_ptr(), 8, B * S, S, t(offs, torch.int64).data_ptr(),
                                        t(rows, torch.int64).data_ptr(), G, 8, counts.data_ptr(), send.data_ptr(),
