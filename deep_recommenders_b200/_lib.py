@@ -29,8 +29,9 @@ _SIGS = {
     "dr_launch_count": [],
     "dr_tune_set": [C.c_char_p, _i],
     "dr_set_workspace": [_p, C.c_uint64],
-    "dr_embed_fm_fwd": [_p, _p, _p, _p, _i, _p, _i64, _i, _i, _i64, _i64, _p, _p, _p, _p],
-    "dr_embed_fm_bwd": [_p, _i, _p, _p, _p, _p, _p, _i64, _i, _i, _i64, _i64, _p, _p, _p, _f, _p],
+    "dr_debug_gemm": [_p, _p, _p, _i64, _i64, _i64, _i, _i, _p],
+    "dr_embed_fm_fwd": [_p, _p, _p, _p, _i, _p, _i64, _i, _i, _i64, _i64, _i, _p, _p, _p, _p],
+    "dr_embed_fm_bwd": [_p, _i, _p, _p, _p, _p, _p, _i64, _i, _i, _i64, _i64, _i, _p, _p, _p, _f, _p],
     "dr_gather_fwd": [_p, _i64, _p, _i, _i64, _i, _p, _p],
     "dr_scatter_add": [_p, _i64, _p, _i, _i64, _i, _p, _f, _p],
     "dr_fm_fwd": [_p, _i64, _i, _i, _p, _p],
@@ -98,6 +99,7 @@ def tune(key: str, value: int) -> None:
 
 
 _workspace = None
+_retired = []
 
 
 def set_workspace(nbytes: int, device=None):
@@ -109,12 +111,43 @@ def set_workspace(nbytes: int, device=None):
         _workspace = None
         return None
     if _workspace is None or _workspace.numel() < nbytes:
+        if _workspace is not None:
+            _retired.append(_workspace)      # a captured CUDA graph may still point at it
         _workspace = torch.empty(int(nbytes), dtype=torch.uint8, device=device or "cuda")
     check(load().dr_set_workspace(_workspace.data_ptr(), _workspace.numel()), "dr_set_workspace")
     return _workspace
 
 
-def enable_tensor_core_gemm(workspace_bytes: int = 2 << 30, device=None) -> None:
+def enable_tensor_core_gemm(workspace_bytes: int = 0, device=None) -> None:
     """Route eligible GEMMs (Dense / Cross / scores) to the tcgen05 3xTF32 kernel."""
-    set_workspace(workspace_bytes, device)
+    global _tc_enabled
+    if workspace_bytes:
+        set_workspace(workspace_bytes, device)
     tune("gemm_variant", 1)
+    _tc_enabled = True
+
+
+def disable_tensor_core_gemm() -> None:
+    global _tc_enabled
+    tune("gemm_variant", 0)
+    _tc_enabled = False
+
+
+# The tcgen05 3xTF32 GEMM is the default; DR_GEMM=ffma selects the FFMA variant.
+_tc_enabled = os.environ.get("DR_GEMM", "tc") != "ffma"
+_tc_applied = False
+
+
+def ensure_gemm_workspace(M: int, K: int, N: int, device=None) -> None:
+    """Make sure the hi/lo operand planes of a [M,K]x[K,N] GEMM and of its two backward GEMMs fit
+    in the registered scratch (grows it if needed); applies the default GEMM variant on first use."""
+    global _tc_applied
+    if not _tc_enabled:
+        return
+    if not _tc_applied:
+        tune("gemm_variant", 1)
+        _tc_applied = True
+    k4, n4, m4 = (K + 3) // 4 * 4, (N + 3) // 4 * 4, (M + 3) // 4 * 4
+    need = 8 * max(M * k4 + N * k4, M * n4 + K * n4, K * m4 + N * m4) + (1 << 16)
+    if _workspace is None or _workspace.numel() < need:
+        set_workspace(int(need * 1.25), device)

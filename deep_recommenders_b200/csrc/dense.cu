@@ -215,3 +215,10 @@ extern "C" int dr_scores_fwd(const float* q, const float* c, const float* p, con
   a.bias = p; a.cand_ids = cand_ids;
   return gemm_launch(a, false, true, (cudaStream_t)stream);
 }
+
+// Developer hook: plain C[M,N] = op(A) @ op(B) through the GEMM dispatcher (variant per dr_tune_set).
+extern "C" int dr_debug_gemm(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int transA,
+                             int transB, void* stream) {
+  GemmArgs a = mk(A, B, C, M, N, K, transA ? M : K, transB ? K : N, N, EPI_STORE);
+  return gemm_launch(a, transA != 0, transB != 0, (cudaStream_t)stream);
+}

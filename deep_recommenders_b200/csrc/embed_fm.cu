@@ -38,6 +38,7 @@ struct EmbedFwdParams {
   int S, D;
   int64_t row_stride;   // floats between consecutive rows of a table (>= D)
   int64_t lin_stride;   // floats between consecutive first-order weights (>= 1)
+  int lin_in_row;       // first-order weight lives in the row at float index D (fetched with the row)
   float* out_stack;
   float* out_sum;
   float* out_logit;
@@ -60,6 +61,7 @@ struct EmbedBwdParams {
   float scale;
   int64_t row_stride;
   int64_t lin_stride;
+  int lin_in_row;
 };
 
 // shared memory carve-up: [S] table ptr | [S] lin ptr | [S] rows | per-warp id slices
@@ -92,7 +94,10 @@ __global__ void __launch_bounds__(512) embed_fm_fwd_kernel(const EmbedFwdParams 
   const int c = lane % LPR;          // 16-byte chunk of the row this lane owns
   const int g = lane / LPR;          // example (lane group) inside the warp tile
   const bool chunk_ok = (c * 4) < D;
-  const bool has_lin = p.lin_ptrs != nullptr;
+  // lin_in_row: the lane owning chunk D/4 fetches [w | pad] with the SAME LDG.128 as the embedding
+  // chunks, so the first-order weight costs no extra request / DRAM line.
+  const bool lin_lane = p.lin_in_row && (c * 4 == D);
+  const bool has_lin = p.lin_ptrs != nullptr && !p.lin_in_row;
   const float bias = p.bias ? __ldg(p.bias) : 0.f;
   const IdT* __restrict__ ids = reinterpret_cast<const IdT*>(p.ids);
 
@@ -114,6 +119,7 @@ __global__ void __launch_bounds__(512) embed_fm_fwd_kernel(const EmbedFwdParams 
     const bool ex_ok = g < nex;
     const IdT* my = s_ids + g * S;
     float4 sum = f4_zero(), sq = f4_zero();
+    float lin = 0.f;
     float* ostack = p.out_stack ? p.out_stack + ((size_t)b * S) * D + c * 4 : nullptr;
 
     for (int s0 = 0; s0 < S; s0 += U) {
@@ -122,7 +128,7 @@ __global__ void __launch_bounds__(512) embed_fm_fwd_kernel(const EmbedFwdParams 
       for (int u = 0; u < U; ++u) {
         const int s = s0 + u;
         v[u] = f4_zero();
-        if (s < S && ex_ok && chunk_ok) {
+        if (s < S && ex_ok && (chunk_ok || lin_lane)) {
           const int64_t id = (int64_t)my[s];
           if ((uint64_t)id < (uint64_t)s_rows[s]) v[u] = ldg_nc_na(s_tab[s] + (size_t)id * p.row_stride + c * 4);
         }
@@ -131,10 +137,14 @@ __global__ void __launch_bounds__(512) embed_fm_fwd_kernel(const EmbedFwdParams 
       for (int u = 0; u < U; ++u) {
         const int s = s0 + u;
         if (s < S) {
-          sum.x += v[u].x; sum.y += v[u].y; sum.z += v[u].z; sum.w += v[u].w;
-          sq.x = fmaf(v[u].x, v[u].x, sq.x); sq.y = fmaf(v[u].y, v[u].y, sq.y);
-          sq.z = fmaf(v[u].z, v[u].z, sq.z); sq.w = fmaf(v[u].w, v[u].w, sq.w);
-          if (ostack && ex_ok && chunk_ok) stg4(ostack + (size_t)s * D, v[u]);
+          if (lin_lane) {
+            lin += v[u].x;
+          } else {
+            sum.x += v[u].x; sum.y += v[u].y; sum.z += v[u].z; sum.w += v[u].w;
+            sq.x = fmaf(v[u].x, v[u].x, sq.x); sq.y = fmaf(v[u].y, v[u].y, sq.y);
+            sq.z = fmaf(v[u].z, v[u].z, sq.z); sq.w = fmaf(v[u].w, v[u].w, sq.w);
+            if (ostack && ex_ok && chunk_ok) stg4(ostack + (size_t)s * D, v[u]);
+          }
         }
       }
     }
@@ -142,7 +152,6 @@ __global__ void __launch_bounds__(512) embed_fm_fwd_kernel(const EmbedFwdParams 
     if (p.out_sum && ex_ok && chunk_ok) stg4(p.out_sum + (size_t)b * D + c * 4, sum);
 
     if (p.out_logit) {
-      float lin = 0.f;
       if (has_lin && ex_ok) {
         for (int s = c; s < S; s += LPR) {   // the LPR lanes split the S scalar gathers
           const int64_t id = (int64_t)my[s];
@@ -185,7 +194,8 @@ __global__ void __launch_bounds__(512) embed_fm_bwd_kernel(const EmbedBwdParams 
   const bool chunk_ok = (c * 4) < D;
   const bool has_fm = p.g_logit != nullptr;
   const bool has_gs = p.g_stack != nullptr;
-  const bool has_lin = p.grad_lin_ptrs != nullptr && has_fm;
+  const bool lin_lane = p.lin_in_row && has_fm && (c * 4 == D);
+  const bool has_lin = p.grad_lin_ptrs != nullptr && has_fm && !p.lin_in_row;
   const float scale = p.scale;
   const IdT* __restrict__ ids = reinterpret_cast<const IdT*>(p.ids);
 
@@ -238,12 +248,13 @@ __global__ void __launch_bounds__(512) embed_fm_bwd_kernel(const EmbedBwdParams 
         if (s >= S) break;     // warp-uniform
         int64_t id = -1;
         if (ex_ok) id = (int64_t)my[s];
-        const bool ok = ex_ok && chunk_ok && (uint64_t)id < (uint64_t)s_rows[s];
+        const bool ok = ex_ok && (chunk_ok || lin_lane) && (uint64_t)id < (uint64_t)s_rows[s];
         float4 d;
         d.x = scale * fmaf(gl, sum.x - e[u].x, gs[u].x);
         d.y = scale * fmaf(gl, sum.y - e[u].y, gs[u].y);
         d.z = scale * fmaf(gl, sum.z - e[u].z, gs[u].z);
         d.w = scale * fmaf(gl, sum.w - e[u].w, gs[u].w);
+        if (lin_lane) d = make_float4(scale * gl, 0.f, 0.f, 0.f);   // [dw | pad] rides in the same request
         bool leader = true;
         if (AGG && G > 1) {
           // lanes that target the same 16 B of the same table row are merged: the lowest
@@ -289,8 +300,8 @@ __global__ void __launch_bounds__(512) embed_fm_bwd_kernel(const EmbedBwdParams 
 }
 
 // ---- host-side dispatch -----------------------------------------------------------------
-static int lpr_for(int D) {
-  int chunks = D / 4, l = 1;
+static int lpr_for(int D, int lin_in_row = 0) {
+  int chunks = D / 4 + (lin_in_row ? 1 : 0), l = 1;
   while (l < chunks) l <<= 1;
   return l;
 }
@@ -371,7 +382,7 @@ static int launch_bwd(const EmbedBwdParams& p, cudaStream_t st) {
 
 #define DR_DISPATCH_LPR(FN, P, ST)                                      \
   do {                                                                  \
-    const int lpr__ = lpr_for((P).D);                                   \
+    const int lpr__ = lpr_for((P).D, (P).lin_in_row);                   \
     if (id_bytes == 8) {                                                \
       switch (lpr__) {                                                  \
         case 1: return FN<1, int64_t>(P, ST);                           \
@@ -408,7 +419,7 @@ using namespace dr;
 
 extern "C" int dr_embed_fm_fwd(const float* const* table_ptrs, const float* const* lin_ptrs,
                                const int64_t* rows, const void* ids, int id_bytes, const float* bias,
-                               int64_t B, int S, int D, int64_t row_stride, int64_t lin_stride,
+                               int64_t B, int S, int D, int64_t row_stride, int64_t lin_stride, int flags,
                                float* out_stack, float* out_sum, float* out_logit, void* stream) {
   if (int rc = check_dims("dr_embed_fm_fwd", B, S, D, id_bytes)) return rc;
   if (B == 0) return DR_OK;
@@ -419,20 +430,23 @@ extern "C" int dr_embed_fm_fwd(const float* const* table_ptrs, const float* cons
   DR_REQUIRE(row_stride >= D && row_stride % 4 == 0, DR_EINVAL,
              "dr_embed_fm_fwd: row_stride=%lld must be >= D and a multiple of 4", (long long)row_stride);
   DR_REQUIRE(lin_stride >= 1, DR_EINVAL, "dr_embed_fm_fwd: lin_stride=%lld < 1", (long long)lin_stride);
+  const int lin_in_row = (flags & DR_EMBED_LIN_IN_ROW) ? 1 : 0;
+  DR_REQUIRE(!lin_in_row || (row_stride >= D + 4 && D <= 124), DR_EINVAL,
+             "dr_embed_fm_fwd: DR_EMBED_LIN_IN_ROW needs row_stride >= D+4 and D <= 124");
   DR_REQUIRE(!out_stack || aligned16(out_stack), DR_EALIGN, "dr_embed_fm_fwd: out_stack not 16-B aligned");
   DR_REQUIRE(!out_sum || aligned16(out_sum), DR_EALIGN, "dr_embed_fm_fwd: out_sum not 16-B aligned");
   if (B == 0) return DR_OK;
   EmbedFwdParams p{};
   p.table_ptrs = table_ptrs; p.lin_ptrs = lin_ptrs; p.rows = rows; p.ids = ids; p.bias = bias;
   p.B = B; p.S = S; p.D = D; p.out_stack = out_stack; p.out_sum = out_sum; p.out_logit = out_logit;
-  p.row_stride = row_stride; p.lin_stride = lin_stride;
+  p.row_stride = row_stride; p.lin_stride = lin_stride; p.lin_in_row = lin_in_row;
   cudaStream_t st = (cudaStream_t)stream;
   DR_DISPATCH_LPR(launch_fwd, p, st);
 }
 
 extern "C" int dr_embed_fm_bwd(const void* ids, int id_bytes, const int64_t* rows, const float* stack,
                                const float* sum_e, const float* g_logit, const float* g_stack,
-                               int64_t B, int S, int D, int64_t row_stride, int64_t lin_stride,
+                               int64_t B, int S, int D, int64_t row_stride, int64_t lin_stride, int flags,
                                float* const* grad_table_ptrs, float* const* grad_lin_ptrs, float* g_bias,
                                float scale, void* stream) {
   if (int rc = check_dims("dr_embed_fm_bwd", B, S, D, id_bytes)) return rc;
@@ -447,11 +461,15 @@ extern "C" int dr_embed_fm_bwd(const void* ids, int id_bytes, const int64_t* row
   if (lin_stride == 0) lin_stride = 1;
   DR_REQUIRE(row_stride >= D && row_stride % 4 == 0 && lin_stride >= 1, DR_EINVAL,
              "dr_embed_fm_bwd: bad strides row=%lld lin=%lld", (long long)row_stride, (long long)lin_stride);
+  const int lin_in_row = (flags & DR_EMBED_LIN_IN_ROW) ? 1 : 0;
+  DR_REQUIRE(!lin_in_row || (row_stride >= D + 4 && D <= 124), DR_EINVAL,
+             "dr_embed_fm_bwd: DR_EMBED_LIN_IN_ROW needs row_stride >= D+4 and D <= 124");
   if (B == 0) return DR_OK;
   EmbedBwdParams p{};
   p.ids = ids; p.rows = rows; p.stack = stack; p.sum_e = sum_e; p.g_logit = g_logit; p.g_stack = g_stack;
   p.B = B; p.S = S; p.D = D; p.grad_table_ptrs = grad_table_ptrs; p.grad_lin_ptrs = grad_lin_ptrs;
   p.g_bias = g_bias; p.scale = scale; p.row_stride = row_stride; p.lin_stride = lin_stride;
+  p.lin_in_row = lin_in_row;
   cudaStream_t st = (cudaStream_t)stream;
   DR_DISPATCH_LPR(launch_bwd, p, st);
 }

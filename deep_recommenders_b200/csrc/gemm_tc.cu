@@ -120,6 +120,36 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict
   }
 }
 
+// x [R, C] row-major (pitch ldx)  ->  hi, lo [C, R] row-major (pitch ldo): transposed hi/lo planes,
+// so that every tensor-core operand is K-major (the operand layout validated on hardware).
+__global__ void __launch_bounds__(256) split_tf32_transpose_kernel(const float* __restrict__ x, int64_t R,
+                                                                    int64_t C, int64_t ldx, int64_t ldo,
+                                                                    float* __restrict__ hi, float* __restrict__ lo) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;   // (32, 8)
+  const int64_t tiles_c = (C + 31) / 32, tiles_r = (R + 31) / 32;
+  for (int64_t t = blockIdx.x; t < tiles_c * tiles_r; t += gridDim.x) {
+    const int64_t r0 = (t / tiles_c) * 32, c0 = (t % tiles_c) * 32;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t r = r0 + ty + 8 * i, c = c0 + tx;
+      tile[ty + 8 * i][tx] = (r < R && c < C) ? __ldg(x + r * ldx + c) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t c = c0 + ty + 8 * i, r = r0 + tx;
+      if (c < C && r < R) {
+        const float v = tile[tx][ty + 8 * i];
+        const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+        hi[c * ldo + r] = h;
+        lo[c * ldo + r] = v - h;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 __device__ __forceinline__ float epi_scalar_tc(const GemmArgs& a, float acc, int64_t m, int64_t n) {
   const int64_t off = m * a.ldc + n;
   switch (a.epi) {
@@ -340,28 +370,63 @@ static int make_map(CUtensorMap* tm, const float* base, int64_t inner, int64_t o
   return DR_OK;
 }
 
+static inline int64_t round4(int64_t v) { return (v + 3) & ~(int64_t)3; }
+
+// Sizes (floats) of the K-major hi/lo planes: A -> [M, pitch], B -> [N, pitch].  An operand that is
+// already K-major keeps its source pitch (one flat float4 pass); a transposed one gets round4(K).
+static void plane_elems(const GemmArgs& a, bool ta, bool tb, size_t* ae, size_t* be) {
+  const int64_t kp = round4(a.K);
+  *ae = (size_t)a.M * (size_t)(!ta ? a.lda : kp);
+  *be = (size_t)a.N * (size_t)(tb ? a.ldb : kp);
+}
+
 bool gemm_tc_eligible(const GemmArgs& a, bool ta, bool tb) {
   if (g_tune_gemm_variant != 1) return false;
   if (a.N < 96 || a.M < 64 || a.K < 32) return false;
-  if ((a.lda & 3) || (a.ldb & 3) || !aligned16(a.A) || !aligned16(a.B)) return false;
-  const size_t a_elems = (size_t)(ta ? a.K : a.M) * (size_t)a.lda;
-  const size_t b_elems = (size_t)(tb ? a.N : a.K) * (size_t)a.ldb;
-  if ((a_elems & 3) || (b_elems & 3)) return false;
-  const size_t need = (a_elems + b_elems) * 2 * sizeof(float) + 4096;
+  // operands already K-major are split in place with float4 accesses
+  if (!ta && ((a.lda & 3) || !aligned16(a.A))) return false;
+  if (tb && ((a.ldb & 3) || !aligned16(a.B))) return false;
+  size_t ae, be;
+  plane_elems(a, ta, tb, &ae, &be);
+  const size_t need = (ae + be) * 2 * sizeof(float) + 4096;
   if (!g_ws_ptr || g_ws_bytes < need) return false;
-  if (a.M >= ((int64_t)1 << 31) || a.K >= ((int64_t)1 << 31)) return false;
+  if (a.M >= ((int64_t)1 << 31) || a.K >= ((int64_t)1 << 31) || a.N >= ((int64_t)1 << 31)) return false;
   return true;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN>
 static int launch_tc(const CUtensorMap* tms, const GemmArgs& a, cudaStream_t st) {
   constexpr int STAGE = 2 * TC_BM * TC_BK * 4 + 2 * BN * TC_BK * 4;
   const size_t smem = (size_t)TC_STAGES * STAGE + 1024;
-  auto k = gemm_tc_kernel<BN, A_MN, B_MN>;
+  auto k = gemm_tc_kernel<BN, false, false>;
   DR_CUDA_CALL(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)((a.M + TC_BM - 1) / TC_BM), (unsigned)((a.N + BN - 1) / BN), (unsigned)a.splitk);
   k<<<grid, TC_THREADS, smem, st>>>(tms[0], tms[1], tms[2], tms[3], a);
   DR_CUDA_LAUNCH_CHECK("gemm_tc");
+  return DR_OK;
+}
+
+// Produce K-major hi/lo planes [rows, pitch] of an operand.  `stored_k_major`: src is [rows, K] with
+// pitch ld (flat split, same pitch); otherwise src is [K, rows] with pitch ld (transpose-split).
+static int make_planes(const float* src, bool stored_k_major, int64_t rows, int64_t K, int64_t ld, float* hi,
+                       float* lo, int64_t* pitch_out, cudaStream_t st) {
+  if (stored_k_major) {
+    const int64_t n4 = rows * ld / 4;
+    int64_t ctas = (n4 + 255) / 256;
+    if (ctas > kNumSMs * 8) ctas = kNumSMs * 8;
+    if (ctas < 1) ctas = 1;
+    split_tf32_kernel<<<(unsigned)ctas, 256, 0, st>>>(src, n4, hi, lo);
+    DR_CUDA_LAUNCH_CHECK("split_tf32");
+    *pitch_out = ld;
+  } else {
+    const int64_t kp = round4(K);
+    const int64_t tiles = ((K + 31) / 32) * ((rows + 31) / 32);
+    int64_t ctas = tiles < (int64_t)kNumSMs * 16 ? tiles : (int64_t)kNumSMs * 16;
+    if (ctas < 1) ctas = 1;
+    split_tf32_transpose_kernel<<<(unsigned)ctas, dim3(32, 8), 0, st>>>(src, K, rows, ld, kp, hi, lo);
+    DR_CUDA_LAUNCH_CHECK("split_tf32_transpose");
+    *pitch_out = kp;
+  }
   return DR_OK;
 }
 
@@ -371,46 +436,26 @@ int gemm_tc_launch(const GemmArgs& a0, bool ta, bool tb, cudaStream_t st) {
   if (a.splitk < 1) a.splitk = 1;
   const int64_t kblocks = (a.K + TC_BK - 1) / TC_BK;
   if (a.splitk > kblocks) a.splitk = (int)kblocks;
-  // hi/lo planes in the registered workspace
-  const size_t a_elems = (size_t)(ta ? a.K : a.M) * (size_t)a.lda;
-  const size_t b_elems = (size_t)(tb ? a.N : a.K) * (size_t)a.ldb;
+  size_t ae, be;
+  plane_elems(a, ta, tb, &ae, &be);
+  const size_t need = (ae + be) * 2 * sizeof(float);
+  DR_REQUIRE(g_ws_ptr && g_ws_bytes >= need, DR_EINVAL, "gemm_tc: workspace too small (%zu needed)", need);
   float* Ah = reinterpret_cast<float*>(g_ws_ptr);
-  float* Al = Ah + a_elems;
-  float* Bh = Al + a_elems;
-  float* Bl = Bh + b_elems;
-  auto split = [&](const float* x, size_t n, float* hi, float* lo) -> int {
-    int64_t n4 = (int64_t)(n / 4);
-    int64_t ctas = (n4 + 255) / 256;
-    if (ctas > kNumSMs * 8) ctas = kNumSMs * 8;
-    split_tf32_kernel<<<(unsigned)ctas, 256, 0, st>>>(x, n4, hi, lo);
-    DR_CUDA_LAUNCH_CHECK("split_tf32");
-    return DR_OK;
-  };
-  if (int rc = split(a.A, a_elems, Ah, Al)) return rc;
-  if (int rc = split(a.B, b_elems, Bh, Bl)) return rc;
-  // A(m,k): !ta -> stored [M,K] (K-major), ta -> stored [K,M] (MN-major)
-  // B(k,n): !tb -> stored [K,N] (MN-major), tb -> stored [N,K] (K-major)
-  const bool A_MN = ta, B_MN = !tb;
-  CUtensorMap tms[4];
-  if (!A_MN) {
-    if (int rc = make_map(&tms[0], Ah, a.K, a.M, a.lda, TC_BM)) return rc;
-    if (int rc = make_map(&tms[1], Al, a.K, a.M, a.lda, TC_BM)) return rc;
-  } else {
-    if (int rc = make_map(&tms[0], Ah, a.M, a.K, a.lda, TC_BK)) return rc;
-    if (int rc = make_map(&tms[1], Al, a.M, a.K, a.lda, TC_BK)) return rc;
-  }
+  float* Al = Ah + ae;
+  float* Bh = Al + ae;
+  float* Bl = Bh + be;
+  int64_t pa = 0, pb = 0;
+  // A(m,k): !ta -> stored [M,K] (already K-major);  ta -> stored [K,M] -> transpose
+  if (int rc = make_planes(a.A, !ta, a.M, a.K, a.lda, Ah, Al, &pa, st)) return rc;
+  // B(k,n):  tb -> stored [N,K] (already K-major); !tb -> stored [K,N] -> transpose
+  if (int rc = make_planes(a.B, tb, a.N, a.K, a.ldb, Bh, Bl, &pb, st)) return rc;
   constexpr int BN = 128;
-  if (!B_MN) {
-    if (int rc = make_map(&tms[2], Bh, a.K, a.N, a.ldb, BN)) return rc;
-    if (int rc = make_map(&tms[3], Bl, a.K, a.N, a.ldb, BN)) return rc;
-  } else {
-    if (int rc = make_map(&tms[2], Bh, a.N, a.K, a.ldb, TC_BK)) return rc;
-    if (int rc = make_map(&tms[3], Bl, a.N, a.K, a.ldb, TC_BK)) return rc;
-  }
-  if (!A_MN && B_MN) return launch_tc<BN, false, true>(tms, a, st);
-  if (!A_MN && !B_MN) return launch_tc<BN, false, false>(tms, a, st);
-  if (A_MN && B_MN) return launch_tc<BN, true, true>(tms, a, st);
-  return launch_tc<BN, true, false>(tms, a, st);
+  CUtensorMap tms[4];
+  if (int rc = make_map(&tms[0], Ah, a.K, a.M, pa, TC_BM)) return rc;
+  if (int rc = make_map(&tms[1], Al, a.K, a.M, pa, TC_BM)) return rc;
+  if (int rc = make_map(&tms[2], Bh, a.K, a.N, pb, BN)) return rc;
+  if (int rc = make_map(&tms[3], Bl, a.K, a.N, pb, BN)) return rc;
+  return launch_tc<BN>(tms, a, st);
 }
 
 }  // namespace dr

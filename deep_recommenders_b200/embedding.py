@@ -58,6 +58,7 @@ class EmbeddingCollection(nn.Module):
             raise ValueError("layout='fused' packs [emb | w] into one 128-B line: needs D <= 28")
         self.row_stride = 32 if self.layout == "fused" else self.dim
         self.lin_stride = self.row_stride if self.layout == "fused" else 1
+        self.flags = 1 if self.layout == "fused" else 0      # DR_EMBED_LIN_IN_ROW
         std = init_stddev if init_stddev is not None else 1.0 / math.sqrt(self.dim)
         w = torch.zeros((self.total_rows, self.row_stride), dtype=torch.float32, device=dev)
         if init == "truncated_normal":

@@ -73,7 +73,7 @@ class EmbedFM(torch.autograd.Function):
         check(lib.dr_embed_fm_fwd(tp.data_ptr(), lp.data_ptr() if has_lin else None,
                                   rows.data_ptr(), ids.data_ptr(), ids.element_size(),
                                   _ptr(bias) if want_logit else None, B, S, D, meta.row_stride, meta.lin_stride,
-                                  stack.data_ptr(), _ptr(sum_e), _ptr(logit), _stream()), "dr_embed_fm_fwd")
+                                  meta.flags if has_lin else 0, stack.data_ptr(), _ptr(sum_e), _ptr(logit), _stream()), "dr_embed_fm_fwd")
         ctx.meta = meta
         ctx.want_logit = want_logit
         ctx.has_lin = has_lin
@@ -112,7 +112,8 @@ class EmbedFM(torch.autograd.Function):
         with torch.no_grad():
             check(lib.dr_embed_fm_bwd(ids.data_ptr(), ids.element_size(), rows.data_ptr(),
                                       stack.data_ptr(), _ptr(sum_e), _ptr(g_logit), _ptr(g_stack),
-                                      B, S, D, meta.row_stride, meta.lin_stride, tp.data_ptr(),
+                                      B, S, D, meta.row_stride, meta.lin_stride,
+                                      meta.flags if lin_grad else 0, tp.data_ptr(),
                                       lp.data_ptr() if lin_grad else None,
                                       _ptr(gb) if g_logit is not None else None, scale, _stream()),
                   "dr_embed_fm_bwd")
@@ -198,6 +199,7 @@ class DenseFn(torch.autograd.Function):
         if w.shape[0] != K:
             raise ValueError(f"Dense: input dim {K} does not match kernel {tuple(w.shape)}")
         N = w.shape[1]
+        _lib.ensure_gemm_workspace(M, K, N, x.device)
         y = torch.empty((M, N), device=x.device, dtype=torch.float32)
         check(lib.dr_dense_fwd(x2.data_ptr(), w.data_ptr(), _ptr(b), M, K, N, act, y.data_ptr(), _stream()),
               "dr_dense_fwd")
@@ -239,6 +241,7 @@ class CrossFn(torch.autograd.Function):
         x_2 = x.reshape(-1, d)
         B = x0_2.shape[0]
         r = 0 if w is not None else uk.shape[1]
+        _lib.ensure_gemm_workspace(B, d, d, x0.device)
         y = torch.empty((B, d), device=x0.device, dtype=torch.float32)
         u = torch.empty((B, d), device=x0.device, dtype=torch.float32)
         xu = torch.empty((B, r), device=x0.device, dtype=torch.float32) if r else None
@@ -331,6 +334,7 @@ def scores(q, c, sampling_prob=None, cand_ids=None) -> torch.Tensor:
     nc = c.shape[0]
     p = None if sampling_prob is None else _f32(sampling_prob, "p").reshape(nc)
     ids = None if cand_ids is None else cand_ids.to(torch.int64).contiguous().reshape(nc)
+    _lib.ensure_gemm_workspace(nq, D, nc, q.device)
     out = torch.empty((nq, nc), device=q.device, dtype=torch.float32)
     check(lib.dr_scores_fwd(q.data_ptr(), c.data_ptr(), _ptr(p), _ptr(ids), nq, nc, D, out.data_ptr(), _stream()),
           "dr_scores_fwd")

@@ -122,6 +122,8 @@ class ShardedDeepFMTrainStep:
         self.gtp = torch.full((S,), gbase, device=dev, dtype=torch.int64)
         self.glp = torch.full((S,), gbase + D * 4, device=dev, dtype=torch.int64)
         self.trows = torch.full((S,), G * self.cap, device=dev, dtype=torch.int64)
+        kmax = max([S * D] + [l.units for l in layers])
+        _lib.ensure_gemm_workspace(B, kmax, kmax, dev)
         self.graph = None
         self.launches_per_step = None
         self._copy_stream = torch.cuda.Stream(device=dev)
@@ -148,7 +150,7 @@ class ShardedDeepFMTrainStep:
         self._a2a(self.vec_recv, self.vec_send)
         mark("a2a_vectors")
         check(lib.dr_embed_fm_fwd(self.tp.data_ptr(), self.lp.data_ptr(), self.trows.data_ptr(), self.inv.data_ptr(), 4,
-                                  self.bias.data_ptr(), B, S, D, V, V, self.stack.data_ptr(), self.sum_e.data_ptr(),
+                                  self.bias.data_ptr(), B, S, D, V, V, 1, self.stack.data_ptr(), self.sum_e.data_ptr(),
                                   self.fm_logit.data_ptr(), st), "dr_embed_fm_fwd")
         mark("embed_fm_fwd")
         x, K = self.stack, S * D
@@ -174,7 +176,7 @@ class ShardedDeepFMTrainStep:
         self.grad_send.zero_()
         self.g_bias.zero_()
         check(lib.dr_embed_fm_bwd(self.inv.data_ptr(), 4, self.trows.data_ptr(), self.stack.data_ptr(),
-                                  self.sum_e.data_ptr(), gz.data_ptr(), self.g_stack.data_ptr(), B, S, D, V, V,
+                                  self.sum_e.data_ptr(), gz.data_ptr(), self.g_stack.data_ptr(), B, S, D, V, V, 1,
                                   self.gtp.data_ptr(), self.glp.data_ptr(), self.g_bias.data_ptr(), 1.0, st),
               "dr_embed_fm_bwd")
         mark("embed_fm_bwd_pack")

@@ -89,6 +89,8 @@ class DeepFMTrainStep:
         self.loss = torch.zeros((1,), **f)
         self.prob = torch.empty((B,), **f)
         self.tp, self.lp, self.rows = coll.pointers(coll.weight, coll.linear)
+        kmax = max([S * D] + [l.units for l in layers])
+        _lib.ensure_gemm_workspace(B, kmax, kmax, dev)
         self.graph = None
         self.use_graph = use_graph
         self._copy_stream = torch.cuda.Stream(device=dev)
@@ -106,7 +108,7 @@ class DeepFMTrainStep:
         mark("start")
         check(lib.dr_embed_fm_fwd(self.tp.data_ptr(), self.lp.data_ptr(), self.rows.data_ptr(), self.ids.data_ptr(),
                                   self.ids.element_size(), c.bias.data_ptr(), B, S, D, c.row_stride, c.lin_stride,
-                                  self.stack.data_ptr(),
+                                  c.flags, self.stack.data_ptr(),
                                   self.sum_e.data_ptr(), self.fm_logit.data_ptr(), st), "dr_embed_fm_fwd")
         mark("embed_fm_fwd")
         x = self.stack
@@ -131,7 +133,7 @@ class DeepFMTrainStep:
             mark(f"dense_bwd_{i}")
         check(lib.dr_embed_fm_bwd(self.ids.data_ptr(), self.ids.element_size(), self.rows.data_ptr(),
                                   self.stack.data_ptr(), self.sum_e.data_ptr(), gz.data_ptr(), self.g_stack.data_ptr(),
-                                  B, S, D, c.row_stride, c.lin_stride, self.tp.data_ptr(), self.lp.data_ptr(),
+                                  B, S, D, c.row_stride, c.lin_stride, c.flags, self.tp.data_ptr(), self.lp.data_ptr(),
                                   c.bias.data_ptr(), -self.lr, st),
               "dr_embed_fm_bwd")
         mark("embed_fm_bwd")

@@ -33,6 +33,11 @@ extern "C" {
 #define DR_EALIGN (-2)     /* a row base or tensor base is not 16-byte aligned   */
 #define DR_ENOTSUP (-3)    /* valid request this build does not implement        */
 
+/* dr_embed_fm_* flags */
+#define DR_EMBED_LIN_IN_ROW 1   /* first-order weight of an id is stored IN its row, at float index D
+                                   (row_stride >= D+4): it is fetched by the same 128-bit request as the
+                                   embedding chunks; lin_ptrs / lin_stride are ignored                  */
+
 /* activation codes (tf.keras.layers.Dense(activation=...)) */
 #define DR_ACT_NONE 0
 #define DR_ACT_RELU 1
@@ -67,7 +72,7 @@ uint64_t dr_launch_count(void);
  * ------------------------------------------------------------------------------------- */
 int dr_embed_fm_fwd(const float* const* table_ptrs, const float* const* lin_ptrs,
                     const int64_t* rows, const void* ids, int id_bytes, const float* bias,
-                    int64_t B, int S, int D, int64_t row_stride, int64_t lin_stride,
+                    int64_t B, int S, int D, int64_t row_stride, int64_t lin_stride, int flags,
                     float* out_stack, float* out_sum, float* out_logit, void* stream);
 
 /* Backward of the above fused with the sparse update ("IndexedSlices" scatter-add):
@@ -83,7 +88,7 @@ int dr_embed_fm_fwd(const float* const* table_ptrs, const float* const* lin_ptrs
 int dr_embed_fm_bwd(const void* ids, int id_bytes, const int64_t* rows,
                     const float* stack, const float* sum_e,
                     const float* g_logit, const float* g_stack,
-                    int64_t B, int S, int D, int64_t row_stride, int64_t lin_stride,
+                    int64_t B, int S, int D, int64_t row_stride, int64_t lin_stride, int flags,
                     float* const* grad_table_ptrs, float* const* grad_lin_ptrs, float* g_bias,
                     float scale, void* stream);
 
@@ -218,6 +223,9 @@ int dr_set_workspace(void* ptr, uint64_t bytes);
 /* Developer hook (not reference-facing): set a kernel tuning knob by name, e.g.
  * "embed_fwd_unroll", "embed_block", "embed_bwd_agg", "gemm_splitk".                     */
 int dr_tune_set(const char* key, int value);
+/* Developer hook: C[M,N] = op(A) @ op(B); transA: A stored [K,M]; transB: B stored [N,K].  */
+int dr_debug_gemm(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
+                  int transA, int transB, void* stream);
 
 #ifdef __cplusplus
 }

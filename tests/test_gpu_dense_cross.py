@@ -13,6 +13,18 @@ from oracle import reference_np as R
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["ffma", "tc"])
+def gemm_variant(request):
+    """Every test in this file runs under both GEMM variants: FFMA and tcgen05 3xTF32."""
+    from deep_recommenders_b200 import _lib
+    if request.param == "tc":
+        _lib.enable_tensor_core_gemm()
+    else:
+        _lib.disable_tensor_core_gemm()
+    yield request.param
+    _lib.enable_tensor_core_gemm()
+
+
 def cu(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 

@@ -256,6 +256,6 @@ def test_full_size_c2_properties():
     tp, lp, rws = coll.pointers(gw, None, cache=False)
     from deep_recommenders_b200 import _lib
     _lib.check(_lib.load().dr_embed_fm_bwd(ids.data_ptr(), 8, rws.data_ptr(), None, None, None, g.data_ptr(),
-                                           B, S, D, coll.row_stride, coll.lin_stride, tp.data_ptr(), None, None, 1.0,
+                                           B, S, D, coll.row_stride, coll.lin_stride, 0, tp.data_ptr(), None, None, 1.0,
                                            torch.cuda.current_stream().cuda_stream), "bwd")
     assert float(gw.sum()) == float(B * S * D)

@@ -82,12 +82,13 @@ def test_bucket_kernel_against_numpy_twin():
     cap = shard_plan.capacity(B * S, G, slack=1.0, floor=16)
     t = lambda a, dt: torch.tensor(a, dtype=dt, device="cuda")
     idt = t(ids, torch.int64)
+    offs_t, rows_t = t(offs, torch.int64), t(rows, torch.int64)     # keep alive: raw pointers are passed
     counts = torch.zeros(G, dtype=torch.int64, device="cuda")
     send = torch.empty(G * cap, dtype=torch.int64, device="cuda")
     inv = torch.empty(B * S, dtype=torch.int32, device="cuda")
     ovf = torch.zeros(1, dtype=torch.int32, device="cuda")
-    _lib.check(lib.dr_shard_bucket_ids(idt.data_ptr(), 8, B * S, S, t(offs, torch.int64).data_ptr(),
-                                       t(rows, torch.int64).data_ptr(), G, cap, counts.data_ptr(), send.data_ptr(),
+    _lib.check(lib.dr_shard_bucket_ids(idt.data_ptr(), 8, B * S, S, offs_t.data_ptr(),
+                                       rows_t.data_ptr(), G, cap, counts.data_ptr(), send.data_ptr(),
                                        inv.data_ptr(), ovf.data_ptr(), torch.cuda.current_stream().cuda_stream), "bucket")
     rsend, rinv, rcounts, rovf = shard_np.bucket_ids(ids, offs, rows, G, cap)
     assert int(ovf) == int(rovf) == 0
@@ -103,8 +104,8 @@ def test_bucket_kernel_against_numpy_twin():
     assert np.array_equal(inv >= 0, live)
     assert len(np.unique(inv[live])) == int(live.sum())
     # overflow is reported, not silently dropped
-    _lib.check(lib.dr_shard_bucket_ids(idt.data_ptr(), 8, B * S, S, t(offs, torch.int64).data_ptr(),
-                                       t(rows, torch.int64).data_ptr(), G, 8, counts.data_ptr(), send.data_ptr(),
+    _lib.check(lib.dr_shard_bucket_ids(idt.data_ptr(), 8, B * S, S, offs_t.data_ptr(),
+                                       rows_t.data_ptr(), G, 8, counts.data_ptr(), send.data_ptr(),
                                        inv.data_ptr(), ovf.data_ptr(), torch.cuda.current_stream().cuda_stream), "bucket")
     assert int(ovf) == 1
 

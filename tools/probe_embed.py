@@ -51,7 +51,7 @@ def main():
     for D, rows, layout, idb in ((16, 1_000_000, "fused", 8), (16, 1_000_000, "split", 8),
                                  (16, 20_000, "split", 8), (32, 1_000_000, "fused", 8), (32, 1_000_000, "split", 8),
                                  (128, 200_000, "split", 8)):
-        if ncu_mode and not (D == 16 and rows == 1_000_000 and layout == "split" and idb == 8):
+        if ncu_mode and not (D == 16 and rows == 1_000_000 and layout == "fused" and idb == 8):
             continue
         coll = EmbeddingCollection([rows] * S, D, device="cuda", seed=1, layout=layout)
         gen = torch.Generator(device="cuda").manual_seed(0)
@@ -68,7 +68,7 @@ def main():
             k = i % NP
             _lib.check(lib.dr_embed_fm_fwd(tp.data_ptr(), lp.data_ptr() if lin else None, rws.data_ptr(),
                                            ids_pool[k].data_ptr(), idb, coll.bias.data_ptr(), B, S, D,
-                                           coll.row_stride, coll.lin_stride,
+                                           coll.row_stride, coll.lin_stride, coll.flags if lin else 0,
                                            stacks[k].data_ptr() if stack else None,
                                            sums[k].data_ptr() if sume else None,
                                            logits[k].data_ptr() if logit else None, st), "fwd")
@@ -78,7 +78,7 @@ def main():
             _lib.check(lib.dr_embed_fm_bwd(ids_pool[k].data_ptr(), idb, rws.data_ptr(), stacks[k].data_ptr(),
                                            sums[k].data_ptr(), gl.data_ptr() if fm else None,
                                            gs[k].data_ptr() if gstack else None, B, S, D, coll.row_stride,
-                                           coll.lin_stride, tp.data_ptr(), lp.data_ptr() if lin else None,
+                                           coll.lin_stride, coll.flags if lin else 0, tp.data_ptr(), lp.data_ptr() if lin else None,
                                            coll.bias.data_ptr(), -1e-6, st), "bwd")
 
         if ncu_mode:

@@ -59,7 +59,7 @@ def main():
         def fwd(i):
             k = i % NP
             _lib.check(lib.dr_embed_fm_fwd(tp.data_ptr(), lp.data_ptr(), rws.data_ptr(), ids_pool[k].data_ptr(), idb,
-                                           coll.bias.data_ptr(), B, S, D, coll.row_stride, coll.lin_stride, stacks[k].data_ptr(), sums[k].data_ptr(),
+                                           coll.bias.data_ptr(), B, S, D, coll.row_stride, coll.lin_stride, coll.flags, stacks[k].data_ptr(), sums[k].data_ptr(),
                                            logits[k].data_ptr(), st), "fwd")
 
         gl = torch.randn(B, device="cuda") * 1e-3
@@ -68,7 +68,7 @@ def main():
         def bwd(i):
             k = i % NP
             _lib.check(lib.dr_embed_fm_bwd(ids_pool[k].data_ptr(), idb, rws.data_ptr(), stacks[k].data_ptr(),
-                                           sums[k].data_ptr(), gl.data_ptr(), gs[k].data_ptr(), B, S, D, coll.row_stride, coll.lin_stride,
+                                           sums[k].data_ptr(), gl.data_ptr(), gs[k].data_ptr(), B, S, D, coll.row_stride, coll.lin_stride, coll.flags,
                                            tp.data_ptr(), lp.data_ptr(), coll.bias.data_ptr(), -1e-6, st), "bwd")
 
         for block, unroll, cps in itertools.product((128, 256, 512), (2, 4, 8, 13, 26), (0,)):
