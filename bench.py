@@ -133,6 +133,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly (for ncu launch lists)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -166,7 +167,7 @@ def main():
     else:
         model = DeepFM([fc.indicator_column(c) for c in cols], [fc.embedding_column(c, D) for c in cols],
                        dnn_units_size=C2["dnn"], seed=1, device=dev, sparse_lr=0.01)
-        trainer = DeepFMTrainStep(model, batch_size=B, lr=0.01).capture()
+        trainer = DeepFMTrainStep(model, batch_size=B, lr=0.01, use_graph=not args.no_graph).capture()
 
     # synthetic MovieLens-shaped batches: pool resident in HBM (value) and in pinned host memory (e2e)
     NP = 8

@@ -24,7 +24,8 @@ int g_tune_embed_fwd_unroll = 0;      // 0 = default per LPR
 int g_tune_embed_bwd_unroll = 0;
 int g_tune_embed_block = 256;         // threads per CTA
 int g_tune_embed_ctas_per_sm = 0;     // 0 = as many as fit (2048 threads / SM)
-int g_tune_embed_bwd_agg = 1;         // warp-aggregate duplicate ids before the atomics
+int g_tune_embed_bwd_agg = 1;         // example-parallel mode: warp-aggregate duplicate ids before the atomics
+int g_tune_embed_bwd_mode = 0;        // 0 = slot-parallel (default), 1 = example-parallel (+ optional aggregation)
 
 struct EmbedFwdParams {
   const float* const* table_ptrs;
@@ -299,6 +300,106 @@ __global__ void __launch_bounds__(512) embed_fm_bwd_kernel(const EmbedBwdParams 
   }
 }
 
+// Backward, slot-parallel mapping (default).  A warp walks ONE example at a time: its 32/LPR lane
+// groups take 32/LPR consecutive SLOTS of that example, so
+//   * the saved stack and the upstream g_stack are read as one contiguous run per instruction
+//     ((32/LPR) rows x D floats), the ids of the example as one contiguous run,
+//   * the lookups a warp issues together belong to DIFFERENT tables and can never collide, so no
+//     intra-warp duplicate detection is needed before the vector atomics (duplicates across warps
+//     are resolved by the L2 atomic unit),
+//   * no shared-memory staging and no cross-lane reduction: sum_e arrives precomputed.
+// U slot-steps are loaded before any atomic is issued (the red.global asm is a compiler barrier).
+template <int LPR, typename IdT, int U>
+__global__ void __launch_bounds__(256) embed_fm_bwd_sp_kernel(const EmbedBwdParams p) {
+  constexpr int SPW = 32 / LPR;      // slots per warp-instruction
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ float s_bias_part[8];
+  const int S = p.S, D = p.D;
+  float** s_tab = reinterpret_cast<float**>(smem_raw);
+  float** s_lin = s_tab + S;
+  int64_t* s_rows = reinterpret_cast<int64_t*>(s_lin + S);
+  for (int i = threadIdx.x; i < S; i += blockDim.x) {
+    s_tab[i] = p.grad_table_ptrs ? p.grad_table_ptrs[i] : p.single_grad;
+    s_lin[i] = p.grad_lin_ptrs ? p.grad_lin_ptrs[i] : nullptr;
+    s_rows[i] = p.rows ? p.rows[i] : p.single_rows;
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp_in_cta = threadIdx.x >> 5, warps_per_cta = blockDim.x >> 5;
+  const int c = lane % LPR, sg = lane / LPR;
+  const bool chunk_ok = (c * 4) < D;
+  const bool has_fm = p.g_logit != nullptr, has_gs = p.g_stack != nullptr;
+  const bool lin_lane = p.lin_in_row && has_fm && (c * 4 == D);
+  const bool has_lin = p.grad_lin_ptrs != nullptr && has_fm && !p.lin_in_row;
+  const float scale = p.scale;
+  const IdT* __restrict__ ids = reinterpret_cast<const IdT*>(p.ids);
+  const int64_t warp0 = (int64_t)blockIdx.x * warps_per_cta + warp_in_cta;
+  const int64_t nwarps = (int64_t)gridDim.x * warps_per_cta;
+  float bias_acc = 0.f;
+
+  for (int64_t b = warp0; b < p.B; b += nwarps) {
+    const float gl = has_fm ? __ldg(p.g_logit + b) : 0.f;
+    if (lane == 0) bias_acc += gl;
+    float4 sum = f4_zero();
+    if (has_fm && chunk_ok) {
+      if (p.sum_e) {
+        sum = ldg4(p.sum_e + (size_t)b * D + c * 4);
+      } else {
+        for (int s = 0; s < S; ++s) sum = f4_add(sum, ldg4(p.stack + ((size_t)b * S + s) * D + c * 4));
+      }
+    }
+    const IdT* my_ids = ids + (size_t)b * S;
+    const size_t ex0 = (size_t)b * S * D + c * 4;
+    for (int s0 = 0; s0 < S; s0 += SPW * U) {
+      float4 e[U], gs[U];
+      int64_t id[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int s = s0 + u * SPW + sg;
+        e[u] = f4_zero();
+        gs[u] = f4_zero();
+        id[u] = -1;
+        if (s < S) {
+          id[u] = (int64_t)__ldg(my_ids + s);
+          if (chunk_ok) {
+            if (has_fm) e[u] = ldg_nc_na(p.stack + ex0 + (size_t)s * D);
+            if (has_gs) gs[u] = ldg_nc_na(p.g_stack + ex0 + (size_t)s * D);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int s = s0 + u * SPW + sg;
+        if (s < S && (uint64_t)id[u] < (uint64_t)s_rows[s]) {
+          float* row = s_tab[s] + (size_t)id[u] * p.row_stride;
+          if (chunk_ok) {
+            float4 d;
+            d.x = scale * fmaf(gl, sum.x - e[u].x, gs[u].x);
+            d.y = scale * fmaf(gl, sum.y - e[u].y, gs[u].y);
+            d.z = scale * fmaf(gl, sum.z - e[u].z, gs[u].z);
+            d.w = scale * fmaf(gl, sum.w - e[u].w, gs[u].w);
+            red_add_v4(row + c * 4, d);
+          } else if (lin_lane) {
+            red_add_v4(row + c * 4, make_float4(scale * gl, 0.f, 0.f, 0.f));
+          }
+          if (has_lin && c == 0) red_add_f32(s_lin[s] + (size_t)id[u] * p.lin_stride, scale * gl);
+        }
+      }
+    }
+  }
+
+  if (p.g_bias && has_fm) {
+    bias_acc = group_sum<32>(bias_acc);
+    if (lane == 0) s_bias_part[warp_in_cta] = bias_acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int w = 0; w < warps_per_cta; ++w) t += s_bias_part[w];
+      red_add_f32(p.g_bias, scale * t);
+    }
+  }
+}
+
 // ---- host-side dispatch -----------------------------------------------------------------
 static int lpr_for(int D, int lin_in_row = 0) {
   int chunks = D / 4 + (lin_in_row ? 1 : 0), l = 1;
@@ -368,8 +469,28 @@ static int launch_bwd_u(const EmbedBwdParams& p, cudaStream_t st) {
   return DR_OK;
 }
 
+template <int LPR, typename IdT, int U>
+static int launch_bwd_sp_u(const EmbedBwdParams& p, cudaStream_t st) {
+  const int threads = 256, warps = threads / 32;
+  const size_t smem = (size_t)p.S * (sizeof(void*) * 2 + sizeof(int64_t));
+  int64_t ctas = (p.B + warps - 1) / warps;
+  int per_sm = g_tune_embed_ctas_per_sm > 0 ? g_tune_embed_ctas_per_sm : 8;
+  if (ctas > (int64_t)kNumSMs * per_sm) ctas = (int64_t)kNumSMs * per_sm;
+  if (ctas < 1) ctas = 1;
+  embed_fm_bwd_sp_kernel<LPR, IdT, U><<<(unsigned)ctas, threads, smem, st>>>(p);
+  DR_CUDA_LAUNCH_CHECK("embed_fm_bwd_sp");
+  return DR_OK;
+}
+
 template <int LPR, typename IdT>
 static int launch_bwd(const EmbedBwdParams& p, cudaStream_t st) {
+  if (g_tune_embed_bwd_mode == 0) {
+    switch (g_tune_embed_bwd_unroll) {
+      case 1: return launch_bwd_sp_u<LPR, IdT, 1>(p, st);
+      case 4: return launch_bwd_sp_u<LPR, IdT, 4>(p, st);
+      default: return launch_bwd_sp_u<LPR, IdT, 2>(p, st);
+    }
+  }
   int U = g_tune_embed_bwd_unroll;
   if (U <= 0) U = 4;
   switch (U) {

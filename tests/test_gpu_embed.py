@@ -127,9 +127,12 @@ BWD_CASES = [
 
 
 @pytest.mark.parametrize("B,rows,D", BWD_CASES)
-@pytest.mark.parametrize("agg,layout", [(1, "fused"), (0, "fused"), (1, "split")])
-def test_backward_parity(B, rows, D, agg, layout):
+@pytest.mark.parametrize("mode,agg,layout", [(0, 0, "fused"), (0, 0, "split"), (1, 1, "fused"), (1, 0, "fused"),
+                                             (1, 1, "split")])
+def test_backward_parity(B, rows, D, mode, agg, layout):
+    """mode 0 = slot-parallel kernel (default), mode 1 = example-parallel kernel (+- warp aggregation)."""
     from deep_recommenders_b200 import _lib
+    _lib.tune("embed_bwd_mode", mode)
     _lib.tune("embed_bwd_agg", agg)
     try:
         tables, lins, bias, ids = make_problem(B, rows, D, seed=7 * B + D, oov_frac=0.05)
@@ -161,6 +164,7 @@ def test_backward_parity(B, rows, D, agg, layout):
             assert float(coll.weight.grad[:, D + 1:].abs().max()) == 0.0      # pad lanes untouched
     finally:
         _lib.tune("embed_bwd_agg", 1)
+        _lib.tune("embed_bwd_mode", 0)
 
 
 def test_backward_same_id_1000_times():

@@ -93,16 +93,15 @@ def test_bucket_kernel_against_numpy_twin():
     rsend, rinv, rcounts, rovf = shard_np.bucket_ids(ids, offs, rows, G, cap)
     assert int(ovf) == int(rovf) == 0
     assert np.array_equal(counts.cpu().numpy(), rcounts)
-    send, inv = send.cpu().numpy(), inv.cpu().numpy()
+    send_np, inv_np = send.cpu().numpy(), inv.cpu().numpy()
     # order inside a segment is unspecified: compare the multiset per segment and the lookup -> id map
     for g in range(G):
-        assert np.array_equal(np.sort(send[g * cap:(g + 1) * cap]), np.sort(rsend[g * cap:(g + 1) * cap]))
+        assert np.array_equal(np.sort(send_np[g * cap:(g + 1) * cap]), np.sort(rsend[g * cap:(g + 1) * cap]))
     lv = rinv >= 0
-    assert np.array_equal(send[inv[lv]], rsend[rinv[lv]])
-    assert np.array_equal(inv[lv] // cap, rinv[lv] // cap)
-    live = rinv >= 0
-    assert np.array_equal(inv >= 0, live)
-    assert len(np.unique(inv[live])) == int(live.sum())
+    assert np.array_equal(send_np[inv_np[lv]], rsend[rinv[lv]])
+    assert np.array_equal(inv_np[lv] // cap, rinv[lv] // cap)
+    assert np.array_equal(inv_np >= 0, lv)
+    assert len(np.unique(inv_np[lv])) == int(lv.sum())
     # overflow is reported, not silently dropped
     _lib.check(lib.dr_shard_bucket_ids(idt.data_ptr(), 8, B * S, S, offs_t.data_ptr(),
                                        rows_t.data_ptr(), G, 8, counts.data_ptr(), send.data_ptr(),

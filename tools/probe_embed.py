@@ -101,6 +101,16 @@ def main():
         }
         for i in range(NP):
             fwd(i)
+        for mode, unroll in ((0, 1), (0, 2), (0, 4), (1, 4)):
+            _lib.tune("embed_bwd_mode", mode)
+            _lib.tune("embed_bwd_unroll", unroll)
+            t = timeit(lambda i: bwd(i))
+            r = dict(exp=f"bwd_full_mode{mode}_u{unroll}", gran=gran, D=D, rows=rows, layout=layout, id_bytes=idb,
+                     us=round(t * 1e6, 2), alg_gbs=round(alg_b / t / 1e9, 1), frac=round(alg_b / t / 1e9 / HBM, 4))
+            print(json.dumps(r), flush=True)
+            out.append(r)
+        _lib.tune("embed_bwd_mode", 0)
+        _lib.tune("embed_bwd_unroll", 0)
         for name, (fn, nbytes) in exps.items():
             t = timeit(fn)
             r = dict(exp=name, gran=gran, D=D, rows=rows, layout=layout, id_bytes=idb, us=round(t * 1e6, 2),
