@@ -25,12 +25,12 @@
 namespace dr {
 
 // ---- workspace registered by the host (dr_set_workspace) ----------------------------------------
+int g_tune_gemm_bn = 0;   // 0 = auto, 128 or 256: tensor-core tile width
 static void* g_ws_ptr = nullptr;
 static size_t g_ws_bytes = 0;
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;          // 32 tf32 = 128 bytes = one SWIZZLE_128B row
-constexpr int TC_STAGES = 3;
 constexpr int TC_THREADS = 192;
 
 // ---- small PTX wrappers ----------------------------------------------------------------------------
@@ -178,44 +178,67 @@ __device__ __forceinline__ float epi_scalar_tc(const GemmArgs& a, float acc, int
   }
 }
 
-template <int BN, bool A_MN, bool B_MN>
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Work item = (m tile, n tile, k split).  Items are strided over the persistent grid.
+struct TcItem {
+  int64_t m0, n0;
+  int kb0, nkb;
+};
+__device__ __forceinline__ TcItem tc_decode(int64_t item, int64_t n_tiles, int64_t m_tiles, int64_t kblocks,
+                                            int64_t per, int BN) {
+  TcItem t;
+  const int64_t nt = item % n_tiles;
+  const int64_t mt = (item / n_tiles) % m_tiles;
+  const int64_t z = item / (n_tiles * m_tiles);
+  t.m0 = mt * TC_BM;
+  t.n0 = nt * BN;
+  t.kb0 = (int)(z * per);
+  const int64_t kb1 = min(kblocks, (z + 1) * per);
+  t.nkb = (int)(kb1 - z * per);
+  return t;
+}
+
+// Persistent, warp-specialised: the accumulator is double buffered in TMEM (2 x BN columns) so the
+// epilogue of item j overlaps the TMA/MMA main loop of item j+1.
+template <int BN, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
-               const GemmArgs a) {
+               const GemmArgs a, const int64_t m_tiles, const int64_t n_tiles, const int64_t per,
+               const int64_t total_items) {
   constexpr int A_TILE = TC_BM * TC_BK * 4;   // 16 KB
   constexpr int B_TILE = BN * TC_BK * 4;
   constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], tmem_full_bar;
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t m0 = (int64_t)blockIdx.x * TC_BM;
-  const int64_t n0 = (int64_t)blockIdx.y * BN;
   const int64_t kblocks = (a.K + TC_BK - 1) / TC_BK;
-  const int64_t per = (kblocks + a.splitk - 1) / a.splitk;
-  const int64_t kb0 = (int64_t)blockIdx.z * per;
-  const int64_t kb1 = min(kblocks, kb0 + per);
-  const int nkb = (int)max((int64_t)0, kb1 - kb0);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAh) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAl) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBh) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBl) : "memory");
-    for (int s = 0; s < TC_STAGES; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(&tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 128);   // every epilogue thread arrives
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (warp == 1) {   // TMEM: BN fp32 accumulator columns (power of two >= 32)
+  if (warp == 1) {   // TMEM: 2 accumulator stages x BN fp32 columns
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
-                 "r"((uint32_t)BN)
+                 "r"((uint32_t)(2 * BN))
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -224,113 +247,112 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
-  if (nkb > 0) {
-    if (warp == 0) {
-      if (lane == 0) {
-        // ===== TMA producer =====
-        for (int i = 0; i < nkb; ++i) {
-          const int s = i % TC_STAGES;
-          const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      uint32_t it = 0;
+      for (int64_t item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const TcItem t = tc_decode(item, n_tiles, m_tiles, kblocks, per, BN);
+        for (int i = 0; i < t.nkb; ++i, ++it) {
+          const int s = (int)(it % STAGES);
+          const uint32_t ph = (it / STAGES) & 1u;
           mbar_wait(&empty_bar[s], ph ^ 1u);
           mbar_expect_tx(&full_bar[s], (uint32_t)STAGE);
           uint8_t* st = smem + (size_t)s * STAGE;
-          const int k = (int)((kb0 + i) * TC_BK);
-          if (!A_MN) {
-            tma_load_2d(st, &tmAh, &full_bar[s], k, (int)m0);
-            tma_load_2d(st + A_TILE, &tmAl, &full_bar[s], k, (int)m0);
-          } else {
-#pragma unroll
-            for (int j = 0; j < TC_BM / 32; ++j) {
-              tma_load_2d(st + j * 4096, &tmAh, &full_bar[s], (int)m0 + j * 32, k);
-              tma_load_2d(st + A_TILE + j * 4096, &tmAl, &full_bar[s], (int)m0 + j * 32, k);
-            }
-          }
-          if (!B_MN) {
-            tma_load_2d(st + 2 * A_TILE, &tmBh, &full_bar[s], k, (int)n0);
-            tma_load_2d(st + 2 * A_TILE + B_TILE, &tmBl, &full_bar[s], k, (int)n0);
-          } else {
-#pragma unroll
-            for (int j = 0; j < BN / 32; ++j) {
-              tma_load_2d(st + 2 * A_TILE + j * 4096, &tmBh, &full_bar[s], (int)n0 + j * 32, k);
-              tma_load_2d(st + 2 * A_TILE + B_TILE + j * 4096, &tmBl, &full_bar[s], (int)n0 + j * 32, k);
-            }
-          }
+          const int k = (t.kb0 + i) * TC_BK;
+          tma_load_2d(st, &tmAh, &full_bar[s], k, (int)t.m0);
+          tma_load_2d(st + A_TILE, &tmAl, &full_bar[s], k, (int)t.m0);
+          tma_load_2d(st + 2 * A_TILE, &tmBh, &full_bar[s], k, (int)t.n0);
+          tma_load_2d(st + 2 * A_TILE + B_TILE, &tmBl, &full_bar[s], k, (int)t.n0);
         }
       }
-      __syncwarp();
-    } else if (warp == 1) {
-      if (lane == 0) {
-        // ===== MMA issuer =====
-        constexpr uint32_t idesc = make_idesc(TC_BM, BN, A_MN, B_MN);
-        for (int i = 0; i < nkb; ++i) {
-          const int s = i % TC_STAGES;
-          const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = make_idesc(TC_BM, BN, false, false);
+      uint32_t it = 0, j = 0;
+      for (int64_t item = blockIdx.x; item < total_items; item += gridDim.x, ++j) {
+        const TcItem t = tc_decode(item, n_tiles, m_tiles, kblocks, per, BN);
+        const uint32_t as = j & 1u, aph = (j >> 1) & 1u;
+        mbar_wait(&tmem_empty_bar[as], aph ^ 1u);      // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * (uint32_t)BN;
+        for (int i = 0; i < t.nkb; ++i, ++it) {
+          const int s = (int)(it % STAGES);
+          const uint32_t ph = (it / STAGES) & 1u;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)s * STAGE);
           const uint32_t sb = sa + 2 * A_TILE;
 #pragma unroll
           for (int k = 0; k < TC_BK / 8; ++k) {
-            // K-major: step 8 tf32 = 32 B inside the 128-B swizzle row, 8-row groups 1024 B apart.
-            // MN-major: step 8 k-rows = 1024 B, MN atoms (32 elements) 4096 B apart.
-            const uint32_t a_off = A_MN ? (uint32_t)k * 1024u : (uint32_t)k * 32u;
-            const uint32_t b_off = B_MN ? (uint32_t)k * 1024u : (uint32_t)k * 32u;
-            const uint32_t a_lbo = A_MN ? 4096u : 16u, b_lbo = B_MN ? 4096u : 16u;
-            const uint64_t dAh = make_smem_desc(sa + a_off, a_lbo, 1024u);
-            const uint64_t dAl = make_smem_desc(sa + A_TILE + a_off, a_lbo, 1024u);
-            const uint64_t dBh = make_smem_desc(sb + b_off, b_lbo, 1024u);
-            const uint64_t dBl = make_smem_desc(sb + B_TILE + b_off, b_lbo, 1024u);
+            // K-major SWIZZLE_128B: one k-step = 8 tf32 = 32 B inside the 128-B row; 8-row groups 1024 B apart
+            const uint32_t off = (uint32_t)k * 32u;
+            const uint64_t dAh = make_smem_desc(sa + off, 16u, 1024u);
+            const uint64_t dAl = make_smem_desc(sa + A_TILE + off, 16u, 1024u);
+            const uint64_t dBh = make_smem_desc(sb + off, 16u, 1024u);
+            const uint64_t dBl = make_smem_desc(sb + B_TILE + off, 16u, 1024u);
             const uint32_t acc0 = (i > 0 || k > 0) ? 1u : 0u;
-            tc_mma_tf32(tmem_base, dAl, dBh, idesc, acc0);   // small cross terms first
-            tc_mma_tf32(tmem_base, dAh, dBl, idesc, 1u);
-            tc_mma_tf32(tmem_base, dAh, dBh, idesc, 1u);
+            tc_mma_tf32(d_tmem, dAl, dBh, idesc, acc0);   // small cross terms first
+            tc_mma_tf32(d_tmem, dAh, dBl, idesc, 1u);
+            tc_mma_tf32(d_tmem, dAh, dBh, idesc, 1u);
           }
           tc_commit(&empty_bar[s]);          // smem stage reusable once these MMAs retire
         }
-        tc_commit(&tmem_full_bar);           // accumulator complete
+        tc_commit(&tmem_full_bar[as]);       // accumulator of this item complete
       }
-      __syncwarp();
-    } else {
-      // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
-      mbar_wait(&tmem_full_bar, 0);
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
+    const int q = warp & 3;
+    const bool vec_ok = ((a.ldc & 3) == 0) && aligned16(a.C);
+    uint32_t j = 0;
+    for (int64_t item = blockIdx.x; item < total_items; item += gridDim.x, ++j) {
+      const TcItem t = tc_decode(item, n_tiles, m_tiles, kblocks, per, BN);
+      const uint32_t as = j & 1u, aph = (j >> 1) & 1u;
+      mbar_wait(&tmem_full_bar[as], aph);
       tc_fence_after();
-      const int q = warp & 3;
-      const int64_t m = m0 + q * 32 + lane;
-      const bool vec_ok = ((a.ldc & 3) == 0) && aligned16(a.C);
+      const int64_t m = t.m0 + q * 32 + lane;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-        const int64_t nb = n0 + c * 32;
+        tmem_ld_32x32(tmem_base + as * (uint32_t)BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+        const int64_t nb = t.n0 + c * 32;
         if (m < a.M && nb < a.N) {
           if (a.epi == EPI_ATOMIC) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nb + j < a.N) red_add_f32(a.C + m * a.ldc + nb + j, __uint_as_float(r[j]));
+            for (int jj = 0; jj < 32; ++jj)
+              if (nb + jj < a.N) red_add_f32(a.C + m * a.ldc + nb + jj, __uint_as_float(r[jj]));
           } else if (vec_ok && nb + 31 < a.N) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
+            for (int jj = 0; jj < 32; jj += 4) {
               float4 o;
-              o.x = epi_scalar_tc(a, __uint_as_float(r[j + 0]), m, nb + j + 0);
-              o.y = epi_scalar_tc(a, __uint_as_float(r[j + 1]), m, nb + j + 1);
-              o.z = epi_scalar_tc(a, __uint_as_float(r[j + 2]), m, nb + j + 2);
-              o.w = epi_scalar_tc(a, __uint_as_float(r[j + 3]), m, nb + j + 3);
-              *reinterpret_cast<float4*>(a.C + m * a.ldc + nb + j) = o;
+              o.x = epi_scalar_tc(a, __uint_as_float(r[jj + 0]), m, nb + jj + 0);
+              o.y = epi_scalar_tc(a, __uint_as_float(r[jj + 1]), m, nb + jj + 1);
+              o.z = epi_scalar_tc(a, __uint_as_float(r[jj + 2]), m, nb + jj + 2);
+              o.w = epi_scalar_tc(a, __uint_as_float(r[jj + 3]), m, nb + jj + 3);
+              *reinterpret_cast<float4*>(a.C + m * a.ldc + nb + jj) = o;
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nb + j < a.N) a.C[m * a.ldc + nb + j] = epi_scalar_tc(a, __uint_as_float(r[j]), m, nb + j);
+            for (int jj = 0; jj < 32; ++jj)
+              if (nb + jj < a.N) a.C[m * a.ldc + nb + jj] = epi_scalar_tc(a, __uint_as_float(r[jj]), m, nb + jj);
           }
         }
       }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[as]);      // this thread is done reading accumulator stage `as`
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN))
+                 : "memory");
   }
 }
 
@@ -394,14 +416,19 @@ bool gemm_tc_eligible(const GemmArgs& a, bool ta, bool tb) {
   return true;
 }
 
-template <int BN>
+template <int BN, int STAGES>
 static int launch_tc(const CUtensorMap* tms, const GemmArgs& a, cudaStream_t st) {
   constexpr int STAGE = 2 * TC_BM * TC_BK * 4 + 2 * BN * TC_BK * 4;
-  const size_t smem = (size_t)TC_STAGES * STAGE + 1024;
-  auto k = gemm_tc_kernel<BN, false, false>;
+  const size_t smem = (size_t)STAGES * STAGE + 1024;
+  auto k = gemm_tc_kernel<BN, STAGES>;
   DR_CUDA_CALL(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((unsigned)((a.M + TC_BM - 1) / TC_BM), (unsigned)((a.N + BN - 1) / BN), (unsigned)a.splitk);
-  k<<<grid, TC_THREADS, smem, st>>>(tms[0], tms[1], tms[2], tms[3], a);
+  const int64_t m_tiles = (a.M + TC_BM - 1) / TC_BM, n_tiles = (a.N + BN - 1) / BN;
+  const int64_t kblocks = (a.K + TC_BK - 1) / TC_BK;
+  const int64_t per = (kblocks + a.splitk - 1) / a.splitk;
+  const int64_t splits = (kblocks + per - 1) / per;          // every split owns >= 1 k-block
+  const int64_t total = m_tiles * n_tiles * splits;
+  const int64_t ctas = total < (int64_t)kNumSMs ? total : (int64_t)kNumSMs;
+  k<<<(unsigned)ctas, TC_THREADS, smem, st>>>(tms[0], tms[1], tms[2], tms[3], a, m_tiles, n_tiles, per, total);
   DR_CUDA_LAUNCH_CHECK("gemm_tc");
   return DR_OK;
 }
@@ -449,13 +476,15 @@ int gemm_tc_launch(const GemmArgs& a0, bool ta, bool tb, cudaStream_t st) {
   if (int rc = make_planes(a.A, !ta, a.M, a.K, a.lda, Ah, Al, &pa, st)) return rc;
   // B(k,n):  tb -> stored [N,K] (already K-major); !tb -> stored [K,N] -> transpose
   if (int rc = make_planes(a.B, tb, a.N, a.K, a.ldb, Bh, Bl, &pb, st)) return rc;
-  constexpr int BN = 128;
+  const bool wide = (g_tune_gemm_bn == 256) || (g_tune_gemm_bn == 0 && a.N >= 256 && a.N % 256 <= 0);
+  const int BN = wide ? 256 : 128;
   CUtensorMap tms[4];
   if (int rc = make_map(&tms[0], Ah, a.K, a.M, pa, TC_BM)) return rc;
   if (int rc = make_map(&tms[1], Al, a.K, a.M, pa, TC_BM)) return rc;
   if (int rc = make_map(&tms[2], Bh, a.K, a.N, pb, BN)) return rc;
   if (int rc = make_map(&tms[3], Bl, a.K, a.N, pb, BN)) return rc;
-  return launch_tc<BN>(tms, a, st);
+  if (wide) return launch_tc<256, 2>(tms, a, st);
+  return launch_tc<128, 3>(tms, a, st);
 }
 
 }  // namespace dr
