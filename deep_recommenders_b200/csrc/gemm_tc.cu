@@ -476,7 +476,8 @@ int gemm_tc_launch(const GemmArgs& a0, bool ta, bool tb, cudaStream_t st) {
   if (int rc = make_planes(a.A, !ta, a.M, a.K, a.lda, Ah, Al, &pa, st)) return rc;
   // B(k,n):  tb -> stored [N,K] (already K-major); !tb -> stored [K,N] -> transpose
   if (int rc = make_planes(a.B, tb, a.N, a.K, a.ldb, Bh, Bl, &pb, st)) return rc;
-  const bool wide = (g_tune_gemm_bn == 256) || (g_tune_gemm_bn == 0 && a.N >= 256 && a.N % 256 <= 0);
+  // measured on B200 (profiles/gemm_tc_r01.md): 128 x 128 tiles with a 3-stage ring beat 128 x 256 with 2 stages
+  const bool wide = (g_tune_gemm_bn == 256);
   const int BN = wide ? 256 : 128;
   CUtensorMap tms[4];
   if (int rc = make_map(&tms[0], Ah, a.K, a.M, pa, TC_BM)) return rc;
