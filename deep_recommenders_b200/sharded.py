@@ -94,7 +94,8 @@ class ShardedDeepFMTrainStep:
                     dst_g.append(self.gflat[o:o + nel].view_as(src))
                     o += nel
         # static buffers
-        self.ids = torch.zeros((B, S), device=dev, dtype=torch.int64)
+        # warm-up ids spread over the tables (all-zero ids would all hit one owner)
+        self.ids = torch.stack([torch.randint(0, max(1, r), (B,), device=dev) for r in rows], dim=1).contiguous()
         self.labels = torch.zeros((B,), **f)
         self.send_counts = torch.zeros((G,), device=dev, dtype=torch.int64)
         self.send_ids = torch.empty((G * self.cap,), device=dev, dtype=torch.int64)
