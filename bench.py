@@ -220,14 +220,17 @@ def main():
            "h2d_bytes_per_step": (host_ids[0].numel() * host_ids[0].element_size() + host_lab[0].numel() * 4) * world,
            "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps}
 
+    # ---- per-kernel timing, live, CUDA events on the launching stream (every rank: the sharded
+    # step contains collectives) -------------------------------------------------------------------
+    roof, shares = trainer.profile_kernels(ids_pool, lab_pool, iters=max(10, args.steps))
+    barrier()
+    if world > 1:
+        dist.destroy_process_group()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return
 
-    # ---- roofline of the headline kernel (fused gather+FM forward), timed live with CUDA events ----
+    # ---- roofline of the headline kernel (fused gather+FM forward) ---------------------------------
     peaks, peak_kind = measured_peaks()
-    roof, shares = trainer.profile_kernels(ids_pool, lab_pool, iters=max(10, args.steps))
     alg_bytes = B * (S * (8 + 4 * D + 4) + 4 * S * D + 4 * D + 4)      # ids + rows + w + stack + sum_e + logit
     traffic = None
     try:
@@ -256,8 +259,6 @@ def main():
             "cpu_baseline": cpu, "final_loss": final_loss,
             "cuda_graph": trainer.graph is not None}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
