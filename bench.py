@@ -163,7 +163,8 @@ def main():
     cols = [fc.categorical_column_with_identity(f"C{i}", C2["rows"]) for i in range(S)]
     if world > 1:
         from deep_recommenders_b200.sharded import ShardedDeepFMTrainStep
-        trainer = ShardedDeepFMTrainStep(cols, D, C2["dnn"], batch_size=B, lr=0.01, seed=1, device=dev).capture()
+        trainer = ShardedDeepFMTrainStep(cols, D, C2["dnn"], batch_size=B, lr=0.01, seed=1, device=dev,
+                                         use_graph=not args.no_graph).capture()
     else:
         model = DeepFM([fc.indicator_column(c) for c in cols], [fc.embedding_column(c, D) for c in cols],
                        dnn_units_size=C2["dnn"], seed=1, device=dev, sparse_lr=0.01)
@@ -244,7 +245,7 @@ def main():
                 "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": fwd_s * 1e6}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:     # CPU arm on rank 0 at N=1 only (torchrun pins OMP threads to 1)
         from oracle.torch_cpu import time_deepfm_cpu
         r = time_deepfm_cpu([C2["rows"]] * S, D, C2["dnn"], B, steps=8, warmup=1, max_seconds=25.0)
         cpu = {"value": r["examples_per_sec"], "unit": "examples/s", "cores": r["cores"], "kind": "port",
@@ -257,7 +258,7 @@ def main():
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(trainer.launches_per_step * args.steps),
             "launches_per_step": int(trainer.launches_per_step), "roofline": roofline, "kernel_ms": shares,
             "cpu_baseline": cpu, "final_loss": final_loss,
-            "cuda_graph": trainer.graph is not None}
+            "cuda_graph": trainer.graph is not None, "graph_error": getattr(trainer, "graph_error", None)}
     print(json.dumps(line), flush=True)
 
 

@@ -400,6 +400,42 @@ __global__ void __launch_bounds__(256) embed_fm_bwd_sp_kernel(const EmbedBwdPara
   }
 }
 
+// Plain single-table row gather / scatter-add (two-tower towers, owner side of the sharded
+// exchange): one 16-byte chunk per thread, flat over (row, chunk), grid-stride.  OOV id -> zeros.
+template <typename IdT>
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ table, int64_t rows,
+                                                           const IdT* __restrict__ ids, int64_t n, int chunks,
+                                                           float* __restrict__ out) {
+  const int64_t total = n * chunks;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < total; f += stride) {
+    const int64_t i = f / chunks;
+    const int c = (int)(f - i * chunks);
+    const int64_t id = (int64_t)__ldg(ids + i);
+    float4 v = f4_zero();
+    if ((uint64_t)id < (uint64_t)rows) v = ldg_nc_na(table + ((size_t)id * chunks + c) * 4);
+    stg4(out + (size_t)f * 4, v);
+  }
+}
+
+template <typename IdT>
+__global__ void __launch_bounds__(256) scatter_add_rows_kernel(float* __restrict__ table, int64_t rows,
+                                                                const IdT* __restrict__ ids, int64_t n, int chunks,
+                                                                const float* __restrict__ g, float scale) {
+  const int64_t total = n * chunks;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < total; f += stride) {
+    const int64_t i = f / chunks;
+    const int c = (int)(f - i * chunks);
+    const int64_t id = (int64_t)__ldg(ids + i);
+    if ((uint64_t)id < (uint64_t)rows) {
+      float4 v = ldg_nc_na(g + (size_t)f * 4);
+      v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+      red_add_v4(table + ((size_t)id * chunks + c) * 4, v);
+    }
+  }
+}
+
 // ---- host-side dispatch -----------------------------------------------------------------
 static int lpr_for(int D, int lin_in_row = 0) {
   int chunks = D / 4 + (lin_in_row ? 1 : 0), l = 1;
@@ -602,12 +638,16 @@ extern "C" int dr_gather_fwd(const float* table, int64_t rows, const void* ids, 
   DR_REQUIRE(table && ids && out, DR_EINVAL, "dr_gather_fwd: null pointer");
   DR_REQUIRE(rows >= 0, DR_EINVAL, "dr_gather_fwd: rows < 0");
   DR_REQUIRE(aligned16(table) && aligned16(out), DR_EALIGN, "dr_gather_fwd: table/out not 16-B aligned");
-  if (n == 0) return DR_OK;
-  EmbedFwdParams p{};
-  p.single_table = table; p.single_rows = rows; p.ids = ids; p.B = n; p.S = 1; p.D = D; p.out_stack = out;
-  p.row_stride = D; p.lin_stride = 1;
+  const int chunks = D / 4;
+  int64_t ctas = (n * chunks + 255) / 256;
+  if (ctas > (int64_t)kNumSMs * 8) ctas = (int64_t)kNumSMs * 8;
   cudaStream_t st = (cudaStream_t)stream;
-  DR_DISPATCH_LPR(launch_fwd, p, st);
+  if (id_bytes == 8)
+    gather_rows_kernel<int64_t><<<(unsigned)ctas, 256, 0, st>>>(table, rows, (const int64_t*)ids, n, chunks, out);
+  else
+    gather_rows_kernel<int32_t><<<(unsigned)ctas, 256, 0, st>>>(table, rows, (const int32_t*)ids, n, chunks, out);
+  DR_CUDA_LAUNCH_CHECK("gather_rows");
+  return DR_OK;
 }
 
 extern "C" int dr_scatter_add(float* grad_table, int64_t rows, const void* ids, int id_bytes, int64_t n,
@@ -617,10 +657,14 @@ extern "C" int dr_scatter_add(float* grad_table, int64_t rows, const void* ids, 
   DR_REQUIRE(grad_table && ids && g, DR_EINVAL, "dr_scatter_add: null pointer");
   DR_REQUIRE(rows >= 0, DR_EINVAL, "dr_scatter_add: rows < 0");
   DR_REQUIRE(aligned16(grad_table) && aligned16(g), DR_EALIGN, "dr_scatter_add: table/g not 16-B aligned");
-  if (n == 0) return DR_OK;
-  EmbedBwdParams p{};
-  p.ids = ids; p.single_rows = rows; p.g_stack = g; p.B = n; p.S = 1; p.D = D; p.single_grad = grad_table;
-  p.scale = scale; p.row_stride = D; p.lin_stride = 1;
+  const int chunks = D / 4;
+  int64_t ctas = (n * chunks + 255) / 256;
+  if (ctas > (int64_t)kNumSMs * 8) ctas = (int64_t)kNumSMs * 8;
   cudaStream_t st = (cudaStream_t)stream;
-  DR_DISPATCH_LPR(launch_bwd, p, st);
+  if (id_bytes == 8)
+    scatter_add_rows_kernel<int64_t><<<(unsigned)ctas, 256, 0, st>>>(grad_table, rows, (const int64_t*)ids, n, chunks, g, scale);
+  else
+    scatter_add_rows_kernel<int32_t><<<(unsigned)ctas, 256, 0, st>>>(grad_table, rows, (const int32_t*)ids, n, chunks, g, scale);
+  DR_CUDA_LAUNCH_CHECK("scatter_add_rows");
+  return DR_OK;
 }

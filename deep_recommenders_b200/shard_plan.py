@@ -30,8 +30,10 @@ def local_rows(total_rows: int, rank: int, world: int) -> int:
     return (total_rows - rank + world - 1) // world if total_rows > rank else 0
 
 
-def capacity(n_lookups: int, world: int, slack: float = 0.25, floor: int = 1024) -> int:
+def capacity(n_lookups: int, world: int, slack: float = 0.04, floor: int = 4096) -> int:
     """Per-destination slots of the padded equal-split exchange: mean + slack, at least `floor`
-    above the mean (uniform ids deviate by ~sqrt(n/G); the overflow flag catches skew)."""
+    above the mean.  Owner = row mod G spreads even heavily repeated ids over the ranks unless ONE
+    row dominates; uniform ids deviate by ~sqrt(n/G) (0.2 % at C2), so 4 % slack is ~20 sigma.
+    The overflow flag catches skew (the caller re-plans with a larger slack)."""
     mean = (n_lookups + world - 1) // world
     return min(n_lookups, mean + max(floor, int(mean * slack))) if world > 1 else n_lookups

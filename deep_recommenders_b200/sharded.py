@@ -51,7 +51,7 @@ class ShardedEmbedding:
 
 class ShardedDeepFMTrainStep:
     def __init__(self, columns, dim: int, dnn_units: Sequence[int], batch_size: int, lr: float = 0.01,
-                 seed: int = 0, device=None, group=None, use_graph: bool = False):
+                 seed: int = 0, device=None, group=None, use_graph: bool = True):
         if not dist.is_initialized():
             raise RuntimeError("ShardedDeepFMTrainStep needs an initialised torch.distributed process group")
         self.lib = _lib.load()
@@ -126,6 +126,8 @@ class ShardedDeepFMTrainStep:
         kmax = max([S * D] + [l.units for l in layers])
         _lib.ensure_gemm_workspace(B, kmax, kmax, dev)
         self.graph = None
+        self.use_graph = use_graph
+        self.graph_error = None
         self.launches_per_step = None
         self._copy_stream = torch.cuda.Stream(device=dev)
         self._staged = None
@@ -194,11 +196,27 @@ class ShardedDeepFMTrainStep:
         mark("sgd")
 
     def capture(self):
+        """Warm up eagerly, then record the whole step -- kernels AND the NCCL collectives -- into one
+        CUDA graph (falls back to eager launches if this NCCL/torch build cannot capture them)."""
         n0 = _lib.launch_count()
-        self._enqueue()
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._enqueue()
+        torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self.launches_per_step = _lib.launch_count() - n0
         self.check_overflow()
+        if self.use_graph:
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._enqueue()
+                self.graph = g
+            except Exception as e:  # pragma: no cover - depends on the NCCL build
+                self.graph = None
+                self.graph_error = repr(e)
+                torch.cuda.synchronize()
         return self
 
     def check_overflow(self):
@@ -207,7 +225,10 @@ class ShardedDeepFMTrainStep:
                                     "raise shard_plan.capacity slack (skewed ids)")
 
     def run(self):
-        self._enqueue()
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._enqueue()
 
     def step(self, ids, labels):
         self.ids.copy_(ids, non_blocking=True)
