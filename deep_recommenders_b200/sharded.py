@@ -135,65 +135,98 @@ class ShardedDeepFMTrainStep:
     def _a2a(self, out, inp):
         dist.all_to_all_single(out, inp, group=self.group)
 
-    def _enqueue(self, mark=None):
-        lib, st = self.lib, torch.cuda.current_stream().cuda_stream
+    # The step is a chain  compute segment -> collective -> compute segment ...  The compute segments
+    # are captured as CUDA graphs; the NCCL collectives are issued between the replays.
+    def _segments(self, mark):
+        lib = self.lib
         B, S, D, G, V = self.B, self.S, self.D, self.world, self.emb.vdim
+
+        def st():
+            return torch.cuda.current_stream().cuda_stream
+
+        def seg_bucket():
+            check(lib.dr_shard_bucket_ids(self.ids.data_ptr(), 8, self.n, S, self.emb.slot_offsets.data_ptr(),
+                                          self.emb.rows.data_ptr(), G, self.cap, self.send_counts.data_ptr(),
+                                          self.send_ids.data_ptr(), self.inv.data_ptr(), self.overflow.data_ptr(), st()),
+                  "dr_shard_bucket_ids")
+            mark("bucket")
+
+        def col_ids():
+            self._a2a(self.recv_ids, self.send_ids)
+            mark("a2a_ids")
+
+        def seg_gather():
+            check(lib.dr_gather_fwd(self.emb.weight.data_ptr(), self.emb.local_rows, self.recv_ids.data_ptr(), 8,
+                                    G * self.cap, V, self.vec_send.data_ptr(), st()), "dr_gather_fwd")
+            mark("owner_gather")
+
+        def col_vec():
+            self._a2a(self.vec_recv, self.vec_send)
+            mark("a2a_vectors")
+
+        def seg_main():
+            check(lib.dr_embed_fm_fwd(self.tp.data_ptr(), self.lp.data_ptr(), self.trows.data_ptr(),
+                                      self.inv.data_ptr(), 4, self.bias.data_ptr(), B, S, D, V, V, 1,
+                                      self.stack.data_ptr(), self.sum_e.data_ptr(), self.fm_logit.data_ptr(), st()),
+                  "dr_embed_fm_fwd")
+            mark("embed_fm_fwd")
+            x, K = self.stack, S * D
+            for i, l in enumerate(self.layers):
+                check(lib.dr_dense_fwd(x.data_ptr(), self.w[i].data_ptr(), self.b[i].data_ptr(), B, K, l.units,
+                                       l._act, self.acts[i].data_ptr(), st()), "dr_dense_fwd")
+                x, K = self.acts[i], l.units
+                mark(f"dense_fwd_{i}")
+            gz = self.g_acts[-1]
+            check(lib.dr_bce_logits_fwd_bwd(self.acts[-1].data_ptr(), self.fm_logit.data_ptr(),
+                                            self.labels.data_ptr(), B, self.prob.data_ptr(), self.loss.data_ptr(),
+                                            gz.data_ptr(), st()), "dr_bce")
+            mark("bce")
+            for i in range(len(self.layers) - 1, -1, -1):
+                l = self.layers[i]
+                xin = self.stack if i == 0 else self.acts[i - 1]
+                Kin = S * D if i == 0 else self.layers[i - 1].units
+                gx = self.g_stack if i == 0 else self.g_acts[i - 1]
+                check(lib.dr_dense_bwd(xin.data_ptr(), self.w[i].data_ptr(), self.acts[i].data_ptr(),
+                                       self.g_acts[i].data_ptr(), B, Kin, l.units, l._act, ops._ptr(self.gz_ws[i]),
+                                       gx.data_ptr(), self.gw[i].data_ptr(), self.gb[i].data_ptr(), st()),
+                      "dr_dense_bwd")
+                mark(f"dense_bwd_{i}")
+            # pack per-lookup gradient rows [dE | g_logit | 0 0 0] into the padded send buffer
+            self.grad_send.zero_()
+            self.g_bias.zero_()
+            check(lib.dr_embed_fm_bwd(self.inv.data_ptr(), 4, self.trows.data_ptr(), self.stack.data_ptr(),
+                                      self.sum_e.data_ptr(), gz.data_ptr(), self.g_stack.data_ptr(), B, S, D, V, V, 1,
+                                      self.gtp.data_ptr(), self.glp.data_ptr(), self.g_bias.data_ptr(), 1.0, st()),
+                  "dr_embed_fm_bwd")
+            mark("embed_fm_bwd_pack")
+
+        def col_grads():
+            self._a2a(self.grad_recv, self.grad_send)
+            mark("a2a_grads")
+
+        def seg_scatter():
+            # owners: row-sparse SGD on the fused rows (mean over the GLOBAL batch: 1/world)
+            check(lib.dr_scatter_add(self.emb.weight.data_ptr(), self.emb.local_rows, self.recv_ids.data_ptr(), 8,
+                                     G * self.cap, V, self.grad_recv.data_ptr(), -self.lr / G, st()), "dr_scatter_add")
+            mark("owner_scatter_sgd")
+
+        def col_allreduce():
+            dist.all_reduce(self.gflat, group=self.group)
+            mark("allreduce_dense")
+
+        def seg_sgd():
+            check(lib.dr_sgd_step(self.flat.data_ptr(), self.gflat.data_ptr(), self.flat.numel(), self.lr / G, st()),
+                  "dr_sgd_step")
+            mark("sgd")
+
+        return [(seg_bucket, True), (col_ids, False), (seg_gather, True), (col_vec, False), (seg_main, True),
+                (col_grads, False), (seg_scatter, True), (col_allreduce, False), (seg_sgd, True)]
+
+    def _enqueue(self, mark=None):
         mark = mark or (lambda label: None)
         mark("start")
-        check(lib.dr_shard_bucket_ids(self.ids.data_ptr(), 8, self.n, S, self.emb.slot_offsets.data_ptr(),
-                                      self.emb.rows.data_ptr(), G, self.cap, self.send_counts.data_ptr(),
-                                      self.send_ids.data_ptr(), self.inv.data_ptr(), self.overflow.data_ptr(), st),
-              "dr_shard_bucket_ids")
-        mark("bucket")
-        self._a2a(self.recv_ids, self.send_ids)
-        mark("a2a_ids")
-        check(lib.dr_gather_fwd(self.emb.weight.data_ptr(), self.emb.local_rows, self.recv_ids.data_ptr(), 8,
-                                G * self.cap, V, self.vec_send.data_ptr(), st), "dr_gather_fwd")
-        mark("owner_gather")
-        self._a2a(self.vec_recv, self.vec_send)
-        mark("a2a_vectors")
-        check(lib.dr_embed_fm_fwd(self.tp.data_ptr(), self.lp.data_ptr(), self.trows.data_ptr(), self.inv.data_ptr(), 4,
-                                  self.bias.data_ptr(), B, S, D, V, V, 1, self.stack.data_ptr(), self.sum_e.data_ptr(),
-                                  self.fm_logit.data_ptr(), st), "dr_embed_fm_fwd")
-        mark("embed_fm_fwd")
-        x, K = self.stack, S * D
-        for i, l in enumerate(self.layers):
-            check(lib.dr_dense_fwd(x.data_ptr(), self.w[i].data_ptr(), self.b[i].data_ptr(), B, K, l.units, l._act,
-                                   self.acts[i].data_ptr(), st), "dr_dense_fwd")
-            x, K = self.acts[i], l.units
-            mark(f"dense_fwd_{i}")
-        gz = self.g_acts[-1]
-        check(lib.dr_bce_logits_fwd_bwd(self.acts[-1].data_ptr(), self.fm_logit.data_ptr(), self.labels.data_ptr(), B,
-                                        self.prob.data_ptr(), self.loss.data_ptr(), gz.data_ptr(), st), "dr_bce")
-        mark("bce")
-        for i in range(len(self.layers) - 1, -1, -1):
-            l = self.layers[i]
-            xin = self.stack if i == 0 else self.acts[i - 1]
-            Kin = S * D if i == 0 else self.layers[i - 1].units
-            gx = self.g_stack if i == 0 else self.g_acts[i - 1]
-            check(lib.dr_dense_bwd(xin.data_ptr(), self.w[i].data_ptr(), self.acts[i].data_ptr(),
-                                   self.g_acts[i].data_ptr(), B, Kin, l.units, l._act, ops._ptr(self.gz_ws[i]),
-                                   gx.data_ptr(), self.gw[i].data_ptr(), self.gb[i].data_ptr(), st), "dr_dense_bwd")
-            mark(f"dense_bwd_{i}")
-        # pack per-lookup gradient rows [dE | g_logit | 0 0 0] into the padded send buffer
-        self.grad_send.zero_()
-        self.g_bias.zero_()
-        check(lib.dr_embed_fm_bwd(self.inv.data_ptr(), 4, self.trows.data_ptr(), self.stack.data_ptr(),
-                                  self.sum_e.data_ptr(), gz.data_ptr(), self.g_stack.data_ptr(), B, S, D, V, V, 1,
-                                  self.gtp.data_ptr(), self.glp.data_ptr(), self.g_bias.data_ptr(), 1.0, st),
-              "dr_embed_fm_bwd")
-        mark("embed_fm_bwd_pack")
-        self._a2a(self.grad_recv, self.grad_send)
-        mark("a2a_grads")
-        # owners: row-sparse SGD on the fused rows (mean over the GLOBAL batch: 1/world)
-        check(lib.dr_scatter_add(self.emb.weight.data_ptr(), self.emb.local_rows, self.recv_ids.data_ptr(), 8,
-                                 G * self.cap, V, self.grad_recv.data_ptr(), -self.lr / G, st), "dr_scatter_add")
-        mark("owner_scatter_sgd")
-        dist.all_reduce(self.gflat, group=self.group)
-        mark("allreduce_dense")
-        check(lib.dr_sgd_step(self.flat.data_ptr(), self.gflat.data_ptr(), self.flat.numel(), self.lr / G, st),
-              "dr_sgd_step")
-        mark("sgd")
+        for fn, _ in self._segments(mark):
+            fn()
 
     def capture(self):
         """Warm up eagerly, then record the whole step -- kernels AND the NCCL collectives -- into one
@@ -208,15 +241,18 @@ class ShardedDeepFMTrainStep:
         self.launches_per_step = _lib.launch_count() - n0
         self.check_overflow()
         if self.use_graph:
-            try:
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._enqueue()
-                self.graph = g
-            except Exception as e:  # pragma: no cover - depends on the NCCL build
-                self.graph = None
-                self.graph_error = repr(e)
-                torch.cuda.synchronize()
+            # compute segments -> CUDA graphs; collectives stay eager NCCL calls between the replays
+            # (capturing the NCCL all-to-all itself dead-locked on this torch/NCCL build)
+            plan = []
+            for fn, is_compute in self._segments(lambda label: None):
+                if is_compute:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        fn()
+                    plan.append(g.replay)
+                else:
+                    plan.append(fn)
+            self.graph = plan
         return self
 
     def check_overflow(self):
@@ -226,7 +262,8 @@ class ShardedDeepFMTrainStep:
 
     def run(self):
         if self.graph is not None:
-            self.graph.replay()
+            for fn in self.graph:
+                fn()
         else:
             self._enqueue()
 
