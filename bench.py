@@ -134,6 +134,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly (for ncu launch lists)")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: fused NVLink peer-memory gather/update (p2p) or NCCL all-to-all pipeline (nccl)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -163,8 +165,16 @@ def main():
     cols = [fc.categorical_column_with_identity(f"C{i}", C2["rows"]) for i in range(S)]
     if world > 1:
         from deep_recommenders_b200.sharded import ShardedDeepFMTrainStep
-        trainer = ShardedDeepFMTrainStep(cols, D, C2["dnn"], batch_size=B, lr=0.01, seed=1, device=dev,
-                                         use_graph=not args.no_graph).capture()
+        exchange_note = None
+        try:
+            trainer = ShardedDeepFMTrainStep(cols, D, C2["dnn"], batch_size=B, lr=0.01, seed=1, device=dev,
+                                             use_graph=not args.no_graph, exchange=args.exchange).capture()
+        except Exception as e:      # symmetric memory unavailable on this box: NCCL all-to-all pipeline instead
+            if args.exchange != "p2p":
+                raise
+            exchange_note = f"p2p unavailable ({type(e).__name__}: {e}); used nccl"
+            trainer = ShardedDeepFMTrainStep(cols, D, C2["dnn"], batch_size=B, lr=0.01, seed=1, device=dev,
+                                             use_graph=not args.no_graph, exchange="nccl").capture()
     else:
         model = DeepFM([fc.indicator_column(c) for c in cols], [fc.embedding_column(c, D) for c in cols],
                        dnn_units_size=C2["dnn"], seed=1, device=dev, sparse_lr=0.01)
@@ -258,7 +268,10 @@ def main():
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(trainer.launches_per_step * args.steps),
             "launches_per_step": int(trainer.launches_per_step), "roofline": roofline, "kernel_ms": shares,
             "cpu_baseline": cpu, "final_loss": final_loss,
-            "cuda_graph": trainer.graph is not None, "graph_error": getattr(trainer, "graph_error", None)}
+            "cuda_graph": trainer.graph is not None,
+            "exchange": getattr(trainer, "exchange", None) if world > 1 else None}
+    if world > 1 and exchange_note:
+        line["exchange_note"] = exchange_note
     print(json.dumps(line), flush=True)
 
 

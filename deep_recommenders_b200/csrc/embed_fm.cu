@@ -40,6 +40,12 @@ struct EmbedFwdParams {
   int64_t row_stride;   // floats between consecutive rows of a table (>= D)
   int64_t lin_stride;   // floats between consecutive first-order weights (>= 1)
   int lin_in_row;       // first-order weight lives in the row at float index D (fetched with the row)
+  // row-sharded mode (shard_world > 0): global row = slot_offsets[s] + id lives on rank row % G at
+  // local row row / G of that rank's arena; peer_bases[g] is rank g's arena mapped into this
+  // process (NVLink peer memory), so the gather itself is the exchange.
+  int shard_world;
+  const float* const* peer_bases;
+  const int64_t* slot_offsets;
   float* out_stack;
   float* out_sum;
   float* out_logit;
@@ -63,11 +69,16 @@ struct EmbedBwdParams {
   int64_t row_stride;
   int64_t lin_stride;
   int lin_in_row;
+  int shard_world;
+  float* const* peer_bases;
+  const int64_t* slot_offsets;
 };
+
+constexpr int kMaxShardWorld = 64;
 
 // shared memory carve-up: [S] table ptr | [S] lin ptr | [S] rows | per-warp id slices
 __host__ __device__ inline size_t embed_smem_bytes(int S, int warps, int G, int id_bytes) {
-  size_t hdr = (size_t)S * (sizeof(void*) * 2 + sizeof(int64_t));
+  size_t hdr = (size_t)S * (sizeof(void*) * 2 + sizeof(int64_t) * 2) + kMaxShardWorld * sizeof(void*);
   size_t ids = (size_t)warps * G * S * id_bytes;
   return hdr + ((ids + 15) & ~(size_t)15);
 }
@@ -80,15 +91,22 @@ __global__ void __launch_bounds__(512) embed_fm_fwd_kernel(const EmbedFwdParams 
   const float** s_tab = reinterpret_cast<const float**>(smem_raw);
   const float** s_lin = s_tab + S;
   int64_t* s_rows = reinterpret_cast<int64_t*>(s_lin + S);
+  int64_t* s_off = s_rows + S;
+  const float** s_peer = reinterpret_cast<const float**>(s_off + S);
   const int warp_in_cta = threadIdx.x >> 5;
   const int warps_per_cta = blockDim.x >> 5;
-  IdT* s_ids = reinterpret_cast<IdT*>(s_rows + S) + (size_t)warp_in_cta * G * S;
+  IdT* s_ids = reinterpret_cast<IdT*>(s_peer + kMaxShardWorld) + (size_t)warp_in_cta * G * S;
+  const int SW = p.shard_world;
+  const bool sw_pow2 = (SW & (SW - 1)) == 0;
+  const int sw_shift = 31 - __clz(SW > 0 ? SW : 1);
 
   for (int i = threadIdx.x; i < S; i += blockDim.x) {
     s_tab[i] = p.table_ptrs ? p.table_ptrs[i] : p.single_table;
     s_lin[i] = p.lin_ptrs ? p.lin_ptrs[i] : nullptr;
     s_rows[i] = p.rows ? p.rows[i] : p.single_rows;
+    s_off[i] = p.slot_offsets ? p.slot_offsets[i] : 0;
   }
+  for (int i = threadIdx.x; i < SW; i += blockDim.x) s_peer[i] = p.peer_bases[i];
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
@@ -131,7 +149,18 @@ __global__ void __launch_bounds__(512) embed_fm_fwd_kernel(const EmbedFwdParams 
         v[u] = f4_zero();
         if (s < S && ex_ok && (chunk_ok || lin_lane)) {
           const int64_t id = (int64_t)my[s];
-          if ((uint64_t)id < (uint64_t)s_rows[s]) v[u] = ldg_nc_na(s_tab[s] + (size_t)id * p.row_stride + c * 4);
+          if ((uint64_t)id < (uint64_t)s_rows[s]) {
+            const float* rowp;
+            if (SW == 0) {
+              rowp = s_tab[s] + (size_t)id * p.row_stride;
+            } else {   // row-sharded: the owner's arena is read directly over NVLink
+              const int64_t r = s_off[s] + id;
+              const int owner = sw_pow2 ? (int)(r & (SW - 1)) : (int)(r % SW);
+              const int64_t local = sw_pow2 ? (r >> sw_shift) : (r / SW);
+              rowp = s_peer[owner] + (size_t)local * p.row_stride;
+            }
+            v[u] = ldg_nc_na(rowp + c * 4);
+          }
         }
       }
 #pragma unroll
@@ -318,11 +347,18 @@ __global__ void __launch_bounds__(256) embed_fm_bwd_sp_kernel(const EmbedBwdPara
   float** s_tab = reinterpret_cast<float**>(smem_raw);
   float** s_lin = s_tab + S;
   int64_t* s_rows = reinterpret_cast<int64_t*>(s_lin + S);
+  int64_t* s_off = s_rows + S;
+  float** s_peer = reinterpret_cast<float**>(s_off + S);
+  const int SW = p.shard_world;
+  const bool sw_pow2 = (SW & (SW - 1)) == 0;
+  const int sw_shift = 31 - __clz(SW > 0 ? SW : 1);
   for (int i = threadIdx.x; i < S; i += blockDim.x) {
     s_tab[i] = p.grad_table_ptrs ? p.grad_table_ptrs[i] : p.single_grad;
     s_lin[i] = p.grad_lin_ptrs ? p.grad_lin_ptrs[i] : nullptr;
     s_rows[i] = p.rows ? p.rows[i] : p.single_rows;
+    s_off[i] = p.slot_offsets ? p.slot_offsets[i] : 0;
   }
+  for (int i = threadIdx.x; i < SW; i += blockDim.x) s_peer[i] = p.peer_bases[i];
   __syncthreads();
 
   const int lane = threadIdx.x & 31, warp_in_cta = threadIdx.x >> 5, warps_per_cta = blockDim.x >> 5;
@@ -371,7 +407,15 @@ __global__ void __launch_bounds__(256) embed_fm_bwd_sp_kernel(const EmbedBwdPara
       for (int u = 0; u < U; ++u) {
         const int s = s0 + u * SPW + sg;
         if (s < S && (uint64_t)id[u] < (uint64_t)s_rows[s]) {
-          float* row = s_tab[s] + (size_t)id[u] * p.row_stride;
+          float* row;
+          if (SW == 0) {
+            row = s_tab[s] + (size_t)id[u] * p.row_stride;
+          } else {     // row-sharded: vector atomics straight into the owner's arena over NVLink
+            const int64_t r = s_off[s] + id[u];
+            const int owner = sw_pow2 ? (int)(r & (SW - 1)) : (int)(r % SW);
+            const int64_t local = sw_pow2 ? (r >> sw_shift) : (r / SW);
+            row = s_peer[owner] + (size_t)local * p.row_stride;
+          }
           if (chunk_ok) {
             float4 d;
             d.x = scale * fmaf(gl, sum.x - e[u].x, gs[u].x);
@@ -508,7 +552,7 @@ static int launch_bwd_u(const EmbedBwdParams& p, cudaStream_t st) {
 template <int LPR, typename IdT, int U>
 static int launch_bwd_sp_u(const EmbedBwdParams& p, cudaStream_t st) {
   const int threads = 256, warps = threads / 32;
-  const size_t smem = (size_t)p.S * (sizeof(void*) * 2 + sizeof(int64_t));
+  const size_t smem = (size_t)p.S * (sizeof(void*) * 2 + sizeof(int64_t) * 2) + kMaxShardWorld * sizeof(void*);
   int64_t ctas = (p.B + warps - 1) / warps;
   int per_sm = g_tune_embed_ctas_per_sm > 0 ? g_tune_embed_ctas_per_sm : 8;
   if (ctas > (int64_t)kNumSMs * per_sm) ctas = (int64_t)kNumSMs * per_sm;
@@ -667,4 +711,69 @@ extern "C" int dr_scatter_add(float* grad_table, int64_t rows, const void* ids, 
     scatter_add_rows_kernel<int32_t><<<(unsigned)ctas, 256, 0, st>>>(grad_table, rows, (const int32_t*)ids, n, chunks, g, scale);
   DR_CUDA_LAUNCH_CHECK("scatter_add_rows");
   return DR_OK;
+}
+
+// ---- row-sharded entries: the gather / scatter IS the exchange (NVLink peer memory) -------------------
+extern "C" int dr_embed_fm_fwd_sharded(const float* const* peer_bases, int world, const int64_t* slot_offsets,
+                                       const int64_t* rows, const void* ids, int id_bytes, const float* bias,
+                                       int64_t B, int S, int D, int64_t row_stride, int flags, float* out_stack,
+                                       float* out_sum, float* out_logit, void* stream) {
+  if (int rc = check_dims("dr_embed_fm_fwd_sharded", B, S, D, id_bytes)) return rc;
+  if (B == 0) return DR_OK;
+  DR_REQUIRE(peer_bases && slot_offsets && rows && ids, DR_EINVAL, "dr_embed_fm_fwd_sharded: null pointer");
+  DR_REQUIRE(world >= 1 && world <= kMaxShardWorld, DR_EINVAL, "dr_embed_fm_fwd_sharded: world=%d outside [1,%d]",
+             world, kMaxShardWorld);
+  DR_REQUIRE(out_stack || out_logit || out_sum, DR_EINVAL, "dr_embed_fm_fwd_sharded: no output requested");
+  const int lin_in_row = (flags & DR_EMBED_LIN_IN_ROW) ? 1 : 0;
+  DR_REQUIRE(row_stride >= D + (lin_in_row ? 4 : 0) && row_stride % 4 == 0 && (!lin_in_row || D <= 124), DR_EINVAL,
+             "dr_embed_fm_fwd_sharded: bad row_stride=%lld for D=%d", (long long)row_stride, D);
+  DR_REQUIRE(!out_stack || aligned16(out_stack), DR_EALIGN, "dr_embed_fm_fwd_sharded: out_stack not 16-B aligned");
+  EmbedFwdParams p{};
+  p.rows = rows; p.ids = ids; p.bias = bias; p.B = B; p.S = S; p.D = D;
+  p.out_stack = out_stack; p.out_sum = out_sum; p.out_logit = out_logit;
+  p.row_stride = row_stride; p.lin_stride = row_stride; p.lin_in_row = lin_in_row;
+  p.shard_world = world; p.peer_bases = peer_bases; p.slot_offsets = slot_offsets;
+  cudaStream_t st = (cudaStream_t)stream;
+  DR_DISPATCH_LPR(launch_fwd, p, st);
+}
+
+extern "C" int dr_embed_fm_bwd_sharded(float* const* peer_bases, int world, const int64_t* slot_offsets,
+                                       const int64_t* rows, const void* ids, int id_bytes, const float* stack,
+                                       const float* sum_e, const float* g_logit, const float* g_stack, int64_t B,
+                                       int S, int D, int64_t row_stride, int flags, float* g_bias, float scale,
+                                       void* stream) {
+  if (int rc = check_dims("dr_embed_fm_bwd_sharded", B, S, D, id_bytes)) return rc;
+  if (B == 0) return DR_OK;
+  DR_REQUIRE(peer_bases && slot_offsets && rows && ids, DR_EINVAL, "dr_embed_fm_bwd_sharded: null pointer");
+  DR_REQUIRE(world >= 1 && world <= kMaxShardWorld, DR_EINVAL, "dr_embed_fm_bwd_sharded: world=%d outside [1,%d]",
+             world, kMaxShardWorld);
+  DR_REQUIRE(g_logit || g_stack, DR_EINVAL, "dr_embed_fm_bwd_sharded: both g_logit and g_stack are NULL");
+  DR_REQUIRE(!g_logit || stack, DR_EINVAL, "dr_embed_fm_bwd_sharded: g_logit given but stack is NULL");
+  const int lin_in_row = (flags & DR_EMBED_LIN_IN_ROW) ? 1 : 0;
+  DR_REQUIRE(row_stride >= D + (lin_in_row ? 4 : 0) && row_stride % 4 == 0 && (!lin_in_row || D <= 124), DR_EINVAL,
+             "dr_embed_fm_bwd_sharded: bad row_stride=%lld for D=%d", (long long)row_stride, D);
+  EmbedBwdParams p{};
+  p.ids = ids; p.rows = rows; p.stack = stack; p.sum_e = sum_e; p.g_logit = g_logit; p.g_stack = g_stack;
+  p.B = B; p.S = S; p.D = D; p.g_bias = g_bias; p.scale = scale;
+  p.row_stride = row_stride; p.lin_stride = row_stride; p.lin_in_row = lin_in_row;
+  p.shard_world = world; p.peer_bases = peer_bases; p.slot_offsets = slot_offsets;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int saved_mode = g_tune_embed_bwd_mode;
+  g_tune_embed_bwd_mode = 0;      // only the slot-parallel kernel implements sharded addressing
+  int rc;
+  do {
+    const int lpr__ = lpr_for(p.D, p.lin_in_row);
+#define DR_SH(L) (id_bytes == 8 ? launch_bwd<L, int64_t>(p, st) : launch_bwd<L, int32_t>(p, st))
+    switch (lpr__) {
+      case 1: rc = DR_SH(1); break;
+      case 2: rc = DR_SH(2); break;
+      case 4: rc = DR_SH(4); break;
+      case 8: rc = DR_SH(8); break;
+      case 16: rc = DR_SH(16); break;
+      default: rc = DR_SH(32); break;
+    }
+#undef DR_SH
+  } while (0);
+  g_tune_embed_bwd_mode = saved_mode;
+  return rc;
 }

@@ -29,19 +29,37 @@ from .keras.layers.base import Dense
 
 
 class ShardedEmbedding:
-    """This rank's shard of the global row space, fused layout [local_rows, D+4]."""
+    """This rank's shard of the global row space, fused rows [emb | w | pad].
 
-    def __init__(self, rows: Sequence[int], dim: int, rank: int, world: int, device, seed: Optional[int] = None):
+    exchange="nccl": rows of D+4 floats in ordinary device memory, moved by all-to-all.
+    exchange="p2p" : rows padded to whole 128-B lines in SYMMETRIC memory (every rank maps every
+                     other rank's shard), read / updated in place over NVLink by the fused kernels.
+    """
+
+    def __init__(self, rows: Sequence[int], dim: int, rank: int, world: int, device, seed: Optional[int] = None,
+                 exchange: str = "nccl", group=None):
         if dim + 4 > 128:
             raise NotImplementedError("sharded fused rows need D + 4 <= 128 in this round")
         self.rows_list = [int(r) for r in rows]
         self.dim, self.rank, self.world = int(dim), rank, world
-        self.vdim = self.dim + 4
+        self.vdim = self.dim + 4 if exchange == "nccl" else (self.dim + 4 + 31) // 32 * 32
         self.total_rows = sum(self.rows_list)
         self.local_rows = shard_plan.local_rows(self.total_rows, rank, world)
         self.device = device
+        self.handle = None
+        self.peer_ptrs = None
         std = 1.0 / self.dim ** 0.5
-        w = torch.zeros((self.local_rows, self.vdim), dtype=torch.float32, device=device)
+        if exchange == "p2p":
+            import torch.distributed._symmetric_memory as symm_mem
+            max_rows = shard_plan.local_rows(self.total_rows, 0, world)       # same size on every rank
+            buf = symm_mem.empty((max_rows, self.vdim), dtype=torch.float32, device=device)
+            self.handle = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
+            buf.zero_()
+            w = buf[:self.local_rows]
+            self._buf = buf
+            self.peer_ptrs = torch.tensor([int(p) for p in self.handle.buffer_ptrs], dtype=torch.int64, device=device)
+        else:
+            w = torch.zeros((self.local_rows, self.vdim), dtype=torch.float32, device=device)
         gen = torch.Generator(device=device).manual_seed((seed or 0) * 1000 + rank)
         torch.nn.init.trunc_normal_(w[:, :self.dim], 0.0, std, -2 * std, 2 * std, generator=gen)
         self.weight = w
@@ -51,7 +69,7 @@ class ShardedEmbedding:
 
 class ShardedDeepFMTrainStep:
     def __init__(self, columns, dim: int, dnn_units: Sequence[int], batch_size: int, lr: float = 0.01,
-                 seed: int = 0, device=None, group=None, use_graph: bool = True):
+                 seed: int = 0, device=None, group=None, use_graph: bool = True, exchange: str = "p2p"):
         if not dist.is_initialized():
             raise RuntimeError("ShardedDeepFMTrainStep needs an initialised torch.distributed process group")
         self.lib = _lib.load()
@@ -64,7 +82,10 @@ class ShardedDeepFMTrainStep:
         rows = [c.num_buckets for c in columns]
         self.B, self.S, self.D = int(batch_size), len(rows), int(dim)
         self.lr = float(lr)
-        self.emb = ShardedEmbedding(rows, dim, self.rank, self.world, dev, seed)
+        if exchange not in ("p2p", "nccl"):
+            raise ValueError(f"exchange must be 'p2p' or 'nccl', got {exchange!r}")
+        self.exchange = exchange
+        self.emb = ShardedEmbedding(rows, dim, self.rank, self.world, dev, seed, exchange, group)
         B, S, D, G = self.B, self.S, self.D, self.world
         self.n = B * S
         self.cap = shard_plan.capacity(self.n, G)
@@ -97,15 +118,16 @@ class ShardedDeepFMTrainStep:
         # warm-up ids spread over the tables (all-zero ids would all hit one owner)
         self.ids = torch.stack([torch.randint(0, max(1, r), (B,), device=dev) for r in rows], dim=1).contiguous()
         self.labels = torch.zeros((B,), **f)
-        self.send_counts = torch.zeros((G,), device=dev, dtype=torch.int64)
-        self.send_ids = torch.empty((G * self.cap,), device=dev, dtype=torch.int64)
-        self.recv_ids = torch.empty((G * self.cap,), device=dev, dtype=torch.int64)
-        self.inv = torch.empty((self.n,), device=dev, dtype=torch.int32)
-        self.overflow = torch.zeros((1,), device=dev, dtype=torch.int32)
-        self.vec_send = torch.empty((G * self.cap, V), **f)      # rows gathered for the requesters
-        self.vec_recv = torch.empty((G * self.cap, V), **f)      # rows this rank asked for
-        self.grad_send = torch.empty((G * self.cap, V), **f)
-        self.grad_recv = torch.empty((G * self.cap, V), **f)
+        if exchange == "nccl":
+            self.send_counts = torch.zeros((G,), device=dev, dtype=torch.int64)
+            self.send_ids = torch.empty((G * self.cap,), device=dev, dtype=torch.int64)
+            self.recv_ids = torch.empty((G * self.cap,), device=dev, dtype=torch.int64)
+            self.inv = torch.empty((self.n,), device=dev, dtype=torch.int32)
+            self.overflow = torch.zeros((1,), device=dev, dtype=torch.int32)
+            self.vec_send = torch.empty((G * self.cap, V), **f)      # rows gathered for the requesters
+            self.vec_recv = torch.empty((G * self.cap, V), **f)      # rows this rank asked for
+            self.grad_send = torch.empty((G * self.cap, V), **f)
+            self.grad_recv = torch.empty((G * self.cap, V), **f)
         self.stack = torch.empty((B, S, D), **f)
         self.sum_e = torch.empty((B, D), **f)
         self.fm_logit = torch.empty((B,), **f)
@@ -115,14 +137,15 @@ class ShardedDeepFMTrainStep:
         self.g_stack = torch.empty((B, S, D), **f)
         self.loss = torch.zeros((1,), **f)
         self.prob = torch.empty((B,), **f)
-        # "identity tables": the S slots all read the receive buffer (table base = vec_recv, rows = G*cap)
-        base = self.vec_recv.data_ptr()
-        self.tp = torch.full((S,), base, device=dev, dtype=torch.int64)
-        self.lp = torch.full((S,), base + D * 4, device=dev, dtype=torch.int64)
-        gbase = self.grad_send.data_ptr()
-        self.gtp = torch.full((S,), gbase, device=dev, dtype=torch.int64)
-        self.glp = torch.full((S,), gbase + D * 4, device=dev, dtype=torch.int64)
-        self.trows = torch.full((S,), G * self.cap, device=dev, dtype=torch.int64)
+        if exchange == "nccl":
+            # "identity tables": the S slots all read the receive buffer (table base = vec_recv, rows = G*cap)
+            base = self.vec_recv.data_ptr()
+            self.tp = torch.full((S,), base, device=dev, dtype=torch.int64)
+            self.lp = torch.full((S,), base + D * 4, device=dev, dtype=torch.int64)
+            gbase = self.grad_send.data_ptr()
+            self.gtp = torch.full((S,), gbase, device=dev, dtype=torch.int64)
+            self.glp = torch.full((S,), gbase + D * 4, device=dev, dtype=torch.int64)
+            self.trows = torch.full((S,), G * self.cap, device=dev, dtype=torch.int64)
         kmax = max([S * D] + [l.units for l in layers])
         _lib.ensure_gemm_workspace(B, kmax, kmax, dev)
         self.graph = None
@@ -137,7 +160,71 @@ class ShardedDeepFMTrainStep:
 
     # The step is a chain  compute segment -> collective -> compute segment ...  The compute segments
     # are captured as CUDA graphs; the NCCL collectives are issued between the replays.
+    def _segments_p2p(self, mark):
+        """exchange="p2p": the fused gather+FM kernel reads every owner's shard directly over NVLink
+        and the backward's vector atomics land directly in the owner's shard -- no id exchange, no
+        owner-side gather/scatter kernels, no all-to-all.  The tower all-reduce separates the step's
+        remote reads from its remote updates; a symmetric-memory barrier ends the step."""
+        lib = self.lib
+        B, S, D, G, V = self.B, self.S, self.D, self.world, self.emb.vdim
+
+        def st():
+            return torch.cuda.current_stream().cuda_stream
+
+        def seg_main():
+            check(lib.dr_embed_fm_fwd_sharded(self.emb.peer_ptrs.data_ptr(), G, self.emb.slot_offsets.data_ptr(),
+                                              self.emb.rows.data_ptr(), self.ids.data_ptr(), 8, self.bias.data_ptr(),
+                                              B, S, D, V, 1, self.stack.data_ptr(), self.sum_e.data_ptr(),
+                                              self.fm_logit.data_ptr(), st()), "dr_embed_fm_fwd_sharded")
+            mark("embed_fm_fwd_p2p")
+            x, K = self.stack, S * D
+            for i, l in enumerate(self.layers):
+                check(lib.dr_dense_fwd(x.data_ptr(), self.w[i].data_ptr(), self.b[i].data_ptr(), B, K, l.units,
+                                       l._act, self.acts[i].data_ptr(), st()), "dr_dense_fwd")
+                x, K = self.acts[i], l.units
+                mark(f"dense_fwd_{i}")
+            gz = self.g_acts[-1]
+            check(lib.dr_bce_logits_fwd_bwd(self.acts[-1].data_ptr(), self.fm_logit.data_ptr(),
+                                            self.labels.data_ptr(), B, self.prob.data_ptr(), self.loss.data_ptr(),
+                                            gz.data_ptr(), st()), "dr_bce")
+            mark("bce")
+            for i in range(len(self.layers) - 1, -1, -1):
+                l = self.layers[i]
+                xin = self.stack if i == 0 else self.acts[i - 1]
+                Kin = S * D if i == 0 else self.layers[i - 1].units
+                gx = self.g_stack if i == 0 else self.g_acts[i - 1]
+                check(lib.dr_dense_bwd(xin.data_ptr(), self.w[i].data_ptr(), self.acts[i].data_ptr(),
+                                       self.g_acts[i].data_ptr(), B, Kin, l.units, l._act, ops._ptr(self.gz_ws[i]),
+                                       gx.data_ptr(), self.gw[i].data_ptr(), self.gb[i].data_ptr(), st()),
+                      "dr_dense_bwd")
+                mark(f"dense_bwd_{i}")
+            torch.sum(gz.view(-1), dim=0, keepdim=True, out=self.g_bias)      # FM bias gradient (tiny)
+            mark("bias_grad")
+
+        def col_allreduce():
+            dist.all_reduce(self.gflat, group=self.group)      # also: every rank has finished its remote reads
+            mark("allreduce_dense")
+
+        def seg_update():
+            gz = self.g_acts[-1]
+            check(lib.dr_embed_fm_bwd_sharded(self.emb.peer_ptrs.data_ptr(), G, self.emb.slot_offsets.data_ptr(),
+                                              self.emb.rows.data_ptr(), self.ids.data_ptr(), 8, self.stack.data_ptr(),
+                                              self.sum_e.data_ptr(), gz.data_ptr(), self.g_stack.data_ptr(), B, S, D,
+                                              V, 1, None, -self.lr / G, st()), "dr_embed_fm_bwd_sharded")
+            mark("embed_fm_bwd_p2p")
+            check(lib.dr_sgd_step(self.flat.data_ptr(), self.gflat.data_ptr(), self.flat.numel(), self.lr / G, st()),
+                  "dr_sgd_step")
+            mark("sgd")
+
+        def col_barrier():
+            self.emb.handle.barrier(channel=0)          # all remote atomics of this step have been issued
+            mark("barrier")
+
+        return [(seg_main, True), (col_allreduce, False), (seg_update, True), (col_barrier, False)]
+
     def _segments(self, mark):
+        if self.exchange == "p2p":
+            return self._segments_p2p(mark)
         lib = self.lib
         B, S, D, G, V = self.B, self.S, self.D, self.world, self.emb.vdim
 
@@ -256,6 +343,8 @@ class ShardedDeepFMTrainStep:
         return self
 
     def check_overflow(self):
+        if self.exchange == "p2p":
+            return
         if int(self.overflow.item()) != 0:
             raise _lib.DeepRecError(f"shard exchange overflow: a destination needed more than cap={self.cap} slots; "
                                     "raise shard_plan.capacity slack (skewed ids)")
@@ -319,4 +408,4 @@ class ShardedDeepFMTrainStep:
             for (l0, e0), (l1, e1) in zip(evs[:-1], evs[1:]):
                 sums[l1] = sums.get(l1, 0.0) + e0.elapsed_time(e1)
         shares = {k: v / count for k, v in sums.items()}
-        return {"embed_fm_fwd_ms": shares["embed_fm_fwd"]}, shares
+        return {"embed_fm_fwd_ms": shares.get("embed_fm_fwd", shares.get("embed_fm_fwd_p2p"))}, shares

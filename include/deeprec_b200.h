@@ -201,6 +201,25 @@ int dr_shard_bucket_ids(const void* ids, int id_bytes, int64_t n, int S,
                         const int64_t* slot_offsets, const int64_t* rows, int G, int64_t cap,
                         int64_t* send_counts, int64_t* send_ids, int32_t* inv, int32_t* overflow,
                         void* stream);
+/* Row-sharded gather / update fused with the exchange over NVLink peer memory (the B200 path for
+ * N > 1).  peer_bases[world] (device array): base of every rank's arena, mapped into this process
+ * (CUDA IPC / symmetric memory); all ranks use the same row_stride.  Lookup (s, id) reads global
+ * row slot_offsets[s] + id from rank (row mod world) at local row (row div world) -- the LDG.128
+ * wave that gathers the row is itself the transfer, so there is no id exchange, no owner-side
+ * gather and no all-to-all.  The backward issues its vector atomics (red.global.add.v4.f32)
+ * straight into the owner's arena.  The caller separates a step's remote reads from its remote
+ * updates with a collective on the tower gradients and ends the step with a barrier.
+ * Same outputs / gradient formulas as dr_embed_fm_fwd / dr_embed_fm_bwd.                         */
+int dr_embed_fm_fwd_sharded(const float* const* peer_bases, int world, const int64_t* slot_offsets,
+                            const int64_t* rows, const void* ids, int id_bytes, const float* bias,
+                            int64_t B, int S, int D, int64_t row_stride, int flags,
+                            float* out_stack, float* out_sum, float* out_logit, void* stream);
+int dr_embed_fm_bwd_sharded(float* const* peer_bases, int world, const int64_t* slot_offsets,
+                            const int64_t* rows, const void* ids, int id_bytes, const float* stack,
+                            const float* sum_e, const float* g_logit, const float* g_stack,
+                            int64_t B, int S, int D, int64_t row_stride, int flags,
+                            float* g_bias, float scale, void* stream);
+
 int dr_permute_rows(const float* in, const int32_t* perm, int64_t n, int D, float* out, void* stream);
 int dr_unpermute_rows(const float* in, const int32_t* perm, int64_t n, int D, float* out, void* stream);
 

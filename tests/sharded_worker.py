@@ -17,16 +17,30 @@ def main():
     from deep_recommenders_b200.keras.models.ranking import DeepFM
     from deep_recommenders_b200.sharded import ShardedDeepFMTrainStep
     from deep_recommenders_b200.training import DeepFMTrainStep
+    for exchange in ("p2p", "nccl"):
+        run(exchange, rank, world, dev)
+    dist.barrier()
+    if rank == 0:
+        print("SHARDED_OK")
+    dist.destroy_process_group()
+
+
+def run(exchange, rank, world, dev):
+    from deep_recommenders_b200 import feature_column as fc
+    from deep_recommenders_b200.keras.models.ranking import DeepFM
+    from deep_recommenders_b200.sharded import ShardedDeepFMTrainStep
+    from deep_recommenders_b200.training import DeepFMTrainStep
     S, D, rows, B = 6, 16, [3000, 7, 500, 1000, 21, 64], 1024
     cols = [fc.categorical_column_with_identity(f"c{i}", r) for i, r in enumerate(rows)]
-    sh = ShardedDeepFMTrainStep(cols, D, [32, 8], batch_size=B, lr=0.05, seed=3, device=dev)
+    sh = ShardedDeepFMTrainStep(cols, D, [32, 8], batch_size=B, lr=0.05, seed=3, device=dev, exchange=exchange)
     total = sum(rows)
     # global arena, identical on all ranks (seeded), scattered into the shards
     g = torch.Generator(device=dev).manual_seed(11)
     arena = torch.zeros((total, D + 4), device=dev)
     arena[:, :D].normal_(0, 0.25, generator=g)
     arena[:, D].normal_(0, 0.1, generator=g)
-    sh.emb.weight.copy_(arena[rank::world])
+    sh.emb.weight[:, :D + 4].copy_(arena[rank::world])
+    dist.barrier()
     # unsharded twin on the GLOBAL batch (every rank computes it redundantly)
     model = DeepFM([fc.indicator_column(c) for c in cols], [fc.embedding_column(c, D) for c in cols],
                    dnn_units_size=[32, 8], seed=3, device=dev, sparse_lr=0.05)
@@ -52,10 +66,8 @@ def main():
     assert torch.allclose(sh.emb.weight[:, :D + 1], want, rtol=1e-4, atol=1e-6), float((sh.emb.weight[:, :D + 1] - want).abs().max())
     for i in range(len(ref.layers)):
         assert torch.allclose(sh.w[i], ref.w[i], rtol=1e-4, atol=1e-6)
+    torch.cuda.synchronize()
     dist.barrier()
-    if rank == 0:
-        print("SHARDED_OK")
-    dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -27,7 +27,8 @@ def _free_port():
     return p
 
 
-def test_world1_sharded_step_equals_single_gpu_step():
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+def test_world1_sharded_step_equals_single_gpu_step(exchange):
     import torch.distributed as dist
     from deep_recommenders_b200 import feature_column as fc
     from deep_recommenders_b200.keras.models.ranking import DeepFM
@@ -38,7 +39,7 @@ def test_world1_sharded_step_equals_single_gpu_step():
     try:
         S, D, rows, B = 5, 16, [300, 7, 50, 1000, 21], 384
         cols = [fc.categorical_column_with_identity(f"c{i}", r) for i, r in enumerate(rows)]
-        sh = ShardedDeepFMTrainStep(cols, D, [32, 8], batch_size=B, lr=0.05, seed=3, device="cuda")
+        sh = ShardedDeepFMTrainStep(cols, D, [32, 8], batch_size=B, lr=0.05, seed=3, device="cuda", exchange=exchange)
         model = DeepFM([fc.indicator_column(c) for c in cols], [fc.embedding_column(c, D) for c in cols],
                        dnn_units_size=[32, 8], seed=3, device="cuda", sparse_lr=0.05)
         ref = DeepFMTrainStep(model, batch_size=B, lr=0.05, use_graph=False)
