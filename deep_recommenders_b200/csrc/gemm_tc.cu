@@ -26,6 +26,7 @@ namespace dr {
 
 // ---- workspace registered by the host (dr_set_workspace) ----------------------------------------
 int g_tune_gemm_bn = 0;   // 0 = auto, 128 or 256: tensor-core tile width
+int g_tune_tc_mn = 0;     // 1 = feed MN-major operands as stored (SWIZZLE_128B_BASE32B) instead of transposing them
 static void* g_ws_ptr = nullptr;
 static size_t g_ws_bytes = 0;
 
@@ -88,13 +89,16 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
 }
 
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B, version 1.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout_type: 2 = SWIZZLE_128B (K-major operands), 1 = SWIZZLE_128B_BASE32B (the only layout UMMA
+// accepts for MN-major 32-bit operands; TMA counterpart CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;   // LayoutType::SWIZZLE_128B
+  d |= (uint64_t)layout_type << 61;
   return d;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): TF32 x TF32 -> F32, dense.
@@ -203,7 +207,7 @@ __device__ __forceinline__ TcItem tc_decode(int64_t item, int64_t n_tiles, int64
 
 // Persistent, warp-specialised: the accumulator is double buffered in TMEM (2 x BN columns) so the
 // epilogue of item j overlaps the TMA/MMA main loop of item j+1.
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
@@ -260,10 +264,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           mbar_expect_tx(&full_bar[s], (uint32_t)STAGE);
           uint8_t* st = smem + (size_t)s * STAGE;
           const int k = (t.kb0 + i) * TC_BK;
-          tma_load_2d(st, &tmAh, &full_bar[s], k, (int)t.m0);
-          tma_load_2d(st + A_TILE, &tmAl, &full_bar[s], k, (int)t.m0);
-          tma_load_2d(st + 2 * A_TILE, &tmBh, &full_bar[s], k, (int)t.n0);
-          tma_load_2d(st + 2 * A_TILE + B_TILE, &tmBl, &full_bar[s], k, (int)t.n0);
+          if (!A_MN) {
+            tma_load_2d(st, &tmAh, &full_bar[s], k, (int)t.m0);
+            tma_load_2d(st + A_TILE, &tmAl, &full_bar[s], k, (int)t.m0);
+          } else {     // MN-major: one [32 k-rows x 32 floats] box per 32-wide MN atom
+#pragma unroll
+            for (int jj = 0; jj < TC_BM / 32; ++jj) {
+              tma_load_2d(st + jj * 4096, &tmAh, &full_bar[s], (int)t.m0 + jj * 32, k);
+              tma_load_2d(st + A_TILE + jj * 4096, &tmAl, &full_bar[s], (int)t.m0 + jj * 32, k);
+            }
+          }
+          if (!B_MN) {
+            tma_load_2d(st + 2 * A_TILE, &tmBh, &full_bar[s], k, (int)t.n0);
+            tma_load_2d(st + 2 * A_TILE + B_TILE, &tmBl, &full_bar[s], k, (int)t.n0);
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < BN / 32; ++jj) {
+              tma_load_2d(st + 2 * A_TILE + jj * 4096, &tmBh, &full_bar[s], (int)t.n0 + jj * 32, k);
+              tma_load_2d(st + 2 * A_TILE + B_TILE + jj * 4096, &tmBl, &full_bar[s], (int)t.n0 + jj * 32, k);
+            }
+          }
         }
       }
     }
@@ -271,7 +291,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
-      constexpr uint32_t idesc = make_idesc(TC_BM, BN, false, false);
+      constexpr uint32_t idesc = make_idesc(TC_BM, BN, A_MN, B_MN);
       uint32_t it = 0, j = 0;
       for (int64_t item = blockIdx.x; item < total_items; item += gridDim.x, ++j) {
         const TcItem t = tc_decode(item, n_tiles, m_tiles, kblocks, per, BN);
@@ -289,11 +309,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
 #pragma unroll
           for (int k = 0; k < TC_BK / 8; ++k) {
             // K-major SWIZZLE_128B: one k-step = 8 tf32 = 32 B inside the 128-B row; 8-row groups 1024 B apart
-            const uint32_t off = (uint32_t)k * 32u;
-            const uint64_t dAh = make_smem_desc(sa + off, 16u, 1024u);
-            const uint64_t dAl = make_smem_desc(sa + A_TILE + off, 16u, 1024u);
-            const uint64_t dBh = make_smem_desc(sb + off, 16u, 1024u);
-            const uint64_t dBl = make_smem_desc(sb + B_TILE + off, 16u, 1024u);
+            // MN-major SWIZZLE_128B_BASE32B: one k-step = 8 k-rows = 1024 B (two 4-row swizzle groups 512 B
+            // apart), 32-wide MN atoms 4096 B apart.
+            const uint32_t a_off = A_MN ? (uint32_t)k * 1024u : (uint32_t)k * 32u;
+            const uint32_t b_off = B_MN ? (uint32_t)k * 1024u : (uint32_t)k * 32u;
+            const uint32_t a_lbo = A_MN ? 4096u : 16u, a_sbo = A_MN ? 512u : 1024u, a_lt = A_MN ? 1u : 2u;
+            const uint32_t b_lbo = B_MN ? 4096u : 16u, b_sbo = B_MN ? 512u : 1024u, b_lt = B_MN ? 1u : 2u;
+            const uint64_t dAh = make_smem_desc(sa + a_off, a_lbo, a_sbo, a_lt);
+            const uint64_t dAl = make_smem_desc(sa + A_TILE + a_off, a_lbo, a_sbo, a_lt);
+            const uint64_t dBh = make_smem_desc(sb + b_off, b_lbo, b_sbo, b_lt);
+            const uint64_t dBl = make_smem_desc(sb + B_TILE + b_off, b_lbo, b_sbo, b_lt);
             const uint32_t acc0 = (i > 0 || k > 0) ? 1u : 0u;
             tc_mma_tf32(d_tmem, dAl, dBh, idesc, acc0);   // small cross terms first
             tc_mma_tf32(d_tmem, dAh, dBl, idesc, 1u);
@@ -376,13 +401,16 @@ static int get_encode() {
 }
 
 // 2-D fp32 tensor [outer, inner] (inner contiguous, pitch floats), box {32, box_outer}, SWIZZLE_128B.
-static int make_map(CUtensorMap* tm, const float* base, int64_t inner, int64_t outer, int64_t pitch, int box_outer) {
+static int make_map(CUtensorMap* tm, const float* base, int64_t inner, int64_t outer, int64_t pitch, int box_outer,
+                    bool mn_major = false) {
   cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
   cuuint64_t strides[1] = {(cuuint64_t)pitch * 4};
   cuuint32_t box[2] = {32u, (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("gemm_tc: cuTensorMapEncodeTiled failed (CUresult %d; inner=%lld outer=%lld pitch=%lld)", (int)r,
@@ -398,6 +426,11 @@ static inline int64_t round4(int64_t v) { return (v + 3) & ~(int64_t)3; }
 // already K-major keeps its source pitch (one flat float4 pass); a transposed one gets round4(K).
 static void plane_elems(const GemmArgs& a, bool ta, bool tb, size_t* ae, size_t* be) {
   const int64_t kp = round4(a.K);
+  if (g_tune_tc_mn) {       // operands stay in their stored layout (flat split, source pitch)
+    *ae = (size_t)(ta ? a.K : a.M) * (size_t)a.lda;
+    *be = (size_t)(tb ? a.N : a.K) * (size_t)a.ldb;
+    return;
+  }
   *ae = (size_t)a.M * (size_t)(!ta ? a.lda : kp);
   *be = (size_t)a.N * (size_t)(tb ? a.ldb : kp);
 }
@@ -406,8 +439,8 @@ bool gemm_tc_eligible(const GemmArgs& a, bool ta, bool tb) {
   if (g_tune_gemm_variant != 1) return false;
   if (a.N < 96 || a.M < 64 || a.K < 32) return false;
   // operands already K-major are split in place with float4 accesses
-  if (!ta && ((a.lda & 3) || !aligned16(a.A))) return false;
-  if (tb && ((a.ldb & 3) || !aligned16(a.B))) return false;
+  if ((!ta || g_tune_tc_mn) && ((a.lda & 3) || !aligned16(a.A))) return false;
+  if ((tb || g_tune_tc_mn) && ((a.ldb & 3) || !aligned16(a.B))) return false;
   size_t ae, be;
   plane_elems(a, ta, tb, &ae, &be);
   const size_t need = (ae + be) * 2 * sizeof(float) + 4096;
@@ -416,11 +449,11 @@ bool gemm_tc_eligible(const GemmArgs& a, bool ta, bool tb) {
   return true;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool A_MN, bool B_MN>
 static int launch_tc(const CUtensorMap* tms, const GemmArgs& a, cudaStream_t st) {
   constexpr int STAGE = 2 * TC_BM * TC_BK * 4 + 2 * BN * TC_BK * 4;
   const size_t smem = (size_t)STAGES * STAGE + 1024;
-  auto k = gemm_tc_kernel<BN, STAGES>;
+  auto k = gemm_tc_kernel<BN, STAGES, A_MN, B_MN>;
   DR_CUDA_CALL(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t m_tiles = (a.M + TC_BM - 1) / TC_BM, n_tiles = (a.N + BN - 1) / BN;
   const int64_t kblocks = (a.K + TC_BK - 1) / TC_BK;
@@ -472,20 +505,44 @@ int gemm_tc_launch(const GemmArgs& a0, bool ta, bool tb, cudaStream_t st) {
   float* Bh = Al + ae;
   float* Bl = Bh + be;
   int64_t pa = 0, pb = 0;
+  CUtensorMap tms[4];
+  if (g_tune_tc_mn) {
+    // MN-major operands are consumed as stored (SWIZZLE_128B_BASE32B): no transposing pre-pass.
+    const bool A_MN = ta, B_MN = !tb;
+    if (int rc = make_planes(a.A, true, ta ? a.K : a.M, 0, a.lda, Ah, Al, &pa, st)) return rc;
+    if (int rc = make_planes(a.B, true, tb ? a.N : a.K, 0, a.ldb, Bh, Bl, &pb, st)) return rc;
+    if (!A_MN) {
+      if (int rc = make_map(&tms[0], Ah, a.K, a.M, pa, TC_BM)) return rc;
+      if (int rc = make_map(&tms[1], Al, a.K, a.M, pa, TC_BM)) return rc;
+    } else {
+      if (int rc = make_map(&tms[0], Ah, a.M, a.K, pa, TC_BK, true)) return rc;
+      if (int rc = make_map(&tms[1], Al, a.M, a.K, pa, TC_BK, true)) return rc;
+    }
+    if (!B_MN) {
+      if (int rc = make_map(&tms[2], Bh, a.K, a.N, pb, 128)) return rc;
+      if (int rc = make_map(&tms[3], Bl, a.K, a.N, pb, 128)) return rc;
+    } else {
+      if (int rc = make_map(&tms[2], Bh, a.N, a.K, pb, TC_BK, true)) return rc;
+      if (int rc = make_map(&tms[3], Bl, a.N, a.K, pb, TC_BK, true)) return rc;
+    }
+    if (!A_MN && !B_MN) return launch_tc<128, 3, false, false>(tms, a, st);
+    if (!A_MN && B_MN) return launch_tc<128, 3, false, true>(tms, a, st);
+    if (A_MN && !B_MN) return launch_tc<128, 3, true, false>(tms, a, st);
+    return launch_tc<128, 3, true, true>(tms, a, st);
+  }
   // A(m,k): !ta -> stored [M,K] (already K-major);  ta -> stored [K,M] -> transpose
   if (int rc = make_planes(a.A, !ta, a.M, a.K, a.lda, Ah, Al, &pa, st)) return rc;
   // B(k,n):  tb -> stored [N,K] (already K-major); !tb -> stored [K,N] -> transpose
   if (int rc = make_planes(a.B, tb, a.N, a.K, a.ldb, Bh, Bl, &pb, st)) return rc;
-  // measured on B200 (profiles/gemm_tc_r01.md): 128 x 128 tiles with a 3-stage ring beat 128 x 256 with 2 stages
+  // measured on B200 (profiles/): 128 x 128 tiles with a 3-stage ring beat 128 x 256 with 2 stages
   const bool wide = (g_tune_gemm_bn == 256);
   const int BN = wide ? 256 : 128;
-  CUtensorMap tms[4];
   if (int rc = make_map(&tms[0], Ah, a.K, a.M, pa, TC_BM)) return rc;
   if (int rc = make_map(&tms[1], Al, a.K, a.M, pa, TC_BM)) return rc;
   if (int rc = make_map(&tms[2], Bh, a.K, a.N, pb, BN)) return rc;
   if (int rc = make_map(&tms[3], Bl, a.K, a.N, pb, BN)) return rc;
-  if (wide) return launch_tc<256, 2>(tms, a, st);
-  return launch_tc<128, 3>(tms, a, st);
+  if (wide) return launch_tc<256, 2, false, false>(tms, a, st);
+  return launch_tc<128, 3, false, false>(tms, a, st);
 }
 
 }  // namespace dr

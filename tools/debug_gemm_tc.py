@@ -21,7 +21,8 @@ def gemm(A, B, M, N, K, ta, tb, variant):
 
 def main():
     _lib.enable_tensor_core_gemm(1 << 30)
-    M, N, K = 128, 128, 32
+    _lib.tune("tc_mn", int(os.environ.get("DR_TC_MN", "0")))
+    M, N, K = [int(x) for x in os.environ.get("DR_MNK", "128,128,32").split(",")]
     for ta in (0, 1):
         for tb in (0, 1):
             print(f"==== ta={ta} tb={tb}")
