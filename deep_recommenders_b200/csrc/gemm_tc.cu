@@ -26,9 +26,18 @@ namespace dr {
 
 // ---- workspace registered by the host (dr_set_workspace) ----------------------------------------
 int g_tune_gemm_bn = 0;   // 0 = auto, 128 or 256: tensor-core tile width
-int g_tune_tc_mn = 0;     // 1 = feed MN-major operands as stored (SWIZZLE_128B_BASE32B) instead of transposing them
+int g_tune_tc_mn = 1;     // 1 = feed MN-major operands as stored (SWIZZLE_128B_BASE32B); 0 = transpose them in the split pre-pass
 static void* g_ws_ptr = nullptr;
 static size_t g_ws_bytes = 0;
+
+// Plane cache (dr_gemm_plane_cache): inside a train step every tensor is split into its TF32 hi/lo
+// planes ONCE and the planes are shared by all the GEMMs that read it (x: forward and dW; gz: dX and
+// dW; W: forward and dX).  Off by default: without it every GEMM call splits its own operands.
+struct PlaneEntry { const float* src; size_t elems; float* hi; float* lo; };
+static PlaneEntry g_planes[64];
+static int g_nplanes = 0;
+static bool g_cache_on = false;
+static size_t g_bump = 0;     // floats used at the front of the workspace
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;          // 32 tf32 = 128 bytes = one SWIZZLE_128B row
@@ -444,7 +453,7 @@ bool gemm_tc_eligible(const GemmArgs& a, bool ta, bool tb) {
   size_t ae, be;
   plane_elems(a, ta, tb, &ae, &be);
   const size_t need = (ae + be) * 2 * sizeof(float) + 4096;
-  if (!g_ws_ptr || g_ws_bytes < need) return false;
+  if (!g_ws_ptr || g_ws_bytes < need + (g_cache_on ? g_bump * sizeof(float) : 0)) return false;
   if (a.M >= ((int64_t)1 << 31) || a.K >= ((int64_t)1 << 31) || a.N >= ((int64_t)1 << 31)) return false;
   return true;
 }
@@ -499,7 +508,7 @@ int gemm_tc_launch(const GemmArgs& a0, bool ta, bool tb, cudaStream_t st) {
   size_t ae, be;
   plane_elems(a, ta, tb, &ae, &be);
   const size_t need = (ae + be) * 2 * sizeof(float);
-  DR_REQUIRE(g_ws_ptr && g_ws_bytes >= need, DR_EINVAL, "gemm_tc: workspace too small (%zu needed)", need);
+  DR_REQUIRE(g_ws_ptr && (g_tune_tc_mn || g_ws_bytes >= need), DR_EINVAL, "gemm_tc: workspace too small (%zu needed)", need);
   float* Ah = reinterpret_cast<float*>(g_ws_ptr);
   float* Al = Ah + ae;
   float* Bh = Al + ae;
@@ -509,8 +518,25 @@ int gemm_tc_launch(const GemmArgs& a0, bool ta, bool tb, cudaStream_t st) {
   if (g_tune_tc_mn) {
     // MN-major operands are consumed as stored (SWIZZLE_128B_BASE32B): no transposing pre-pass.
     const bool A_MN = ta, B_MN = !tb;
-    if (int rc = make_planes(a.A, true, ta ? a.K : a.M, 0, a.lda, Ah, Al, &pa, st)) return rc;
-    if (int rc = make_planes(a.B, true, tb ? a.N : a.K, 0, a.ldb, Bh, Bl, &pb, st)) return rc;
+    if (!g_cache_on) g_bump = 0;
+    auto planes = [&](const float* src, size_t elems, int64_t rows, int64_t ld, float** hi, float** lo,
+                      int64_t* pitch) -> int {
+      if (g_cache_on)
+        for (int i = 0; i < g_nplanes; ++i)
+          if (g_planes[i].src == src && g_planes[i].elems == elems) {
+            *hi = g_planes[i].hi; *lo = g_planes[i].lo; *pitch = ld;
+            return DR_OK;
+          }
+      DR_REQUIRE((g_bump + 2 * elems) * sizeof(float) <= g_ws_bytes, DR_EINVAL,
+                 "gemm_tc: workspace exhausted (%zu B registered)", g_ws_bytes);
+      *hi = reinterpret_cast<float*>(g_ws_ptr) + g_bump;
+      *lo = *hi + elems;
+      g_bump += 2 * elems;
+      if (g_cache_on && g_nplanes < 64) g_planes[g_nplanes++] = PlaneEntry{src, elems, *hi, *lo};
+      return make_planes(src, true, rows, 0, ld, *hi, *lo, pitch, st);
+    };
+    if (int rc = planes(a.A, ae, ta ? a.K : a.M, a.lda, &Ah, &Al, &pa)) return rc;
+    if (int rc = planes(a.B, be, tb ? a.N : a.K, a.ldb, &Bh, &Bl, &pb)) return rc;
     if (!A_MN) {
       if (int rc = make_map(&tms[0], Ah, a.K, a.M, pa, TC_BM)) return rc;
       if (int rc = make_map(&tms[1], Al, a.K, a.M, pa, TC_BM)) return rc;
@@ -547,7 +573,16 @@ int gemm_tc_launch(const GemmArgs& a0, bool ta, bool tb, cudaStream_t st) {
 
 }  // namespace dr
 
+extern "C" int dr_gemm_plane_cache(int enable) {
+  dr::g_nplanes = 0;
+  dr::g_bump = 0;
+  dr::g_cache_on = enable != 0;
+  return DR_OK;
+}
+
 extern "C" int dr_set_workspace(void* ptr, uint64_t bytes) {
+  dr::g_nplanes = 0;
+  dr::g_bump = 0;
   using namespace dr;
   DR_REQUIRE(ptr == nullptr || aligned16(ptr), DR_EALIGN, "dr_set_workspace: pointer not 16-B aligned");
   g_ws_ptr = ptr;

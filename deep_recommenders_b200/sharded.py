@@ -148,6 +148,9 @@ class ShardedDeepFMTrainStep:
             self.trows = torch.full((S,), G * self.cap, device=dev, dtype=torch.int64)
         kmax = max([S * D] + [l.units for l in layers])
         _lib.ensure_gemm_workspace(B, kmax, kmax, dev)
+        widths = [S * D] + [l.units for l in layers]
+        cache_bytes = 8 * (B * (widths[0] + 2 * sum(widths[1:])) + sum(a * b for a, b in zip(widths[:-1], widths[1:])))
+        _lib.set_workspace(max(cache_bytes * 5 // 4 + (1 << 20), _lib._workspace.numel() if _lib._workspace is not None else 0), dev)
         self.graph = None
         self.use_graph = use_graph
         self.graph_error = None
@@ -172,6 +175,7 @@ class ShardedDeepFMTrainStep:
             return torch.cuda.current_stream().cuda_stream
 
         def seg_main():
+            check(lib.dr_gemm_plane_cache(1), "dr_gemm_plane_cache")
             check(lib.dr_embed_fm_fwd_sharded(self.emb.peer_ptrs.data_ptr(), G, self.emb.slot_offsets.data_ptr(),
                                               self.emb.rows.data_ptr(), self.ids.data_ptr(), 8, self.bias.data_ptr(),
                                               B, S, D, V, 1, self.stack.data_ptr(), self.sum_e.data_ptr(),
@@ -198,6 +202,7 @@ class ShardedDeepFMTrainStep:
                                        gx.data_ptr(), self.gw[i].data_ptr(), self.gb[i].data_ptr(), st()),
                       "dr_dense_bwd")
                 mark(f"dense_bwd_{i}")
+            check(lib.dr_gemm_plane_cache(0), "dr_gemm_plane_cache")
             torch.sum(gz.view(-1), dim=0, keepdim=True, out=self.g_bias)      # FM bias gradient (tiny)
             mark("bias_grad")
 
@@ -252,6 +257,7 @@ class ShardedDeepFMTrainStep:
             mark("a2a_vectors")
 
         def seg_main():
+            check(lib.dr_gemm_plane_cache(1), "dr_gemm_plane_cache")
             check(lib.dr_embed_fm_fwd(self.tp.data_ptr(), self.lp.data_ptr(), self.trows.data_ptr(),
                                       self.inv.data_ptr(), 4, self.bias.data_ptr(), B, S, D, V, V, 1,
                                       self.stack.data_ptr(), self.sum_e.data_ptr(), self.fm_logit.data_ptr(), st()),
@@ -278,6 +284,7 @@ class ShardedDeepFMTrainStep:
                                        gx.data_ptr(), self.gw[i].data_ptr(), self.gb[i].data_ptr(), st()),
                       "dr_dense_bwd")
                 mark(f"dense_bwd_{i}")
+            check(lib.dr_gemm_plane_cache(0), "dr_gemm_plane_cache")
             # pack per-lookup gradient rows [dE | g_logit | 0 0 0] into the padded send buffer
             self.grad_send.zero_()
             self.g_bias.zero_()

@@ -91,6 +91,10 @@ class DeepFMTrainStep:
         self.tp, self.lp, self.rows = coll.pointers(coll.weight, coll.linear)
         kmax = max([S * D] + [l.units for l in layers])
         _lib.ensure_gemm_workspace(B, kmax, kmax, dev)
+        # plane cache: x, every activation, every upstream gradient and every kernel, hi + lo
+        widths = [S * D] + [l.units for l in layers]
+        cache_bytes = 8 * (B * (widths[0] + 2 * sum(widths[1:])) + sum(a * b for a, b in zip(widths[:-1], widths[1:])))
+        _lib.set_workspace(max(cache_bytes * 5 // 4 + (1 << 20), _lib._workspace.numel() if _lib._workspace is not None else 0), dev)
         self.graph = None
         self.use_graph = use_graph
         self._copy_stream = torch.cuda.Stream(device=dev)
@@ -105,6 +109,7 @@ class DeepFMTrainStep:
         B, S, D = self.B, self.S, self.D
         c = self.coll
         mark = mark or (lambda label: None)
+        check(lib.dr_gemm_plane_cache(1), "dr_gemm_plane_cache")   # one split per tensor per step
         mark("start")
         check(lib.dr_embed_fm_fwd(self.tp.data_ptr(), self.lp.data_ptr(), self.rows.data_ptr(), self.ids.data_ptr(),
                                   self.ids.element_size(), c.bias.data_ptr(), B, S, D, c.row_stride, c.lin_stride,
@@ -138,6 +143,7 @@ class DeepFMTrainStep:
               "dr_embed_fm_bwd")
         mark("embed_fm_bwd")
         check(lib.dr_sgd_step(self.flat.data_ptr(), self.gflat.data_ptr(), self.flat.numel(), self.lr, st), "dr_sgd_step")
+        check(lib.dr_gemm_plane_cache(0), "dr_gemm_plane_cache")
         mark("sgd")
 
     def profile_kernels(self, ids_pool, labels_pool, iters: int = 10):

@@ -239,6 +239,13 @@ int dr_bce_logits_fwd_bwd(const float* z, const float* z_add, const float* y, in
  * streams.  Without a (large enough) workspace the FFMA variant is used.                  */
 int dr_set_workspace(void* ptr, uint64_t bytes);
 
+/* Operand-plane cache of the tensor-core GEMMs.  enable=1: forget all cached planes and start
+ * caching -- until the next call every distinct operand buffer is split into TF32 hi/lo planes once
+ * and the planes are reused by later GEMMs that read the same buffer (valid only while the buffer
+ * contents do not change: bracket ONE forward+backward pass, e.g. at the top of a train step).
+ * enable=0: stop caching (every GEMM call splits its own operands; always safe).              */
+int dr_gemm_plane_cache(int enable);
+
 /* Developer hook (not reference-facing): set a kernel tuning knob by name, e.g.
  * "embed_fwd_unroll", "embed_block", "embed_bwd_agg", "gemm_splitk".                     */
 int dr_tune_set(const char* key, int value);
