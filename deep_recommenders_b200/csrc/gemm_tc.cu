@@ -452,8 +452,21 @@ bool gemm_tc_eligible(const GemmArgs& a, bool ta, bool tb) {
   if ((tb || g_tune_tc_mn) && ((a.ldb & 3) || !aligned16(a.B))) return false;
   size_t ae, be;
   plane_elems(a, ta, tb, &ae, &be);
-  const size_t need = (ae + be) * 2 * sizeof(float) + 4096;
-  if (!g_ws_ptr || g_ws_bytes < need + (g_cache_on ? g_bump * sizeof(float) : 0)) return false;
+  if (!g_ws_ptr) return false;
+  if (g_cache_on && g_tune_tc_mn) {      // operands whose planes are already cached need no new space
+    auto cached = [](const float* src, size_t elems) {
+      for (int i = 0; i < g_nplanes; ++i)
+        if (g_planes[i].src == src && g_planes[i].elems == elems) return true;
+      return false;
+    };
+    size_t need = 0;
+    if (!cached(a.A, ae)) need += 2 * ae;
+    if (!cached(a.B, be)) need += 2 * be;
+    if ((g_bump + need) * sizeof(float) > g_ws_bytes) return false;
+  } else {
+    const size_t need = (ae + be) * 2 * sizeof(float) + 4096;
+    if (g_ws_bytes < need) return false;
+  }
   if (a.M >= ((int64_t)1 << 31) || a.K >= ((int64_t)1 << 31) || a.N >= ((int64_t)1 << 31)) return false;
   return true;
 }

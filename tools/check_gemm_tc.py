@@ -51,9 +51,12 @@ def run(M, K, N, variant, act=1, iters=0):
 
 def main():
     _lib.enable_tensor_core_gemm(3 << 30)
+    _lib.tune("tc_mn", int(os.environ.get("DR_TC_MN", "1")))
     out = []
     shapes = [(256, 64, 128), (300, 96, 200), (1000, 416, 256), (4096, 256, 416), (65536, 416, 256), (65536, 256, 256),
               (131072, 832, 832)]
+    if os.environ.get("DR_SHAPES") == "big":
+        shapes = [(65536, 416, 256), (131072, 832, 832)]
     bns = [int(x) for x in os.environ.get("DR_BN", "0").split(",")]
     for (M, K, N), bn in [(sh, bn) for sh in shapes for bn in bns]:
         _lib.tune("gemm_bn", bn)
