@@ -395,22 +395,53 @@ class ShardedDeepFMTrainStep:
         self.run()
         return float(self.loss.item())
 
+    def time_embed_fwd(self, ids_pool, iters: int = 30) -> float:
+        """Mean duration (ms) of this rank's fused gather+FM forward alone (p2p: (G-1)/G of the rows are
+        read from peers over NVLink inside the same kernel).  nccl exchange: times the local
+        identity-table kernel only."""
+        lib, st = self.lib, torch.cuda.current_stream().cuda_stream
+        B, S, D, G, V = self.B, self.S, self.D, self.world, self.emb.vdim
+
+        def launch(k):
+            if self.exchange == "p2p":
+                ids = ids_pool[k % len(ids_pool)]
+                check(lib.dr_embed_fm_fwd_sharded(self.emb.peer_ptrs.data_ptr(), G, self.emb.slot_offsets.data_ptr(),
+                                                  self.emb.rows.data_ptr(), ids.data_ptr(), 8, self.bias.data_ptr(),
+                                                  B, S, D, V, 1, self.stack.data_ptr(), self.sum_e.data_ptr(),
+                                                  self.fm_logit.data_ptr(), st), "dr_embed_fm_fwd_sharded")
+            else:
+                check(lib.dr_embed_fm_fwd(self.tp.data_ptr(), self.lp.data_ptr(), self.trows.data_ptr(),
+                                          self.inv.data_ptr(), 4, self.bias.data_ptr(), B, S, D, V, V, 1,
+                                          self.stack.data_ptr(), self.sum_e.data_ptr(), self.fm_logit.data_ptr(), st),
+                      "dr_embed_fm_fwd")
+
+        for k in range(5):
+            launch(k)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(iters):
+            launch(k)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
     def profile_kernels(self, ids_pool, labels_pool, iters: int = 10):
-        sums, count = {}, 0
-        for it in range(iters + 2):
+        runs = []
+        for it in range(iters + 2):      # back-to-back, no host sync in between (steady-state clocks / caches)
             self.ids.copy_(ids_pool[it % len(ids_pool)], non_blocking=True)
             self.labels.copy_(labels_pool[it % len(labels_pool)].reshape(-1), non_blocking=True)
             evs = []
 
-            def mark(label):
+            def mark(label, evs=evs):
                 e = torch.cuda.Event(enable_timing=True)
                 e.record()
                 evs.append((label, e))
 
             self._enqueue(mark)
-            torch.cuda.synchronize()
-            if it < 2:
-                continue
+            runs.append(evs)
+        torch.cuda.synchronize()
+        sums, count = {}, 0
+        for evs in runs[2:]:
             count += 1
             for (l0, e0), (l1, e1) in zip(evs[:-1], evs[1:]):
                 sums[l1] = sums.get(l1, 0.0) + e0.elapsed_time(e1)

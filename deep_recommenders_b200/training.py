@@ -146,25 +146,49 @@ class DeepFMTrainStep:
         check(lib.dr_gemm_plane_cache(0), "dr_gemm_plane_cache")
         mark("sgd")
 
+    def time_embed_fwd(self, ids_pool, iters: int = 30) -> float:
+        """Mean duration (ms) of the fused gather+FM forward alone: `iters` back-to-back launches on the
+        launching stream between two CUDA events, cycling through the id pool (tables >> L2)."""
+        lib, st, c = self.lib, torch.cuda.current_stream().cuda_stream, self.coll
+        B, S, D = self.B, self.S, self.D
+
+        def launch(k):
+            ids = ids_pool[k % len(ids_pool)]
+            check(lib.dr_embed_fm_fwd(self.tp.data_ptr(), self.lp.data_ptr(), self.rows.data_ptr(), ids.data_ptr(),
+                                      ids.element_size(), c.bias.data_ptr(), B, S, D, c.row_stride, c.lin_stride,
+                                      c.flags, self.stack.data_ptr(), self.sum_e.data_ptr(),
+                                      self.fm_logit.data_ptr(), st), "dr_embed_fm_fwd")
+
+        for k in range(5):
+            launch(k)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(iters):
+            launch(k)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
     def profile_kernels(self, ids_pool, labels_pool, iters: int = 10):
         """Eager (non-graph) passes with a CUDA event on the launching stream between kernel groups.
         Returns ({"embed_fm_fwd_ms": ...}, {label: mean ms}) -- the live per-kernel timing bench.py
         reports in `roofline` and `kernel_ms`."""
-        sums, count = {}, 0
-        for it in range(iters + 2):
+        runs = []
+        for it in range(iters + 2):      # back-to-back, no host sync in between (steady-state clocks / caches)
             self.ids.copy_(ids_pool[it % len(ids_pool)], non_blocking=True)
             self.labels.copy_(labels_pool[it % len(labels_pool)].reshape(-1), non_blocking=True)
             evs = []
 
-            def mark(label):
+            def mark(label, evs=evs):
                 e = torch.cuda.Event(enable_timing=True)
                 e.record()
                 evs.append((label, e))
 
             self._enqueue(mark)
-            torch.cuda.synchronize()
-            if it < 2:
-                continue
+            runs.append(evs)
+        torch.cuda.synchronize()
+        sums, count = {}, 0
+        for evs in runs[2:]:
             count += 1
             for (l0, e0), (l1, e1) in zip(evs[:-1], evs[1:]):
                 sums[l1] = sums.get(l1, 0.0) + e0.elapsed_time(e1)
