@@ -83,7 +83,7 @@ __host__ __device__ inline size_t embed_smem_bytes(int S, int warps, int G, int 
   return hdr + ((ids + 15) & ~(size_t)15);
 }
 
-template <int LPR, typename IdT, int U>
+template <int LPR, typename IdT, int U, bool SHARD>
 __global__ void __launch_bounds__(512) embed_fm_fwd_kernel(const EmbedFwdParams p) {
   constexpr int G = 32 / LPR;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(512) embed_fm_fwd_kernel(const EmbedFwdParams 
   const int warp_in_cta = threadIdx.x >> 5;
   const int warps_per_cta = blockDim.x >> 5;
   IdT* s_ids = reinterpret_cast<IdT*>(s_peer + kMaxShardWorld) + (size_t)warp_in_cta * G * S;
-  const int SW = p.shard_world;
+  const int SW = SHARD ? p.shard_world : 0;
   const bool sw_pow2 = (SW & (SW - 1)) == 0;
   const int sw_shift = 31 - __clz(SW > 0 ? SW : 1);
 
@@ -104,9 +104,10 @@ __global__ void __launch_bounds__(512) embed_fm_fwd_kernel(const EmbedFwdParams 
     s_tab[i] = p.table_ptrs ? p.table_ptrs[i] : p.single_table;
     s_lin[i] = p.lin_ptrs ? p.lin_ptrs[i] : nullptr;
     s_rows[i] = p.rows ? p.rows[i] : p.single_rows;
-    s_off[i] = p.slot_offsets ? p.slot_offsets[i] : 0;
+    if (SHARD) s_off[i] = p.slot_offsets ? p.slot_offsets[i] : 0;
   }
-  for (int i = threadIdx.x; i < SW; i += blockDim.x) s_peer[i] = p.peer_bases[i];
+  if (SHARD)
+    for (int i = threadIdx.x; i < SW; i += blockDim.x) s_peer[i] = p.peer_bases[i];
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(512) embed_fm_fwd_kernel(const EmbedFwdParams 
           const int64_t id = (int64_t)my[s];
           if ((uint64_t)id < (uint64_t)s_rows[s]) {
             const float* rowp;
-            if (SW == 0) {
+            if (!SHARD) {
               rowp = s_tab[s] + (size_t)id * p.row_stride;
             } else {   // row-sharded: the owner's arena is read directly over NVLink
               const int64_t r = s_off[s] + id;
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(512) embed_fm_bwd_kernel(const EmbedBwdParams 
 //     are resolved by the L2 atomic unit),
 //   * no shared-memory staging and no cross-lane reduction: sum_e arrives precomputed.
 // U slot-steps are loaded before any atomic is issued (the red.global asm is a compiler barrier).
-template <int LPR, typename IdT, int U>
+template <int LPR, typename IdT, int U, bool SHARD>
 __global__ void __launch_bounds__(256) embed_fm_bwd_sp_kernel(const EmbedBwdParams p) {
   constexpr int SPW = 32 / LPR;      // slots per warp-instruction
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -349,16 +350,17 @@ __global__ void __launch_bounds__(256) embed_fm_bwd_sp_kernel(const EmbedBwdPara
   int64_t* s_rows = reinterpret_cast<int64_t*>(s_lin + S);
   int64_t* s_off = s_rows + S;
   float** s_peer = reinterpret_cast<float**>(s_off + S);
-  const int SW = p.shard_world;
+  const int SW = SHARD ? p.shard_world : 0;
   const bool sw_pow2 = (SW & (SW - 1)) == 0;
   const int sw_shift = 31 - __clz(SW > 0 ? SW : 1);
   for (int i = threadIdx.x; i < S; i += blockDim.x) {
     s_tab[i] = p.grad_table_ptrs ? p.grad_table_ptrs[i] : p.single_grad;
     s_lin[i] = p.grad_lin_ptrs ? p.grad_lin_ptrs[i] : nullptr;
     s_rows[i] = p.rows ? p.rows[i] : p.single_rows;
-    s_off[i] = p.slot_offsets ? p.slot_offsets[i] : 0;
+    if (SHARD) s_off[i] = p.slot_offsets ? p.slot_offsets[i] : 0;
   }
-  for (int i = threadIdx.x; i < SW; i += blockDim.x) s_peer[i] = p.peer_bases[i];
+  if (SHARD)
+    for (int i = threadIdx.x; i < SW; i += blockDim.x) s_peer[i] = p.peer_bases[i];
   __syncthreads();
 
   const int lane = threadIdx.x & 31, warp_in_cta = threadIdx.x >> 5, warps_per_cta = blockDim.x >> 5;
@@ -408,7 +410,7 @@ __global__ void __launch_bounds__(256) embed_fm_bwd_sp_kernel(const EmbedBwdPara
         const int s = s0 + u * SPW + sg;
         if (s < S && (uint64_t)id[u] < (uint64_t)s_rows[s]) {
           float* row;
-          if (SW == 0) {
+          if (!SHARD) {
             row = s_tab[s] + (size_t)id[u] * p.row_stride;
           } else {     // row-sharded: vector atomics straight into the owner's arena over NVLink
             const int64_t r = s_off[s] + id[u];
@@ -512,9 +514,15 @@ static LaunchGeom geom(int64_t B, int S, int LPR, int id_bytes) {
 template <int LPR, typename IdT, int U>
 static int launch_fwd_u(const EmbedFwdParams& p, cudaStream_t st) {
   LaunchGeom lg = geom(p.B, p.S, LPR, sizeof(IdT));
-  auto k = embed_fm_fwd_kernel<LPR, IdT, U>;
-  if (lg.smem > 48 * 1024) DR_CUDA_CALL(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lg.smem));
-  k<<<lg.ctas, lg.threads, lg.smem, st>>>(p);
+  if (p.shard_world > 0) {
+    auto k = embed_fm_fwd_kernel<LPR, IdT, U, true>;
+    if (lg.smem > 48 * 1024) DR_CUDA_CALL(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lg.smem));
+    k<<<lg.ctas, lg.threads, lg.smem, st>>>(p);
+  } else {
+    auto k = embed_fm_fwd_kernel<LPR, IdT, U, false>;
+    if (lg.smem > 48 * 1024) DR_CUDA_CALL(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lg.smem));
+    k<<<lg.ctas, lg.threads, lg.smem, st>>>(p);
+  }
   DR_CUDA_LAUNCH_CHECK("embed_fm_fwd");
   return DR_OK;
 }
@@ -557,7 +565,8 @@ static int launch_bwd_sp_u(const EmbedBwdParams& p, cudaStream_t st) {
   int per_sm = g_tune_embed_ctas_per_sm > 0 ? g_tune_embed_ctas_per_sm : 8;
   if (ctas > (int64_t)kNumSMs * per_sm) ctas = (int64_t)kNumSMs * per_sm;
   if (ctas < 1) ctas = 1;
-  embed_fm_bwd_sp_kernel<LPR, IdT, U><<<(unsigned)ctas, threads, smem, st>>>(p);
+  if (p.shard_world > 0) embed_fm_bwd_sp_kernel<LPR, IdT, U, true><<<(unsigned)ctas, threads, smem, st>>>(p);
+  else embed_fm_bwd_sp_kernel<LPR, IdT, U, false><<<(unsigned)ctas, threads, smem, st>>>(p);
   DR_CUDA_LAUNCH_CHECK("embed_fm_bwd_sp");
   return DR_OK;
 }
