@@ -446,7 +446,7 @@ static void plane_elems(const GemmArgs& a, bool ta, bool tb, size_t* ae, size_t*
 
 bool gemm_tc_eligible(const GemmArgs& a, bool ta, bool tb) {
   if (g_tune_gemm_variant != 1) return false;
-  if (a.N < 96 || a.M < 64 || a.K < 32) return false;
+  if (a.N < 32 || (a.N & 3) || a.M < 64 || a.K < 32) return false;
   // operands already K-major are split in place with float4 accesses
   if ((!ta || g_tune_tc_mn) && ((a.lda & 3) || !aligned16(a.A))) return false;
   if ((tb || g_tune_tc_mn) && ((a.ldb & 3) || !aligned16(a.B))) return false;
@@ -557,17 +557,26 @@ int gemm_tc_launch(const GemmArgs& a0, bool ta, bool tb, cudaStream_t st) {
       if (int rc = make_map(&tms[0], Ah, a.M, a.K, pa, TC_BK, true)) return rc;
       if (int rc = make_map(&tms[1], Al, a.M, a.K, pa, TC_BK, true)) return rc;
     }
+    // skinny outputs (the 256->32 tower layer and its weight gradient) get a 128 x 32 tile and a deeper ring
+    const int bn = a.N <= 32 ? 32 : (a.N <= 64 ? 64 : 128);
     if (!B_MN) {
-      if (int rc = make_map(&tms[2], Bh, a.K, a.N, pb, 128)) return rc;
-      if (int rc = make_map(&tms[3], Bl, a.K, a.N, pb, 128)) return rc;
+      if (int rc = make_map(&tms[2], Bh, a.K, a.N, pb, bn)) return rc;
+      if (int rc = make_map(&tms[3], Bl, a.K, a.N, pb, bn)) return rc;
     } else {
       if (int rc = make_map(&tms[2], Bh, a.N, a.K, pb, TC_BK, true)) return rc;
       if (int rc = make_map(&tms[3], Bl, a.N, a.K, pb, TC_BK, true)) return rc;
     }
-    if (!A_MN && !B_MN) return launch_tc<128, 3, false, false>(tms, a, st);
-    if (!A_MN && B_MN) return launch_tc<128, 3, false, true>(tms, a, st);
-    if (A_MN && !B_MN) return launch_tc<128, 3, true, false>(tms, a, st);
-    return launch_tc<128, 3, true, true>(tms, a, st);
+#define DR_TC_LAUNCH(BN_, ST_)                                                              \
+    do {                                                                                    \
+      if (!A_MN && !B_MN) return launch_tc<BN_, ST_, false, false>(tms, a, st);             \
+      if (!A_MN && B_MN) return launch_tc<BN_, ST_, false, true>(tms, a, st);               \
+      if (A_MN && !B_MN) return launch_tc<BN_, ST_, true, false>(tms, a, st);               \
+      return launch_tc<BN_, ST_, true, true>(tms, a, st);                                   \
+    } while (0)
+    if (bn == 32) DR_TC_LAUNCH(32, 5);
+    if (bn == 64) DR_TC_LAUNCH(64, 4);
+    DR_TC_LAUNCH(128, 3);
+#undef DR_TC_LAUNCH
   }
   // A(m,k): !ta -> stored [M,K] (already K-major);  ta -> stored [K,M] -> transpose
   if (int rc = make_planes(a.A, !ta, a.M, a.K, a.lda, Ah, Al, &pa, st)) return rc;
