@@ -26,6 +26,7 @@ namespace dr {
 
 // ---- workspace registered by the host (dr_set_workspace) ----------------------------------------
 int g_tune_gemm_bn = 0;   // 0 = auto, 128 or 256: tensor-core tile width
+int g_tune_tc_min_n = 96;
 int g_tune_tc_mn = 1;     // 1 = feed MN-major operands as stored (SWIZZLE_128B_BASE32B); 0 = transpose them in the split pre-pass
 static void* g_ws_ptr = nullptr;
 static size_t g_ws_bytes = 0;
@@ -446,7 +447,9 @@ static void plane_elems(const GemmArgs& a, bool ta, bool tb, size_t* ae, size_t*
 
 bool gemm_tc_eligible(const GemmArgs& a, bool ta, bool tb) {
   if (g_tune_gemm_variant != 1) return false;
-  if (a.N < 32 || (a.N & 3) || a.M < 64 || a.K < 32) return false;
+  // measured (profiles/README.md): for N = 32 the extra hi/lo split of the activations costs more than the
+  // 128 x 32 tensor-core tile saves over the FFMA kernel, so skinny layers stay on FFMA unless tc_min_n is lowered
+  if (a.N < g_tune_tc_min_n || (a.N & 3) || a.M < 64 || a.K < 32) return false;
   // operands already K-major are split in place with float4 accesses
   if ((!ta || g_tune_tc_mn) && ((a.lda & 3) || !aligned16(a.A))) return false;
   if ((tb || g_tune_tc_mn) && ((a.ldb & 3) || !aligned16(a.B))) return false;
