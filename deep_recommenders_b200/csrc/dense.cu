@@ -128,14 +128,14 @@ extern "C" int dr_dense_fwd(const float* x, const float* w, const float* b, int6
 extern "C" int dr_dense_bwd(const float* x, const float* w, const float* y, const float* gy, int64_t M,
                             int K, int N, int act, float* gz_ws, float* gx, float* gw, float* gb,
                             void* stream) {
-  DR_REQUIRE(x && w && gy && gw, DR_EINVAL, "dr_dense_bwd: null pointer");
+  DR_REQUIRE(x && w && gy && (gw || gx), DR_EINVAL, "dr_dense_bwd: null pointer");
   DR_REQUIRE(M >= 0 && K >= 1 && N >= 1, DR_EINVAL, "dr_dense_bwd: bad shape");
   DR_REQUIRE(act >= DR_ACT_NONE && act <= DR_ACT_TANH, DR_EINVAL, "dr_dense_bwd: unknown activation %d", act);
   DR_REQUIRE(act == DR_ACT_NONE || (y && gz_ws), DR_EINVAL, "dr_dense_bwd: activation needs y and gz_ws");
   cudaStream_t st = (cudaStream_t)stream;
   if (gb) DR_CUDA_CALL(cudaMemsetAsync(gb, 0, sizeof(float) * N, st));
   if (M == 0) {
-    DR_CUDA_CALL(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)K * N, st));
+    if (gw) DR_CUDA_CALL(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)K * N, st));
     return DR_OK;
   }
   const float* gz = gy;
@@ -150,6 +150,7 @@ extern "C" int dr_dense_bwd(const float* x, const float* w, const float* y, cons
     GemmArgs a = mk(gz, w, gx, M, K, N, N, N, K, EPI_STORE);   // gx[M,K] = gz[M,N] @ W^T
     if (int rc = gemm_launch(a, false, true, st)) return rc;
   }
+  if (!gw) return DR_OK;      // caller computes the weight gradient in a second call (e.g. on another stream)
   return gemm_xt_g(x, gz, gw, M, K, N, st);
 }
 

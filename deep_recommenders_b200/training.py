@@ -98,6 +98,7 @@ class DeepFMTrainStep:
         self.graph = None
         self.use_graph = use_graph
         self._copy_stream = torch.cuda.Stream(device=dev)
+        self._side_stream = torch.cuda.Stream(device=dev)
         self._staged = None
         self.launches_per_step = None
 
@@ -127,21 +128,34 @@ class DeepFMTrainStep:
         check(lib.dr_bce_logits_fwd_bwd(self.acts[-1].data_ptr(), self.fm_logit.data_ptr(), self.labels.data_ptr(), B,
                                         self.prob.data_ptr(), self.loss.data_ptr(), gz.data_ptr(), st), "dr_bce")
         mark("bce")
-        for i in range(len(self.layers) - 1, -1, -1):
+        for i in range(len(self.layers) - 1, 0, -1):
             l = self.layers[i]
-            xin = self.stack if i == 0 else self.acts[i - 1]
-            Kin = S * D if i == 0 else self.layers[i - 1].units
-            gx = self.g_stack if i == 0 else self.g_acts[i - 1]
+            xin, Kin, gx = self.acts[i - 1], self.layers[i - 1].units, self.g_acts[i - 1]
             check(lib.dr_dense_bwd(xin.data_ptr(), self.w[i].data_ptr(), self.acts[i].data_ptr(),
                                    self.g_acts[i].data_ptr(), B, Kin, l.units, l._act, ops._ptr(self.gz_ws[i]),
                                    gx.data_ptr(), self.gw[i].data_ptr(), ops._ptr(self.gb[i]), st), "dr_dense_bwd")
             mark(f"dense_bwd_{i}")
-        check(lib.dr_embed_fm_bwd(self.ids.data_ptr(), self.ids.element_size(), self.rows.data_ptr(),
-                                  self.stack.data_ptr(), self.sum_e.data_ptr(), gz.data_ptr(), self.g_stack.data_ptr(),
-                                  B, S, D, c.row_stride, c.lin_stride, c.flags, self.tp.data_ptr(), self.lp.data_ptr(),
-                                  c.bias.data_ptr(), -self.lr, st),
-              "dr_embed_fm_bwd")
-        mark("embed_fm_bwd")
+        # layer 0: input gradient first, then its weight gradient (tensor cores, reads cached planes) runs
+        # CONCURRENTLY with the HBM-bound embedding update on a side stream
+        l = self.layers[0]
+        gz0 = self.gz_ws[0] if l._act != 0 else self.g_acts[0]
+        check(lib.dr_dense_bwd(self.stack.data_ptr(), self.w[0].data_ptr(), self.acts[0].data_ptr(),
+                               self.g_acts[0].data_ptr(), B, S * D, l.units, l._act, ops._ptr(self.gz_ws[0]),
+                               self.g_stack.data_ptr(), None, ops._ptr(self.gb[0]), st), "dr_dense_bwd(dx)")
+        mark("dense_bwd_0_dx")
+        main = torch.cuda.current_stream()
+        side = self._side_stream
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            check(lib.dr_embed_fm_bwd(self.ids.data_ptr(), self.ids.element_size(), self.rows.data_ptr(),
+                                      self.stack.data_ptr(), self.sum_e.data_ptr(), gz.data_ptr(),
+                                      self.g_stack.data_ptr(), B, S, D, c.row_stride, c.lin_stride, c.flags,
+                                      self.tp.data_ptr(), self.lp.data_ptr(), c.bias.data_ptr(), -self.lr,
+                                      side.cuda_stream), "dr_embed_fm_bwd")
+        check(lib.dr_dense_bwd(self.stack.data_ptr(), self.w[0].data_ptr(), None, gz0.data_ptr(), B, S * D, l.units, 0,
+                               None, None, self.gw[0].data_ptr(), None, st), "dr_dense_bwd(dw)")
+        main.wait_stream(side)
+        mark("dense_bwd_0_dw+embed_fm_bwd")
         check(lib.dr_sgd_step(self.flat.data_ptr(), self.gflat.data_ptr(), self.flat.numel(), self.lr, st), "dr_sgd_step")
         check(lib.dr_gemm_plane_cache(0), "dr_gemm_plane_cache")
         mark("sgd")

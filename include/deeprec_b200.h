@@ -115,7 +115,9 @@ int dr_fm_bwd(const float* x, const float* g, int64_t B, int S, int D, float* gx
  *   fp32 accumulate, fp32-accurate products (no single-pass TF32/BF16).
  * backward: gz = gy * act'(y) ; gx = gz @ W^T (NULL = skip) ; gw = x^T @ gz ; gb = colsum(gz).
  *   gz_ws: [M,N] workspace (may alias gy if the caller no longer needs gy).  gw and gb
- *   are OVERWRITTEN (not accumulated).
+ *   are OVERWRITTEN (not accumulated).  gw == NULL skips the weight gradient; a second call with
+ *   gy = gz_ws, act = DR_ACT_NONE, gx = NULL, gb = NULL then computes only gw (lets the caller run
+ *   it concurrently with whatever consumes gx).
  * ------------------------------------------------------------------------------------- */
 int dr_dense_fwd(const float* x, const float* w, const float* b, int64_t M, int K, int N,
                  int act, float* y, void* stream);
