@@ -99,12 +99,14 @@ class ShardedDeepFMTrainStep:
             l.build((B, in_dim), device=dev)
             in_dim = l.units
         self.layers = layers
-        total = 1 + sum(l.kernel.numel() + l.bias.numel() for l in layers)
+        # every parameter starts on a 16-byte boundary (the tensor-core path splits operands with float4)
+        r4 = lambda n: (n + 3) // 4 * 4
+        total = 4 + sum(r4(l.kernel.numel()) + r4(l.bias.numel()) for l in layers)
         self.flat = torch.zeros(total, **f)
         self.gflat = torch.zeros(total, **f)
         self.bias, self.g_bias = self.flat[0:1], self.gflat[0:1]
         self.w, self.b, self.gw, self.gb = [], [], [], []
-        o = 1
+        o = 4
         with torch.no_grad():
             for l in layers:
                 for src, dst_p, dst_g in ((l.kernel, self.w, self.gw), (l.bias, self.b, self.gb)):
@@ -113,7 +115,7 @@ class ShardedDeepFMTrainStep:
                     src.data = self.flat[o:o + nel].view_as(src)
                     dst_p.append(src.data)
                     dst_g.append(self.gflat[o:o + nel].view_as(src))
-                    o += nel
+                    o += r4(nel)
         # static buffers
         # warm-up ids spread over the tables (all-zero ids would all hit one owner)
         self.ids = torch.stack([torch.randint(0, max(1, r), (B,), device=dev) for r in rows], dim=1).contiguous()

@@ -46,9 +46,10 @@ class DeepFMTrainStep:
                 l.build((self.B, in_dim), device=dev)
             in_dim = l.units
         self.layers = layers
+        r4 = lambda n: (n + 3) // 4 * 4      # every parameter starts on a 16-byte boundary
         sizes = []
         for l in layers:
-            sizes += [l.kernel.numel(), l.bias.numel() if l.bias is not None else 0]
+            sizes += [r4(l.kernel.numel()), r4(l.bias.numel()) if l.bias is not None else 0]
         total = sum(sizes)
         self.flat = torch.empty(total, device=dev, dtype=torch.float32)
         self.gflat = torch.zeros(total, device=dev, dtype=torch.float32)
@@ -64,14 +65,14 @@ class DeepFMTrainStep:
                 l.kernel.data = self.flat[o:o + n].view_as(l.kernel)     # parameters alias the flat buffer
                 self.w.append(l.kernel.data)
                 self.gw.append(self.gflat[o:o + n].view_as(l.kernel))
-                o += n
+                o += r4(n)
                 if l.bias is not None:
                     n = l.bias.numel()
                     self.flat[o:o + n].copy_(l.bias)
                     l.bias.data = self.flat[o:o + n]
                     self.b.append(l.bias.data)
                     self.gb.append(self.gflat[o:o + n])
-                    o += n
+                    o += r4(n)
                 else:
                     self.b.append(None)
                     self.gb.append(None)
