@@ -80,3 +80,20 @@ def test_hashing_known_answers():
     # tf.strings.to_hash_bucket_fast(["Hello", "TensorFlow", "2.x"], 3) -> [0, 2, 2] (TF API docs)
     assert hash_bucket(["Hello", "TensorFlow", "2.x"], 3).tolist() == [0, 2, 2]
     assert hash_bucket([1, "1", b"1"], 100).tolist()[0] == hash_bucket(["1"], 100)[0]
+
+
+def test_bench_reference_arm_json_contract():
+    """`bench.py --impl reference` runs without a GPU and prints the contract's JSON line."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "examples/s" and line["value"] > 0
+    assert line["metric"].startswith("examples/sec (fwd+bwd) DeepFM")
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["higher_is_better"] is True

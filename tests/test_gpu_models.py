@@ -129,3 +129,49 @@ def test_dcn_and_two_tower_train_step():
         opt.step()
         l0 = l0 if l0 is not None else float(loss)
     assert float(loss) < l0
+
+
+def test_c1_movielens_shaped_fm_matches_oracle():
+    """BASELINE config C1 (examples/train_fm_on_movielens_estimator.py:10-35 columns, D=16, B=1024):
+    hash-bucket ids via FarmHash Fingerprint64, vocabulary ids with OOV -> -1, the always-OOV genre slot."""
+    import importlib.util
+    import pathlib
+    from deep_recommenders_b200.hashing import hash_bucket
+    spec = importlib.util.spec_from_file_location(
+        "c1_example", pathlib.Path(__file__).resolve().parent.parent / "examples" / "train_fm_on_movielens_synthetic.py")
+    ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ex)
+    from deep_recommenders.estimator.models.feature_interaction import FM
+    ind, emb = ex.build_columns()
+    model = FM(ind, emb, seed=1, device="cuda")
+    coll = model.collection
+    with torch.no_grad():
+        coll.lin_view().normal_(0, 0.1)
+        coll.bias.fill_(-0.2)
+    rng = np.random.default_rng(0)
+    feats, labels = ex.synthetic_batch(rng, 1024)
+    logits = model(feats)
+    assert logits.shape == (1024, 1) and len(model.embeddings) == 6
+    ids = np.stack([
+        hash_bucket(feats["user_id"].tolist(), ex.NUM_USERS),
+        np.asarray([ex.GENDER_VOCAB.index(v) for v in feats["user_gender"]]),
+        np.asarray([ex.AGE_VOCAB.index(int(v)) for v in feats["user_age"]]),
+        np.asarray([ex.OCCUPATION_VOCAB.index(int(v)) for v in feats["user_occupation"]]),
+        hash_bucket(feats["movie_id"].tolist(), ex.NUM_MOVIES),
+        np.full(1024, -1),                                   # genres are never in the gender vocabulary
+    ], axis=1).astype(np.int64)
+    tables, lins, bias = collection_arrays(coll)
+    ref, stack = R.fm_logit(tables, lins, bias, ids, np.float64)
+    assert float(np.abs(stack[:, 5]).max()) == 0.0
+    assert np.allclose(logits.detach().cpu().numpy(), ref, rtol=1e-5, atol=2e-5)
+    assert torch.equal(model.embeddings[5], torch.zeros_like(model.embeddings[5]))
+    opt = torch.optim.Adam(model.parameters(), lr=0.01)
+    y = torch.from_numpy(labels).cuda()
+    first = None
+    for _ in range(15):
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(model(feats), y)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        first = first if first is not None else float(loss)
+    assert float(loss) < first
