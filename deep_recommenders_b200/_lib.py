@@ -52,8 +52,19 @@ _SIGS = {
     "dr_unpermute_rows": [_p, _p, _i64, _i, _p, _p],
     "dr_sgd_step": [_p, _p, _i64, _f, _p],
     "dr_bce_logits_fwd_bwd": [_p, _p, _p, _i64, _p, _p, _p, _p],
+    # SURVEY 8(f) "next" rows
+    "dr_adam_step": [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _i, _p],
+    "dr_hash_bucket_i64": [_p, _i64, _i64, _p, _p],
+    "dr_hash_bucket_bytes": [_p, _p, _i64, _i64, _p, _p],
+    "dr_hash_bucket_i64_host": [_p, _i64, _i64, _p],
+    "dr_hash_bucket_bytes_host": [_p, _p, _i64, _i64, _p],
+    "dr_fingerprint64_host": [_p, _i64],
+    "dr_vocab_lookup_i64": [_p, _i64, _p, _p, _i64, _i64, _p, _p],
+    "dr_embed_bag_fwd": [_p, _i64, _i64, _p, _i, _p, _i64, _i, _i, _p, _i64, _p],
+    "dr_embed_bag_bwd": [_p, _i, _p, _i64, _i, _i, _p, _i64, _i64, _i64, _p, _f, _p],
+    "dr_topk_rows": [_p, _i64, _i64, _i64, _i, _p, _p, _p],
 }
-_RESTYPES = {"dr_last_error": C.c_char_p, "dr_launch_count": C.c_uint64}
+_RESTYPES = {"dr_last_error": C.c_char_p, "dr_launch_count": C.c_uint64, "dr_fingerprint64_host": C.c_uint64}
 
 
 class DeepRecError(RuntimeError):

@@ -11,7 +11,7 @@ import torch
 
 from .... import ops
 from ....embedding import EmbeddingCollection
-from ....hashing import column_ids
+from ....hashing import ids_and_bags
 
 
 def fm(x):
@@ -52,9 +52,8 @@ class FM(object):
         return self.call(*args, **kwargs)
 
     def call(self, features):
-        dev = self.collection.weight.device
-        ids = torch.stack([column_ids(self._cat[k], features.get(k), dev) for k in self._keys], dim=1)
-        stack, logit = self.collection(ids, want_logit=True)
+        ids, bags = ids_and_bags(self._keys, self._cat, features, self.collection.weight.device)
+        stack, logit = self.collection(ids, want_logit=True, bags=bags)
         self.embeddings = [stack[:, s, :] for s in range(stack.shape[1])]
         self._stack = stack
         return logit.unsqueeze(1)          # linear_outputs + factorized_outputs

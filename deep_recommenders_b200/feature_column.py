@@ -18,6 +18,19 @@ from dataclasses import dataclass, field
 from typing import Optional, Sequence, Tuple
 
 
+@dataclass
+class RaggedFeature:
+    """A multi-valued feature for one batch (what tf.io.VarLenFeature / a SparseTensor carries, e.g. "Genres",
+    datasets/movielens.py): flat raw `values` (list / numpy / torch) and `row_splits` [B+1]; example b owns
+    values[row_splits[b]:row_splits[b+1]].  Embedding columns mean-combine it, indicator columns count it."""
+    values: object
+    row_splits: object
+
+    @property
+    def batch_size(self) -> int:
+        return len(self.row_splits) - 1
+
+
 @dataclass(frozen=True)
 class CategoricalColumn:
     key: str

@@ -1,159 +1,29 @@
 """Host side of the id pipeline: raw feature value -> int64 id.
 
-`categorical_column_with_hash_bucket` in TensorFlow is
-``string_to_hash_bucket_fast(str(value), N)`` = FarmHash ``Fingerprint64`` (== farmhashna
-``Hash64``, google/farmhash, MIT licence) of the UTF-8 bytes, modulo N.  FarmHash is a
-third-party dependency of TensorFlow that is not vendored in the reference; the published
-algorithm is restated here and checked against the known answers in tests/test_hashing.py.
-This runs on the CPU because the inputs are Python strings; integer ids that are already in
-[0, N) go straight to the GPU through `categorical_column_with_identity`.
+`categorical_column_with_hash_bucket` in TensorFlow is ``string_to_hash_bucket_fast(str(value), N)`` =
+FarmHash ``Fingerprint64`` of the UTF-8 bytes, modulo N; `categorical_column_with_vocabulary_list` is the
+position in the list with out-of-vocabulary -> -1.  The arithmetic lives in the C-ABI library
+(deep_recommenders_b200/csrc/farmhash.cuh, idpipe.cu):
+
+  * features that are already CUDA integer tensors are hashed / looked up on the device
+    (`dr_hash_bucket_i64`, `dr_vocab_lookup_i64`) and never leave it;
+  * features that arrive as host strings (TFRecord parse, python lists) go through the host twins
+    (`dr_hash_bucket_bytes_host`: same source compiled for the CPU, as TensorFlow's own hash op is a CPU op),
+    packed as one byte buffer + offsets, then one H2D copy of the ids.
+
+There is no pure-Python path here; the independent Python restatement used to pin the hash lives in
+oracle/farmhash_py.py (test infrastructure).
 """
 from __future__ import annotations
 
-import struct
-from typing import Iterable
+import ctypes as C
+from typing import Iterable, Sequence
 
 import numpy as np
 import torch
 
-from .feature_column import CategoricalColumn
-
-_M = (1 << 64) - 1
-_K0 = 0xC3A5C85C97CB3127
-_K1 = 0xB492B66FBE98F273
-_K2 = 0x9AE16A3B2F90404F
-
-
-def _rot(v: int, s: int) -> int:
-    return v if s == 0 else ((v >> s) | (v << (64 - s))) & _M
-
-
-def _smix(v: int) -> int:
-    return v ^ (v >> 47)
-
-
-def _f64(b: bytes, i: int) -> int:
-    return struct.unpack_from("<Q", b, i)[0]
-
-
-def _f32(b: bytes, i: int) -> int:
-    return struct.unpack_from("<I", b, i)[0]
-
-
-def _hl16(u: int, v: int, mul: int) -> int:
-    a = ((u ^ v) * mul) & _M
-    a ^= a >> 47
-    b = ((v ^ a) * mul) & _M
-    b ^= b >> 47
-    return (b * mul) & _M
-
-
-def _h0to16(s: bytes) -> int:
-    n = len(s)
-    if n >= 8:
-        mul = (_K2 + n * 2) & _M
-        a = (_f64(s, 0) + _K2) & _M
-        b = _f64(s, n - 8)
-        c = (_rot(b, 37) * mul + a) & _M
-        d = ((_rot(a, 25) + b) * mul) & _M
-        return _hl16(c, d, mul)
-    if n >= 4:
-        mul = (_K2 + n * 2) & _M
-        a = _f32(s, 0)
-        return _hl16((n + (a << 3)) & _M, _f32(s, n - 4), mul)
-    if n > 0:
-        a, b, c = s[0], s[n >> 1], s[n - 1]
-        y = (a + (b << 8)) & 0xFFFFFFFF
-        z = (n + (c << 2)) & 0xFFFFFFFF
-        return (_smix(((y * _K2) & _M) ^ ((z * _K0) & _M)) * _K2) & _M
-    return _K2
-
-
-def _h17to32(s: bytes) -> int:
-    n = len(s)
-    mul = (_K2 + n * 2) & _M
-    a = (_f64(s, 0) * _K1) & _M
-    b = _f64(s, 8)
-    c = (_f64(s, n - 8) * mul) & _M
-    d = (_f64(s, n - 16) * _K2) & _M
-    return _hl16((_rot((a + b) & _M, 43) + _rot(c, 30) + d) & _M,
-                 (a + _rot((b + _K2) & _M, 18) + c) & _M, mul)
-
-
-def _h33to64(s: bytes) -> int:
-    n = len(s)
-    mul = (_K2 + n * 2) & _M
-    a = (_f64(s, 0) * _K2) & _M
-    b = _f64(s, 8)
-    c = (_f64(s, n - 8) * mul) & _M
-    d = (_f64(s, n - 16) * _K2) & _M
-    y = (_rot((a + b) & _M, 43) + _rot(c, 30) + d) & _M
-    z = _hl16(y, (a + _rot((b + _K2) & _M, 18) + c) & _M, mul)
-    e = (_f64(s, 16) * mul) & _M
-    f = _f64(s, 24)
-    g = ((y + _f64(s, n - 32)) * mul) & _M
-    h = ((z + _f64(s, n - 24)) * mul) & _M
-    return _hl16((_rot((e + f) & _M, 43) + _rot(g, 30) + h) & _M,
-                 (e + _rot((f + a) & _M, 18) + g) & _M, mul)
-
-
-def _weak32(s: bytes, i: int, a: int, b: int):
-    w, x, y, z = _f64(s, i), _f64(s, i + 8), _f64(s, i + 16), _f64(s, i + 24)
-    a = (a + w) & _M
-    b = _rot((b + a + z) & _M, 21)
-    c = a
-    a = (a + x) & _M
-    a = (a + y) & _M
-    b = (b + _rot(a, 44)) & _M
-    return (a + z) & _M, (b + c) & _M
-
-
-def fingerprint64(s: bytes) -> int:
-    """farmhash::Fingerprint64 (farmhashna::Hash64)."""
-    n = len(s)
-    if n <= 16:
-        return _h0to16(s)
-    if n <= 32:
-        return _h17to32(s)
-    if n <= 64:
-        return _h33to64(s)
-    seed = 81
-    x = seed
-    y = (seed * _K1 + 113) & _M
-    z = (_smix((y * _K2 + 113) & _M) * _K2) & _M
-    v = (0, 0)
-    w = (0, 0)
-    x = (x * _K2 + _f64(s, 0)) & _M
-    end = ((n - 1) // 64) * 64
-    last64 = end + ((n - 1) & 63) - 63
-    i = 0
-    while True:
-        x = (_rot((x + y + v[0] + _f64(s, i + 8)) & _M, 37) * _K1) & _M
-        y = (_rot((y + v[1] + _f64(s, i + 48)) & _M, 42) * _K1) & _M
-        x ^= w[1]
-        y = (y + v[0] + _f64(s, i + 40)) & _M
-        z = (_rot((z + w[0]) & _M, 33) * _K1) & _M
-        v = _weak32(s, i, (v[1] * _K1) & _M, (x + w[0]) & _M)
-        w = _weak32(s, i + 32, (z + w[1]) & _M, (y + _f64(s, i + 16)) & _M)
-        z, x = x, z
-        i += 64
-        if i == end:
-            break
-    mul = (_K1 + ((z & 0xFF) << 1)) & _M
-    i = last64
-    w = ((w[0] + ((n - 1) & 63)) & _M, w[1])
-    v = ((v[0] + w[0]) & _M, v[1])
-    w = ((w[0] + v[0]) & _M, w[1])
-    x = (_rot((x + y + v[0] + _f64(s, i + 8)) & _M, 37) * mul) & _M
-    y = (_rot((y + v[1] + _f64(s, i + 48)) & _M, 42) * mul) & _M
-    x ^= (w[1] * 9) & _M
-    y = (y + v[0] * 9 + _f64(s, i + 40)) & _M
-    z = (_rot((z + w[0]) & _M, 33) * mul) & _M
-    v = _weak32(s, i, (v[1] * mul) & _M, (x + w[0]) & _M)
-    w = _weak32(s, i + 32, (z + w[1]) & _M, (y + _f64(s, i + 16)) & _M)
-    z, x = x, z
-    return _hl16((_hl16(v[0], w[0], mul) + (_smix(y) * _K0) + z) & _M,
-                 (_hl16(v[1], w[1], mul) + x) & _M, mul)
+from . import _lib
+from .feature_column import CategoricalColumn, RaggedFeature
 
 
 def _to_bytes(v) -> bytes:
@@ -168,47 +38,122 @@ def _to_bytes(v) -> bytes:
     return str(v).encode("utf-8")
 
 
+def fingerprint64(s: bytes) -> int:
+    """farmhash::Fingerprint64 of a byte string (native host twin)."""
+    lib = _lib.load()
+    buf = (C.c_uint8 * max(1, len(s))).from_buffer_copy(s if s else b"\0")
+    return int(lib.dr_fingerprint64_host(C.cast(buf, C.c_void_p), len(s)))
+
+
+def pack_strings(values: Iterable):
+    """python values -> (uint8 buffer, int64 offsets [n+1]) in the layout the C-ABI hash entries take."""
+    parts = [_to_bytes(v) for v in values]
+    offsets = np.zeros(len(parts) + 1, dtype=np.int64)
+    if parts:
+        np.cumsum([len(p) for p in parts], out=offsets[1:])
+    data = np.frombuffer(b"".join(parts), dtype=np.uint8) if offsets[-1] else np.zeros(1, dtype=np.uint8)
+    return data, offsets
+
+
 def hash_bucket(values: Iterable, num_buckets: int) -> np.ndarray:
-    """tf.strings.to_hash_bucket_fast(values, num_buckets) on the host."""
-    cache = {}
-    out = []
-    for v in values:
-        b = _to_bytes(v)
-        h = cache.get(b)
-        if h is None:
-            h = fingerprint64(b) % num_buckets
-            cache[b] = h
-        out.append(h)
-    return np.asarray(out, dtype=np.int64)
+    """tf.strings.to_hash_bucket_fast(values, num_buckets) for host values -> int64 ids (numpy)."""
+    lib = _lib.load()
+    if isinstance(values, np.ndarray) and values.dtype.kind in "iu":
+        v = np.ascontiguousarray(values, dtype=np.int64).reshape(-1)
+        out = np.empty_like(v)
+        _lib.check(lib.dr_hash_bucket_i64_host(v.ctypes.data, v.size, int(num_buckets), out.ctypes.data),
+                   "dr_hash_bucket_i64_host")
+        return out
+    data, offsets = pack_strings(values)
+    n = offsets.size - 1
+    out = np.empty(n, dtype=np.int64)
+    _lib.check(lib.dr_hash_bucket_bytes_host(data.ctypes.data, offsets.ctypes.data, n, int(num_buckets),
+                                             out.ctypes.data), "dr_hash_bucket_bytes_host")
+    return out
 
 
-def column_ids(col: CategoricalColumn, value, device) -> torch.Tensor:
-    """Raw feature values of one single-valued categorical column -> int64 ids [B] on `device`.
+def vocabulary_ids(col: CategoricalColumn, values: Sequence) -> np.ndarray:
+    """categorical_column_with_vocabulary_list on host values: index in the list, OOV -> -1."""
+    if col.dtype == "string":
+        table = {_to_bytes(k): i for i, k in enumerate(col.vocabulary_list)}
+        return np.asarray([table.get(_to_bytes(v), -1) for v in values], dtype=np.int64)
+    table = {int(k): i for i, k in enumerate(col.vocabulary_list)}
+    return np.asarray([table.get(int(v), -1) for v in values], dtype=np.int64)
 
-    Out-of-vocabulary / out-of-range values become -1 (TF default), which the gather kernel
-    turns into a zero row.
+
+def _vocab_device_tables(col: CategoricalColumn, device):
+    cache = _vocab_device_tables.cache
+    key = (col, str(device))
+    if key not in cache:
+        keys = np.asarray([int(k) for k in col.vocabulary_list], dtype=np.int64)
+        order = np.argsort(keys, kind="stable")
+        cache[key] = (torch.from_numpy(keys[order]).to(device), torch.from_numpy(order.astype(np.int64)).to(device))
+    return cache[key]
+
+
+_vocab_device_tables.cache = {}
+
+
+def flat_ids(col: CategoricalColumn, values, device) -> torch.Tensor:
+    """Raw values of one categorical column (any shape, flattened) -> int64 ids on `device`.
+
+    CUDA integer tensors stay on the device; everything else is converted on the host and copied once.
+    Out-of-vocabulary / out-of-range values become -1 (TF default), which the gather kernels turn into a zero row.
     """
-    if isinstance(value, torch.Tensor) and value.dtype in (torch.int64, torch.int32) and col.kind == "identity":
-        v = value
-        if v.dim() == 2 and v.shape[1] == 1:
-            v = v[:, 0]
-        if v.dim() != 1:
-            raise NotImplementedError("multi-valued categorical features (mean combiner over >1 value) are not implemented yet")
-        return v.to(device=device, dtype=torch.int64)
-    arr = value.detach().cpu().numpy() if isinstance(value, torch.Tensor) else np.asarray(value)
-    if arr.ndim == 2 and arr.shape[1] == 1:
-        arr = arr[:, 0]
-    if arr.ndim != 1:
-        raise NotImplementedError("multi-valued categorical features (mean combiner over >1 value) are not implemented yet")
+    from . import ops
+    if isinstance(values, torch.Tensor) and values.is_cuda and values.dtype in (torch.int64, torch.int32):
+        v = values.reshape(-1).to(torch.int64)
+        if col.kind == "identity":
+            return torch.where((v >= 0) & (v < col.num_buckets), v, torch.full_like(v, -1))
+        if col.kind == "hash":
+            return ops.hash_bucket_i64(v, col.num_buckets)
+        if col.dtype != "string":
+            keys, index = _vocab_device_tables(col, v.device)
+            return ops.vocab_lookup_i64(v, keys, index, -1)
+        raise TypeError(f"column {col.key!r} has a string vocabulary but received an integer tensor")
+    arr = values.detach().cpu().numpy() if isinstance(values, torch.Tensor) else np.asarray(values)
+    arr = arr.reshape(-1)
     if col.kind == "hash":
-        ids = hash_bucket(arr.tolist(), col.num_buckets)
+        ids = hash_bucket(arr if arr.dtype.kind in "iu" else arr.tolist(), col.num_buckets)
     elif col.kind == "vocab":
-        table = {(_to_bytes(k) if col.dtype == "string" else int(k)): i for i, k in enumerate(col.vocabulary_list)}
-        if col.dtype == "string":
-            ids = np.asarray([table.get(_to_bytes(v), -1) for v in arr.tolist()], dtype=np.int64)
-        else:
-            ids = np.asarray([table.get(int(v), -1) for v in arr.tolist()], dtype=np.int64)
+        ids = vocabulary_ids(col, arr.tolist())
     else:
         ids = arr.astype(np.int64)
         ids = np.where((ids >= 0) & (ids < col.num_buckets), ids, -1)
-    return torch.from_numpy(ids).to(device)
+    return torch.from_numpy(np.ascontiguousarray(ids)).to(device)
+
+
+def column_ids(col: CategoricalColumn, value, device) -> torch.Tensor:
+    """Single-valued categorical column -> int64 ids [B] on `device` (accepts [B] or [B, 1])."""
+    shape = tuple(value.shape) if hasattr(value, "shape") else np.asarray(value).shape
+    if len(shape) == 2 and shape[1] == 1:
+        shape = shape[:1]
+    if len(shape) != 1:
+        raise ValueError(f"column {col.key!r}: expected one value per example ([B] or [B, 1]), got shape {shape}; "
+                         "pass multi-valued features as a RaggedIds")
+    return flat_ids(col, value, device)
+
+
+def ids_and_bags(keys: Sequence[str], cats: dict, inputs, device):
+    """Feature dict -> (ids [B, S] int64 on `device`, {slot: (flat ids, row_splits)} or None).
+
+    Slot order is `keys`.  Single-valued features fill their column of `ids`; a RaggedFeature (multi-valued
+    slot) goes to the bag dict and leaves a zero column that the mixed gather ignores.
+    """
+    cols, bags, B = [], {}, None
+    for s, k in enumerate(keys):
+        if k not in inputs:
+            raise KeyError(f"feature {k!r} missing from inputs")
+        v = inputs[k]
+        if isinstance(v, RaggedFeature):
+            rs = v.row_splits
+            splits = (rs if isinstance(rs, torch.Tensor) else torch.from_numpy(np.asarray(rs, dtype=np.int64)))
+            splits = splits.to(device=device, dtype=torch.int64)
+            bags[s] = (flat_ids(cats[k], v.values, device), splits)
+            cols.append(None)
+            B = splits.numel() - 1 if B is None else B
+        else:
+            cols.append(column_ids(cats[k], v, device))
+            B = cols[-1].shape[0]
+    cols = [c if c is not None else torch.zeros((B,), dtype=torch.int64, device=device) for c in cols]
+    return torch.stack(cols, dim=1), (bags or None)

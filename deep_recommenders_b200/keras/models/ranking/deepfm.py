@@ -48,8 +48,7 @@ class DeepFM(_ColumnModel):
         self._dnn = DNN(self._dnn_units_size, activation=self._dnn_activation, seed=seed)
 
     def logits(self, inputs) -> torch.Tensor:
-        ids = self._ids_matrix(inputs)
-        stack, fm_logit = self.embeddings(ids, want_logit=True)          # [B,S,D], [B]
+        stack, fm_logit = self._embed(inputs)                           # [B,S,D], [B]
         concat_embeddings = stack.view(stack.shape[0], -1)              # tf.concat(embeddings, axis=1)
         return fm_logit.unsqueeze(1) + self._dnn(concat_embeddings)
 

@@ -17,7 +17,7 @@ import torch
 from .... import ops
 from ....embedding import EmbeddingCollection
 from ....feature_column import EmbeddingColumn, IndicatorColumn
-from ....hashing import column_ids
+from ....hashing import ids_and_bags
 from ...layers.base import Dense, Layer, Model, register_keras_serializable
 
 
@@ -66,16 +66,22 @@ class _ColumnModel(Model):
                                               device=device, init_stddev=std, seed=seed, sparse_lr=sparse_lr)
         self.built = True
 
-    def _ids_matrix(self, inputs) -> torch.Tensor:
-        """dict[str -> ids] (reference: deepfm.py:39-43 iterates inputs.items()) or a ready [B,S] matrix."""
+    def _ids_and_bags(self, inputs):
+        """dict[str -> raw feature] (reference: deepfm.py:39-43 iterates inputs.items()) or a ready [B,S] id matrix
+        -> (ids [B,S] int64, {slot: (flat ids, row_splits)} for multi-valued features)."""
         if isinstance(inputs, torch.Tensor):
-            return inputs
-        cols = []
-        for k in self._keys:
-            if k not in inputs:
-                raise KeyError(f"feature {k!r} missing from inputs")
-            cols.append(column_ids(self._cat[k], inputs[k], self.embeddings.weight.device))
-        return torch.stack(cols, dim=1)
+            return inputs, None
+        return ids_and_bags(self._keys, self._cat, inputs, self.embeddings.weight.device)
+
+    def _ids_matrix(self, inputs) -> torch.Tensor:
+        ids, bags = self._ids_and_bags(inputs)
+        if bags:
+            raise ValueError("multi-valued features present: use _ids_and_bags")
+        return ids
+
+    def _embed(self, inputs):
+        ids, bags = self._ids_and_bags(inputs)
+        return self.embeddings(ids, want_logit=True, bags=bags)
 
 
 class FactorizationMachine(_ColumnModel):
@@ -84,12 +90,11 @@ class FactorizationMachine(_ColumnModel):
         super().__init__(indicator_columns, embedding_columns, **kwargs)
 
     def call(self, inputs, training=None, mask=None):
-        ids = self._ids_matrix(inputs)
-        _, logit = self.embeddings(ids, want_logit=True)
+        _, logit = self._embed(inputs)
         return torch.sigmoid(logit).unsqueeze(1)
 
     def logits(self, inputs) -> torch.Tensor:
-        _, logit = self.embeddings(self._ids_matrix(inputs), want_logit=True)
+        _, logit = self._embed(inputs)
         return logit
 
     def get_config(self):

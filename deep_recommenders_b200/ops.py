@@ -371,3 +371,242 @@ def bce_with_logits(z: torch.Tensor, y: torch.Tensor, z_add: torch.Tensor = None
 def sgd_step_(p: torch.Tensor, g: torch.Tensor, lr: float) -> None:
     lib = _lib.load()
     check(lib.dr_sgd_step(p.data_ptr(), g.data_ptr(), p.numel(), float(lr), _stream()), "dr_sgd_step")
+
+
+# ------------------------------------------------------------------------------------------
+# SURVEY 8(f) "next" rows: Adam, id pipeline on the device, multi-valued slots, row top-k
+# ------------------------------------------------------------------------------------------
+COMBINER_CODES = {"sum": 0, "mean": 1, "sqrtn": 2}
+
+
+def adam_step_(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, lr_t: float,
+               beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-7, zero_grad: bool = True) -> None:
+    """In-place dense Adam over a flat fp32 buffer (TensorFlow's ApplyAdam arithmetic; lr_t carries the bias correction)."""
+    lib = _lib.load()
+    for name, t in (("p", p), ("g", g), ("m", m), ("v", v)):
+        _f32(t, name)
+        if not t.is_contiguous() or t.numel() != p.numel():
+            raise ValueError(f"adam_step_: {name} must be contiguous with {p.numel()} elements")
+    check(lib.dr_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), float(lr_t),
+                           float(beta1), float(beta2), float(eps), int(bool(zero_grad)), _stream()), "dr_adam_step")
+
+
+def hash_bucket_i64(values: torch.Tensor, num_buckets: int) -> torch.Tensor:
+    """tf.strings.to_hash_bucket_fast(tf.as_string(values), num_buckets) for a CUDA int64 tensor."""
+    lib = _lib.load()
+    if not values.is_cuda:
+        raise _lib.DeepRecError("hash_bucket_i64: values must be a CUDA tensor (host features use hashing.hash_bucket)")
+    v = values.to(torch.int64).contiguous()
+    out = torch.empty_like(v)
+    check(lib.dr_hash_bucket_i64(v.data_ptr(), v.numel(), int(num_buckets), out.data_ptr(), _stream()),
+          "dr_hash_bucket_i64")
+    return out
+
+
+def hash_bucket_bytes(data: torch.Tensor, offsets: torch.Tensor, num_buckets: int) -> torch.Tensor:
+    """Strings shipped as one uint8 CUDA buffer + int64 offsets [n+1] -> bucket ids [n]."""
+    lib = _lib.load()
+    if not (data.is_cuda and offsets.is_cuda):
+        raise _lib.DeepRecError("hash_bucket_bytes: data / offsets must be CUDA tensors")
+    if data.dtype != torch.uint8 or offsets.dtype != torch.int64:
+        raise TypeError("hash_bucket_bytes: data must be uint8 and offsets int64")
+    data, offsets = data.contiguous(), offsets.contiguous()
+    n = offsets.numel() - 1
+    out = torch.empty((max(n, 0),), device=data.device, dtype=torch.int64)
+    check(lib.dr_hash_bucket_bytes(data.data_ptr(), offsets.data_ptr(), n, int(num_buckets), out.data_ptr(), _stream()),
+          "dr_hash_bucket_bytes")
+    return out
+
+
+def vocab_lookup_i64(values: torch.Tensor, keys_sorted: torch.Tensor, vocab_index: torch.Tensor,
+                     default_id: int = -1) -> torch.Tensor:
+    lib = _lib.load()
+    if not values.is_cuda:
+        raise _lib.DeepRecError("vocab_lookup_i64: values must be a CUDA tensor")
+    v = values.to(torch.int64).contiguous()
+    out = torch.empty_like(v)
+    check(lib.dr_vocab_lookup_i64(v.data_ptr(), v.numel(), keys_sorted.data_ptr(), vocab_index.data_ptr(),
+                                  keys_sorted.numel(), int(default_id), out.data_ptr(), _stream()),
+          "dr_vocab_lookup_i64")
+    return out
+
+
+def _bag_fwd(lib, table_ptr, rows, row_stride, ids, splits, B, D, combiner, out_ptr, out_stride):
+    check(lib.dr_embed_bag_fwd(table_ptr, rows, row_stride, ids.data_ptr(), ids.element_size(), splits.data_ptr(),
+                               B, D, COMBINER_CODES[combiner], out_ptr, out_stride, _stream()), "dr_embed_bag_fwd")
+
+
+def _bag_bwd(lib, ids, splits, B, D, combiner, g_ptr, g_stride, rows, row_stride, grad_ptr, scale):
+    check(lib.dr_embed_bag_bwd(ids.data_ptr(), ids.element_size(), splits.data_ptr(), B, D, COMBINER_CODES[combiner],
+                               g_ptr, g_stride, rows, row_stride, grad_ptr, float(scale), _stream()),
+          "dr_embed_bag_bwd")
+
+
+def _splits(row_splits: torch.Tensor) -> torch.Tensor:
+    if not isinstance(row_splits, torch.Tensor) or row_splits.dtype != torch.int64 or not row_splits.is_cuda:
+        raise TypeError("row_splits must be a CUDA int64 tensor [B+1]")
+    return row_splits.contiguous()
+
+
+class EmbedBag(torch.autograd.Function):
+    """out[B, D] = combine over the valid ids of each ragged bag (multi-valued slot); see dr_embed_bag_fwd.
+
+    `table` is a contiguous [rows, row_stride] fp32 tensor; the D embedding columns start at `col_offset`
+    (row_stride == D, col_offset == 0 for a plain table).  sparse_lr: None -> dense gradient for `table`;
+    a float -> fused sparse SGD in backward.
+    """
+
+    @staticmethod
+    def forward(ctx, table, ids, row_splits, D: int, combiner: str, sparse_lr, col_offset: int = 0):
+        lib = _lib.load()
+        table = _f32(table, "table")
+        ids = _ids(ids)
+        row_splits = _splits(row_splits)
+        B = row_splits.numel() - 1
+        rows, stride = table.shape
+        if col_offset + D > stride:
+            raise ValueError(f"EmbedBag: columns [{col_offset}, {col_offset + D}) exceed the row pitch {stride}")
+        out = torch.empty((B, D), device=table.device, dtype=torch.float32)
+        _bag_fwd(lib, table.data_ptr() + 4 * col_offset, rows, stride, ids, row_splits, B, D, combiner, out.data_ptr(), D)
+        ctx.save_for_backward(table, ids, row_splits)
+        ctx.D, ctx.combiner, ctx.sparse_lr, ctx.col_offset = D, combiner, sparse_lr, col_offset
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        table, ids, row_splits = ctx.saved_tensors
+        g = _f32(g, "g")
+        fused = ctx.sparse_lr is not None
+        tgt = table if fused else torch.zeros_like(table)
+        B = row_splits.numel() - 1
+        with torch.no_grad():
+            _bag_bwd(lib, ids, row_splits, B, ctx.D, ctx.combiner, g.data_ptr(), ctx.D, table.shape[0], table.shape[1],
+                     tgt.data_ptr() + 4 * ctx.col_offset, -float(ctx.sparse_lr) if fused else 1.0)
+        return (None if fused else tgt), None, None, None, None, None, None
+
+
+class EmbedFMMixed(torch.autograd.Function):
+    """EmbedFM for a collection in which some slots are multi-valued.
+
+    Each ragged slot r is first reduced into a per-batch scratch "table" of B rows in the collection's own row
+    layout (embedding columns = mean of the bag's valid rows, first-order entry = SUM of their weights: the
+    indicator column is a multi-hot count vector); the fused gather + FM kernel then reads slot r from that
+    scratch with ids 0..B-1, so the whole model is still ONE dr_embed_fm_fwd launch.  Backward mirrors it: the
+    fused backward accumulates slot r's per-example gradient in a scratch grad table, dr_embed_bag_bwd spreads
+    it over the bag's rows (embedding / count, first-order x 1).
+
+    ids [B, S]: columns of ragged slots are ignored.  bags: {slot: (flat_ids, row_splits[B+1])}.
+    """
+
+    @staticmethod
+    def forward(ctx, ids, weight, linear, bias, meta, bags):
+        lib = _lib.load()
+        if not meta.with_linear or bias is None:
+            raise ValueError("EmbedFMMixed needs a collection with the first-order term (with_linear=True)")
+        ids = _ids(ids).clone()
+        B, S = ids.shape
+        D, RS = meta.dim, meta.row_stride
+        dev = weight.device
+        fused_rows = meta.layout == "fused"
+        tp, lp, rows = meta.pointers(weight, linear)
+        tp, lp, rows = tp.clone(), lp.clone(), rows.clone()
+        slots = sorted(bags)
+        scratch = torch.zeros((len(slots), B, RS), device=dev, dtype=torch.float32)
+        scratch_lin = None if fused_rows else torch.zeros((len(slots), B), device=dev, dtype=torch.float32)
+        ar = torch.arange(B, device=dev, dtype=ids.dtype)
+        saved_bags = []
+        for k, s in enumerate(slots):
+            bid, bsp = bags[s]
+            bid, bsp = _ids(bid, "bag ids"), _splits(bsp)
+            if bsp.numel() != B + 1:
+                raise ValueError(f"slot {s}: row_splits has {bsp.numel()} entries, expected B+1 = {B + 1}")
+            off, n_rows = int(meta._offsets[s]), meta.rows_list[s]
+            base = weight.data_ptr() + 4 * off * RS
+            _bag_fwd(lib, base, n_rows, RS, bid, bsp, B, D, "mean", scratch[k].data_ptr(), RS)
+            if fused_rows:
+                _bag_fwd(lib, base + 4 * D, n_rows, RS, bid, bsp, B, 1, "sum", scratch[k].data_ptr() + 4 * D, RS)
+                lin_ptr = scratch[k].data_ptr() + 4 * D
+            else:
+                _bag_fwd(lib, linear.data_ptr() + 4 * off, n_rows, 1, bid, bsp, B, 1, "sum",
+                         scratch_lin[k].data_ptr(), 1)
+                lin_ptr = scratch_lin[k].data_ptr()
+            tp[s] = scratch[k].data_ptr()
+            lp[s] = lin_ptr
+            rows[s] = B
+            ids[:, s] = ar
+            saved_bags.append((s, bid, bsp))
+        stack = torch.empty((B, S, D), device=dev, dtype=torch.float32)
+        sum_e = torch.empty((B, D), device=dev, dtype=torch.float32)
+        logit = torch.empty((B,), device=dev, dtype=torch.float32)
+        check(lib.dr_embed_fm_fwd(tp.data_ptr(), lp.data_ptr(), rows.data_ptr(), ids.data_ptr(), ids.element_size(),
+                                  _ptr(bias), B, S, D, RS, meta.lin_stride, meta.flags, stack.data_ptr(),
+                                  sum_e.data_ptr(), logit.data_ptr(), _stream()), "dr_embed_fm_fwd")
+        ctx.meta, ctx.saved_bags = meta, saved_bags
+        ctx.save_for_backward(ids, stack, sum_e, weight, linear, bias, rows)
+        return stack, logit
+
+    @staticmethod
+    def backward(ctx, g_stack, g_logit):
+        lib = _lib.load()
+        ids, stack, sum_e, weight, linear, bias, rows = ctx.saved_tensors
+        meta = ctx.meta
+        B, S = ids.shape
+        D, RS = meta.dim, meta.row_stride
+        dev = weight.device
+        fused_rows = meta.layout == "fused"
+        g_stack = None if g_stack is None else _f32(g_stack, "g_stack")
+        g_logit = None if g_logit is None else _f32(g_logit, "g_logit")
+        if g_stack is None and g_logit is None:
+            return None, None, None, None, None, None
+        if g_logit is None:
+            g_logit = torch.zeros((B,), device=dev, dtype=torch.float32)
+        fused_sgd = meta.sparse_lr is not None
+        if fused_sgd:
+            gw, gl, gb, scale = weight, linear, bias, -float(meta.sparse_lr)
+        else:
+            gw = torch.zeros_like(weight)
+            gl = None if linear is None else torch.zeros_like(linear)
+            gb = None if bias is None else torch.zeros_like(bias)
+            scale = 1.0
+        tp, lp, _ = meta.pointers(gw, gl, cache=False)
+        tp, lp = tp.clone(), lp.clone()
+        nb = len(ctx.saved_bags)
+        gscratch = torch.zeros((nb, B, RS), device=dev, dtype=torch.float32)
+        gscratch_lin = None if fused_rows else torch.zeros((nb, B), device=dev, dtype=torch.float32)
+        for k, (s, _, _) in enumerate(ctx.saved_bags):
+            tp[s] = gscratch[k].data_ptr()
+            lp[s] = gscratch[k].data_ptr() + 4 * D if fused_rows else gscratch_lin[k].data_ptr()
+        with torch.no_grad():
+            check(lib.dr_embed_fm_bwd(ids.data_ptr(), ids.element_size(), rows.data_ptr(), stack.data_ptr(),
+                                      sum_e.data_ptr(), g_logit.data_ptr(), _ptr(g_stack), B, S, D, RS,
+                                      meta.lin_stride, meta.flags, tp.data_ptr(), lp.data_ptr(), _ptr(gb), scale,
+                                      _stream()), "dr_embed_fm_bwd")
+            for k, (s, bid, bsp) in enumerate(ctx.saved_bags):
+                off, n_rows = int(meta._offsets[s]), meta.rows_list[s]
+                base = gw.data_ptr() + 4 * off * RS
+                # the scratch already carries `scale`: spread it with scale = 1
+                _bag_bwd(lib, bid, bsp, B, D, "mean", gscratch[k].data_ptr(), RS, n_rows, RS, base, 1.0)
+                if fused_rows:
+                    _bag_bwd(lib, bid, bsp, B, 1, "sum", gscratch[k].data_ptr() + 4 * D, RS, n_rows, RS, base + 4 * D, 1.0)
+                else:
+                    _bag_bwd(lib, bid, bsp, B, 1, "sum", gscratch_lin[k].data_ptr(), 1, n_rows, 1,
+                             gl.data_ptr() + 4 * off, 1.0)
+        if fused_sgd:
+            return None, None, None, None, None, None
+        return None, gw, gl, gb, None, None
+
+
+def topk_rows(scores_: torch.Tensor, k: int):
+    """tf.math.top_k(scores, k) on a CUDA [nq, nc] matrix: (values [nq,k] descending, int32 indices [nq,k])."""
+    lib = _lib.load()
+    s = _f32(scores_, "scores")
+    if s.dim() != 2:
+        raise ValueError(f"topk_rows: expected a 2-D score matrix, got shape {tuple(s.shape)}")
+    nq, nc = s.shape
+    if k > nc or k < 1:
+        raise ValueError(f"input must have at least k columns. Had {nc}, needed {k}")
+    vals = torch.empty((nq, k), device=s.device, dtype=torch.float32)
+    idx = torch.empty((nq, k), device=s.device, dtype=torch.int32)
+    check(lib.dr_topk_rows(s.data_ptr(), nq, nc, nc, k, vals.data_ptr(), idx.data_ptr(), _stream()), "dr_topk_rows")
+    return vals, idx

@@ -39,6 +39,11 @@ extern "C" {
                                    embedding chunks; lin_ptrs / lin_stride are ignored                  */
 
 /* activation codes (tf.keras.layers.Dense(activation=...)) */
+/* combiner of a multi-valued slot (tf.feature_column.embedding_column(combiner=...)) */
+#define DR_COMBINER_SUM 0
+#define DR_COMBINER_MEAN 1
+#define DR_COMBINER_SQRTN 2
+
 #define DR_ACT_NONE 0
 #define DR_ACT_RELU 1
 #define DR_ACT_SIGMOID 2
@@ -234,6 +239,63 @@ int dr_sgd_step(float* p, const float* g, int64_t n, float lr, void* stream);
  *   prob_out [B] (sigmoid) and gz may be NULL.                                            */
 int dr_bce_logits_fwd_bwd(const float* z, const float* z_add, const float* y, int64_t B,
                           float* prob_out, float* loss_out, float* gz, void* stream);
+
+/* =======================================================================================
+ * SURVEY.md 8(f) "next" rows: the callers either side of the hot path.
+ * ======================================================================================= */
+
+/* ---- 8(f) #1  Adam (examples/train_deepfm_on_movielens_keras.py:44, train_fm_on_movielens_estimator.py:51).
+ * TensorFlow's Adam is dense even for IndexedSlices gradients (every row's m, v decay and every row moves
+ * each step), so the parity-exact form is one pass over the whole parameter / table arena:
+ *   m += (g - m)(1 - beta1);  v += (g*g - v)(1 - beta2);  p -= lr_t * m / (sqrt(v) + eps)
+ * with lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t) computed by the caller (t = 1, 2, ...).
+ * g holds the accumulated gradient (dr_embed_fm_bwd / dr_scatter_add with scale = 1, or a dense gradient);
+ * zero_grad = 1 clears it in the same pass.  eps = 1e-7 (tf.keras) or 1e-8 (tf.train.AdamOptimizer).   */
+int dr_adam_step(float* p, float* g, float* m, float* v, int64_t n, float lr_t, float beta1, float beta2,
+                 float eps, int zero_grad, void* stream);
+
+/* ---- 8(f) #2  id pipeline: raw feature value -> int64 row id, bit-exact with TensorFlow's columns.
+ * categorical_column_with_hash_bucket = FarmHash Fingerprint64(bytes of str(value)) mod num_buckets
+ * (tf.strings.to_hash_bucket_fast).  Device entries take device pointers; strings travel as one byte
+ * buffer + offsets [n+1].  Integer features are hashed through their decimal string, as TF does.
+ * The *_host twins run the same code on the CPU for features that arrive as host strings (TFRecord parse);
+ * they take host pointers and need no GPU.                                                              */
+int dr_hash_bucket_i64(const int64_t* values, int64_t n, int64_t num_buckets, int64_t* out_ids, void* stream);
+int dr_hash_bucket_bytes(const uint8_t* bytes, const int64_t* offsets, int64_t n, int64_t num_buckets,
+                         int64_t* out_ids, void* stream);
+int dr_hash_bucket_i64_host(const int64_t* values, int64_t n, int64_t num_buckets, int64_t* out_ids);
+int dr_hash_bucket_bytes_host(const uint8_t* bytes, const int64_t* offsets, int64_t n, int64_t num_buckets,
+                              int64_t* out_ids);
+uint64_t dr_fingerprint64_host(const uint8_t* s, int64_t len);
+/* categorical_column_with_vocabulary_list on integer keys: keys_sorted [vocab_size] ascending,
+ * vocab_index[j] = position of keys_sorted[j] in the user's list; a value not in the list -> default_id
+ * (TF default -1 => zero embedding row, all-zero indicator).                                            */
+int dr_vocab_lookup_i64(const int64_t* values, int64_t n, const int64_t* keys_sorted, const int64_t* vocab_index,
+                        int64_t vocab_size, int64_t default_id, int64_t* out_ids, void* stream);
+
+/* Multi-valued slot (VarLenFeature, e.g. "Genres" movielens.py:122): ids [nnz] + row_splits [B+1].
+ *   out[b, :] = combine_j table[ids[j], :D]  over the VALID ids (0 <= id < rows) of bag b;
+ *   DR_COMBINER_MEAN divides by the number of valid ids (safe_embedding_lookup_sparse: ids < 0 are pruned
+ *   first), SQRTN by its square root, SUM by 1; a bag without a valid id gives zeros.
+ *   The indicator-column (first-order) term of such a slot is DR_COMBINER_SUM with D = 1.
+ * bwd: grad_table[id, :D] += scale * g_out[b, :] / den(b) for every valid id (duplicates accumulate);
+ *   scale = 1 for plain gradients, -lr for fused sparse SGD.  row_stride / out_stride / g_stride are row
+ *   pitches in floats (>= D): out may be a [B, 32]-pitched scratch "table" in the fused row layout, which
+ *   dr_embed_fm_fwd then reads as slot s with ids = 0..B-1 (this is how a multi-valued slot joins the fused
+ *   gather + FM launch; its backward goes through the same scratch).                                     */
+int dr_embed_bag_fwd(const float* table, int64_t rows, int64_t row_stride, const void* ids, int id_bytes,
+                     const int64_t* row_splits, int64_t B, int D, int combiner, float* out, int64_t out_stride,
+                     void* stream);
+int dr_embed_bag_bwd(const void* ids, int id_bytes, const int64_t* row_splits, int64_t B, int D, int combiner,
+                     const float* g_out, int64_t g_stride, int64_t rows, int64_t row_stride, float* grad_table,
+                     float scale, void* stream);
+
+/* ---- 8(f) #3  row-wise top-k (factorized_top_k.py:58-62,196-226,330-334 tf.math.top_k):
+ * out_vals [nq,k] descending, out_idx [nq,k] int32 column indices, ties -> lower index first.
+ * scores is [nq, nc] with row pitch ld floats.  k > nc is rejected like TF ("input must have at least k
+ * columns").                                                                                            */
+int dr_topk_rows(const float* scores, int64_t nq, int64_t nc, int64_t ld, int k, float* out_vals,
+                 int32_t* out_idx, void* stream);
 
 /* Scratch for the tensor-core GEMM variant (hi/lo TF32 operand planes).  The caller owns the
  * buffer and keeps it alive until it registers another one (ptr = NULL unregisters).  One
