@@ -273,3 +273,147 @@ def embed_fm_grad(tables_rows, ids, stack, g_logit, g_stack, dtype=np.float64):
         gts.append(gt)
         gls.append(glin)
     return gts, gls, dtype(gl.sum())
+
+
+# ------------------------------------------------------------------------------------------
+# SURVEY.md 8(f) "next" rows.  The arithmetic of these lives in TensorFlow (un-vendored), so each
+# function restates TF's documented op; parity is UNPINNED by the reference except where a
+# reference test is cited.
+# ------------------------------------------------------------------------------------------
+def embedding_bag(table, flat_ids, row_splits, combiner="mean", dtype=np.float32):
+    """tf.nn.safe_embedding_lookup_sparse(table, ids, combiner=...) for a ragged slot (embedding_column over a
+    VarLenFeature, datasets/movielens.py:122; default combiner "mean"): ids < 0 (OOV) are pruned, a bag with no
+    valid id gives the zero vector.  Ids >= rows cannot occur in TF (hash / vocab columns are in range by
+    construction); here they are pruned like OOV.  Sequential accumulation, then a true division."""
+    flat_ids = np.asarray(flat_ids, dtype=np.int64)
+    row_splits = np.asarray(row_splits, dtype=np.int64)
+    B, D = row_splits.size - 1, table.shape[1]
+    out = np.zeros((B, D), dtype=dtype)
+    for b in range(B):
+        acc, cnt = np.zeros((D,), dtype=dtype), 0
+        for j in range(row_splits[b], row_splits[b + 1]):
+            i = flat_ids[j]
+            if 0 <= i < table.shape[0]:
+                acc = acc + table[i].astype(dtype)
+                cnt += 1
+        if cnt:
+            den = {"sum": 1.0, "mean": float(cnt), "sqrtn": float(np.sqrt(dtype(cnt)))}[combiner]
+            out[b] = acc / dtype(den)
+    return out
+
+
+def embedding_bag_grad(rows, flat_ids, row_splits, g_out, combiner="mean", dtype=np.float64):
+    """Dense gradient of embedding_bag w.r.t. the table: every valid id of bag b receives g_out[b] / den(b)."""
+    flat_ids = np.asarray(flat_ids, dtype=np.int64)
+    row_splits = np.asarray(row_splits, dtype=np.int64)
+    B, D = g_out.shape
+    gt = np.zeros((rows, D), dtype=dtype)
+    for b in range(B):
+        seg = flat_ids[row_splits[b]:row_splits[b + 1]]
+        seg = seg[(seg >= 0) & (seg < rows)]
+        if seg.size == 0:
+            continue
+        den = {"sum": 1.0, "mean": float(seg.size), "sqrtn": float(np.sqrt(seg.size))}[combiner]
+        np.add.at(gt, seg, np.asarray(g_out[b], dtype) / den)
+    return gt
+
+
+def adam_lr_t(lr, step, beta1=0.9, beta2=0.999):
+    """Keras optimizer_v2 Adam / tf.train.AdamOptimizer: lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t), t = 1, 2, ..."""
+    return lr * np.sqrt(1.0 - beta2 ** step) / (1.0 - beta1 ** step)
+
+
+def adam_dense(p, g, m, v, lr_t, beta1=0.9, beta2=0.999, eps=1e-7, dtype=np.float32):
+    """TensorFlow's ApplyAdam functor (the optimizer both reference examples use:
+    examples/train_deepfm_on_movielens_keras.py:44, examples/train_fm_on_movielens_estimator.py:51):
+        m += (g - m)(1 - b1);  v += (g*g - v)(1 - b2);  p -= lr_t * m / (sqrt(v) + eps)
+    Returns (p, m, v).  TF applies it densely to embedding variables too (module docstring of optim.cu)."""
+    p, g, m, v = (np.asarray(a, dtype=dtype) for a in (p, g, m, v))
+    m = m + (g - m) * dtype(1.0 - dtype(beta1))
+    v = v + (g * g - v) * dtype(1.0 - dtype(beta2))
+    p = p - (m * dtype(lr_t)) / (np.sqrt(v) + dtype(eps))
+    return p, m, v
+
+
+def adam_rows_lazy(p, g_rows, m, v, touched, lr_t, beta1=0.9, beta2=0.999, eps=1e-7, dtype=np.float32):
+    """Row-sparse ("lazy") Adam: the ApplyAdam functor on the `touched` rows only, with the row gradient already
+    summed over duplicate ids; untouched rows keep p, m and v.  This is tfa.optimizers.LazyAdam's semantics,
+    NOT tf.keras.optimizers.Adam's (which decays m, v of every row every step): an opt-in deviation for tables
+    whose dense pass would dominate the step."""
+    p, m, v = (np.array(a, dtype=dtype, copy=True) for a in (p, m, v))
+    t = np.unique(np.asarray(touched, dtype=np.int64))
+    t = t[(t >= 0) & (t < p.shape[0])]
+    p[t], m[t], v[t] = adam_dense(p[t], np.asarray(g_rows, dtype)[t], m[t], v[t], lr_t, beta1, beta2, eps, dtype)
+    return p, m, v
+
+
+def top_k(scores, k):
+    """tf.math.top_k(scores, k): values descending; equal values -> lower index first.  -> (values, int32 idx)."""
+    scores = np.asarray(scores)
+    if k > scores.shape[1]:
+        raise ValueError("input must have at least k columns")
+    idx = np.argsort(-scores, axis=1, kind="stable")[:, :k]
+    return np.take_along_axis(scores, idx, axis=1), idx.astype(np.int32)
+
+
+def take_long_axis(arr, indices):                              # factorized_top_k.py:26-41
+    return np.take_along_axis(np.asarray(arr), np.asarray(indices), axis=1)
+
+
+def exclude(scores, identifiers, exclude_ids, k):              # factorized_top_k.py:44-67
+    scores, identifiers, exclude_ids = np.asarray(scores), np.asarray(identifiers), np.asarray(exclude_ids)
+    isin = (identifiers[:, :, None] == exclude_ids[:, None, :]).any(-1)
+    adjusted = scores - isin.astype(np.float32) * np.float32(1.0e5)
+    k = min(k, scores.shape[1])
+    _, idx = top_k(adjusted, k)
+    return take_long_axis(scores, idx), take_long_axis(identifiers, idx)
+
+
+def brute_force_topk(queries, candidates, identifiers, k, dtype=np.float32):   # factorized_top_k.py:322-334
+    scores = queries.astype(dtype) @ candidates.astype(dtype).T
+    vals, idx = top_k(scores, k)
+    ident = np.arange(candidates.shape[0]) if identifiers is None else np.asarray(identifiers)
+    return vals, ident[idx]
+
+
+def streaming_topk(queries, candidate_batches, identifier_batches, k, handle_incomplete_batches=True,
+                   dtype=np.float32):
+    """Streaming.call (factorized_top_k.py:180-262): per-batch top-k (:199-211), then the reduction that
+    re-selects top-k over [state | batch top-k] (:213-230); candidates are numbered by a running counter when
+    no identifiers are given (:240-249)."""
+    nq = queries.shape[0]
+    st_s = np.zeros((nq, 0), dtype=dtype)
+    st_i = None
+    counter = 0
+    for bi, cand in enumerate(candidate_batches):
+        n = cand.shape[0]
+        ident = np.arange(counter, counter + n, dtype=np.int32) if identifier_batches is None \
+            else np.asarray(identifier_batches[bi])
+        counter += n
+        scores = queries.astype(dtype) @ cand.astype(dtype).T
+        k_ = min(k, n) if handle_incomplete_batches else k
+        s, idx = top_k(scores, k_)
+        xi = ident[idx]
+        if st_i is None:
+            st_i = np.zeros((nq, 0), dtype=xi.dtype)
+        js, ji = np.concatenate([st_s, s], axis=1), np.concatenate([st_i, xi], axis=1)
+        k_ = min(k, js.shape[1]) if handle_incomplete_batches else k
+        st_s, idx = top_k(js, k_)
+        st_i = np.take_along_axis(ji, idx, axis=1)
+    return st_s, st_i
+
+
+def topk_categorical_accuracy(y_true, y_pred, k):
+    """tf.keras.metrics.TopKCategoricalAccuracy(k) on one batch = mean(in_top_k(y_pred, argmax(y_true), k));
+    tf.math.in_top_k counts a target as inside when fewer than k predictions are STRICTLY larger."""
+    y_true, y_pred = np.asarray(y_true), np.asarray(y_pred)
+    tgt = y_true.argmax(axis=1)
+    tv = np.take_along_axis(y_pred, tgt[:, None], axis=1)
+    return float(((y_pred > tv).sum(axis=1) < k).mean())
+
+
+def factorized_topk_metric(queries, true_candidates, top_k_scores, ks):       # factorized_top_k.py:487-511
+    pos = (queries * true_candidates).sum(axis=1, keepdims=True)
+    y_true = np.concatenate([np.ones_like(pos), np.zeros_like(top_k_scores)], axis=1)
+    y_pred = np.concatenate([pos, top_k_scores], axis=1)
+    return [topk_categorical_accuracy(y_true, y_pred, k) for k in ks]

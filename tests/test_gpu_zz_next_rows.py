@@ -1,0 +1,240 @@
+"""SURVEY 8(f) "next" rows on the GPU through the C-ABI, against the oracle: device id pipeline (FarmHash bucket,
+vocabulary lookup: bit-exact), multi-valued slot bags (mean / sum / sqrtn, OOV pruning), mixed single- and
+multi-valued collections through the fused gather, dense Adam (TF ApplyAdam arithmetic), row top-k (tf.math.top_k
+order incl. ties).  (File name sorts after the hot-path suites on purpose: rows (a)-(e) run first.)"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import farmhash_py as F
+from oracle import reference_np as R
+
+pytestmark = pytest.mark.gpu
+
+
+# ---- id pipeline ---------------------------------------------------------------------------------------
+def test_device_hash_bucket_i64_bit_exact():
+    from deep_recommenders_b200 import ops
+    rng = np.random.default_rng(0)
+    vals = np.concatenate([np.array([0, 1, -1, 9, 10, 6040, -2 ** 63, 2 ** 63 - 1], dtype=np.int64),
+                           rng.integers(-10 ** 12, 10 ** 12, size=5000), rng.integers(0, 7000, size=5000)])
+    for nb in (1, 100, 1_000_000, 2 ** 40 + 9):
+        got = ops.hash_bucket_i64(torch.from_numpy(vals).cuda(), nb).cpu().numpy()
+        assert got.tolist() == F.hash_bucket_py(vals.tolist(), nb)
+
+
+def test_device_hash_bucket_bytes_bit_exact_all_length_branches():
+    from deep_recommenders_b200 import ops
+    from deep_recommenders_b200.hashing import pack_strings, hash_bucket
+    rng = np.random.default_rng(1)
+    lengths = list(range(0, 70)) + [127, 128, 129, 192, 193, 500]
+    strings = [bytes(rng.integers(0, 256, size=n, dtype=np.uint8)) for n in lengths for _ in range(2)]
+    data, offs = pack_strings(strings)
+    got = ops.hash_bucket_bytes(torch.from_numpy(data.copy()).cuda(), torch.from_numpy(offs).cuda(), 1_000_003)
+    assert got.cpu().tolist() == F.hash_bucket_py(strings, 1_000_003)
+    assert got.cpu().tolist() == hash_bucket(strings, 1_000_003).tolist()      # host twin, same source
+    empty = ops.hash_bucket_bytes(torch.zeros(1, dtype=torch.uint8, device="cuda"),
+                                  torch.zeros(1, dtype=torch.int64, device="cuda"), 10)
+    assert empty.numel() == 0
+
+
+def test_device_vocab_lookup_bit_exact():
+    from deep_recommenders_b200 import feature_column as fc
+    from deep_recommenders_b200.hashing import flat_ids, vocabulary_ids
+    vocab = [56, 1, 18, 25, 35, 45, 50]                           # deliberately unsorted
+    col = fc.categorical_column_with_vocabulary_list("age", vocab)
+    rng = np.random.default_rng(2)
+    vals = rng.integers(-5, 70, size=4000).astype(np.int64)
+    got = flat_ids(col, torch.from_numpy(vals).cuda(), torch.device("cuda"))
+    want = np.array([vocab.index(v) if v in vocab else -1 for v in vals.tolist()])
+    assert np.array_equal(got.cpu().numpy(), want)
+    assert np.array_equal(vocabulary_ids(col, vals.tolist()), want)
+
+
+def test_device_and_host_id_paths_agree_for_hash_columns():
+    from deep_recommenders_b200 import feature_column as fc
+    from deep_recommenders_b200.hashing import flat_ids
+    col = fc.categorical_column_with_hash_bucket("user_id", 6040, dtype="int64")
+    vals = np.random.default_rng(3).integers(1, 6041, size=3000).astype(np.int64)
+    on_dev = flat_ids(col, torch.from_numpy(vals).cuda(), torch.device("cuda")).cpu().numpy()
+    on_host = flat_ids(col, vals, torch.device("cuda")).cpu().numpy()
+    assert np.array_equal(on_dev, on_host)
+    assert on_dev.min() >= 0 and on_dev.max() < 6040
+
+
+# ---- multi-valued slots -----------------------------------------------------------------------------------
+def make_bags(B, rows, seed, max_len=6, oov_frac=0.15, empty_frac=0.2):
+    rng = np.random.default_rng(seed)
+    lens = rng.integers(1, max_len + 1, size=B)
+    lens[rng.random(B) < empty_frac] = 0
+    splits = np.zeros(B + 1, dtype=np.int64)
+    np.cumsum(lens, out=splits[1:])
+    ids = rng.integers(0, rows, size=int(splits[-1])).astype(np.int64)
+    oov = rng.random(ids.shape) < oov_frac
+    ids = np.where(oov, np.where(rng.random(ids.shape) < 0.5, -1, rows + 5), ids)
+    return ids, splits
+
+
+@pytest.mark.parametrize("D", [1, 3, 4, 16, 20, 64, 128])
+@pytest.mark.parametrize("combiner", ["mean", "sum", "sqrtn"])
+def test_embed_bag_forward_and_backward(D, combiner):
+    from deep_recommenders_b200 import ops
+    rows, B = 37, 301
+    rng = np.random.default_rng(D)
+    table = rng.standard_normal((rows, D)).astype(np.float32)
+    ids, splits = make_bags(B, rows, seed=D + 1)
+    t = torch.from_numpy(table).cuda().requires_grad_(True)
+    out = ops.EmbedBag.apply(t, torch.from_numpy(ids).cuda(), torch.from_numpy(splits).cuda(), D, combiner, None)
+    ref64 = R.embedding_bag(table, ids, splits, combiner, np.float64)
+    scale = R.embedding_bag(np.abs(table), ids, splits, "sum", np.float64)
+    assert (np.abs(out.detach().cpu().numpy() - ref64) <= 1e-6 * scale + 1e-7).all()
+    if combiner == "sum":       # same accumulation order as the sequential oracle: bit-exact
+        assert np.array_equal(out.detach().cpu().numpy(), R.embedding_bag(table, ids, splits, "sum", np.float32))
+    g = rng.standard_normal((B, D)).astype(np.float32)
+    out.backward(torch.from_numpy(g).cuda())
+    gref = R.embedding_bag_grad(rows, ids, splits, g, combiner, np.float64)
+    gabs = R.embedding_bag_grad(rows, ids, splits, np.abs(g), combiner, np.float64)
+    assert (np.abs(t.grad.cpu().numpy() - gref) <= 1e-5 * gabs + 1e-7).all()
+
+
+def test_embed_bag_int32_ids_empty_batch_and_fused_sgd():
+    from deep_recommenders_b200 import ops
+    rows, B, D = 11, 40, 8
+    rng = np.random.default_rng(5)
+    table = rng.standard_normal((rows, D)).astype(np.float32)
+    ids, splits = make_bags(B, rows, seed=6)
+    t = torch.from_numpy(table).cuda().requires_grad_(True)
+    out = ops.EmbedBag.apply(t, torch.from_numpy(ids.astype(np.int32)).cuda(), torch.from_numpy(splits).cuda(), D,
+                             "mean", 0.5)
+    assert np.allclose(out.detach().cpu().numpy(), R.embedding_bag(table, ids, splits, "mean"), rtol=1e-6, atol=1e-7)
+    g = rng.standard_normal((B, D)).astype(np.float32)
+    out.backward(torch.from_numpy(g).cuda())
+    assert t.grad is None                                           # fused: the table itself moved
+    want = table - 0.5 * R.embedding_bag_grad(rows, ids, splits, g, "mean", np.float64)
+    assert np.allclose(t.detach().cpu().numpy(), want, rtol=1e-5, atol=1e-6)
+    z = ops.EmbedBag.apply(t.detach(), torch.zeros(0, dtype=torch.int64, device="cuda"),
+                           torch.zeros(1, dtype=torch.int64, device="cuda"), D, "mean", None)
+    assert tuple(z.shape) == (0, D)
+
+
+@pytest.mark.parametrize("D,layout", [(16, "fused"), (16, "split"), (32, "split")])
+def test_mixed_collection_forward_backward_vs_oracle(D, layout):
+    """DeepFM-style collection where slot 1 is multi-valued (the MovieLens "Genres" shape): the stack row of that
+    slot is the mean of the bag, its first-order term the SUM of the bag's weights (multi-hot indicator)."""
+    from deep_recommenders_b200.embedding import EmbeddingCollection
+    rows, B = [13, 9, 21], 130
+    S = len(rows)
+    rng = np.random.default_rng(D)
+    tables = [rng.standard_normal((r, D)).astype(np.float32) / 4 for r in rows]
+    lins = [rng.standard_normal((r,)).astype(np.float32) / 4 for r in rows]
+    ids = np.stack([rng.integers(-1, r, size=B) for r in rows], axis=1).astype(np.int64)
+    bag_ids, bag_splits = make_bags(B, rows[1], seed=9)
+    coll = EmbeddingCollection(rows, D, device="cuda", init="empty", layout=layout)
+    with torch.no_grad():
+        coll.emb_view().copy_(torch.from_numpy(np.concatenate(tables, 0)))
+        coll.lin_view().copy_(torch.from_numpy(np.concatenate(lins, 0)))
+        coll.bias.fill_(0.25)
+    bags = {1: (torch.from_numpy(bag_ids).cuda(), torch.from_numpy(bag_splits).cuda())}
+    stack, logit = coll(torch.from_numpy(ids).cuda(), want_logit=True, bags=bags)
+
+    # oracle: the reference's composition (deepfm.py:39-45) with the ragged slot combined TF's way
+    ref_stack = R.stack_embeddings(tables, ids).astype(np.float64)
+    ref_stack[:, 1, :] = R.embedding_bag(tables[1], bag_ids, bag_splits, "mean", np.float64)
+    ids_lin = ids.copy()
+    ids_lin[:, 1] = -1
+    lin = R.linear_term(lins, 0.25, ids_lin, np.float64).reshape(-1)
+    lin = lin + R.embedding_bag(lins[1].reshape(-1, 1), bag_ids, bag_splits, "sum", np.float64).reshape(-1)
+    ref_logit = lin + R.fm_second_order(ref_stack, np.float64).reshape(-1)
+    scale = np.abs(lin) + 0.5 * ((ref_stack.sum(1) ** 2).sum(1) + (ref_stack ** 2).sum((1, 2))) + 1.0
+    assert np.allclose(stack.detach().cpu().numpy(), ref_stack, rtol=1e-6, atol=1e-7)
+    assert (np.abs(logit.detach().cpu().numpy() - ref_logit) <= 1e-5 * scale).all()
+
+    # backward: torch-CPU autograd of the same composition in float64 is the checker
+    g_stack = rng.standard_normal((B, S, D)).astype(np.float32)
+    g_logit = rng.standard_normal((B,)).astype(np.float32)
+    (stack * torch.from_numpy(g_stack).cuda()).sum().add((logit * torch.from_numpy(g_logit).cuda()).sum()).backward()
+    tt = [torch.tensor(t, dtype=torch.float64, requires_grad=True) for t in tables]
+    tl = [torch.tensor(l, dtype=torch.float64, requires_grad=True) for l in lins]
+    cols, lin_t = [], torch.zeros(B, dtype=torch.float64)
+    for s in range(S):
+        if s == 1:
+            e = torch.zeros(B, D, dtype=torch.float64)
+            rowsb, lw = [], []
+            for b in range(B):
+                seg = bag_ids[bag_splits[b]:bag_splits[b + 1]]
+                seg = seg[(seg >= 0) & (seg < rows[1])]
+                if len(seg):
+                    rowsb.append(tt[1][torch.from_numpy(seg)].mean(0))
+                    lw.append(tl[1][torch.from_numpy(seg)].sum())
+                else:
+                    rowsb.append(torch.zeros(D, dtype=torch.float64))
+                    lw.append(torch.zeros((), dtype=torch.float64))
+            e = torch.stack(rowsb)
+            lin_t = lin_t + torch.stack(lw)
+        else:
+            ok = torch.from_numpy((ids[:, s] >= 0) & (ids[:, s] < rows[s]))
+            idx = torch.from_numpy(np.clip(ids[:, s], 0, rows[s] - 1))
+            e = tt[s][idx] * ok[:, None]
+            lin_t = lin_t + tl[s][idx] * ok
+        cols.append(e)
+    st = torch.stack(cols, 1)
+    lg = lin_t + 0.5 * ((st.sum(1) ** 2) - (st ** 2).sum(1)).sum(1)
+    ((st * torch.from_numpy(g_stack).double()).sum() + (lg * torch.from_numpy(g_logit).double()).sum()).backward()
+    gw_t, gl_t, gb_t = coll.grads()
+    gw, gl = gw_t.cpu().numpy(), gl_t.cpu().numpy().reshape(-1)
+    assert abs(float(gb_t) - float(g_logit.astype(np.float64).sum())) <= 1e-4 * (np.abs(g_logit).sum() + 1)
+    ref_gw = np.concatenate([t.grad.numpy() for t in tt], 0)
+    ref_gl = np.concatenate([l.grad.numpy() for l in tl], 0)
+    tol_w = 1e-5 * (np.abs(ref_gw).max() + 1) * 8
+    assert np.abs(gw - ref_gw).max() <= tol_w, np.abs(gw - ref_gw).max()
+    assert np.abs(gl - ref_gl).max() <= 1e-5 * (np.abs(ref_gl).max() + 1) * 8
+
+
+# ---- Adam ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 3, 4, 1000, 4099, 1 << 20])
+def test_adam_step_matches_apply_adam(n):
+    from deep_recommenders_b200 import ops
+    rng = np.random.default_rng(n)
+    p, g = rng.standard_normal(n).astype(np.float32), rng.standard_normal(n).astype(np.float32)
+    m, v = (rng.standard_normal(n) * 0.1).astype(np.float32), (rng.random(n) * 0.1).astype(np.float32)
+    tp, tg, tm, tv = (torch.from_numpy(a.copy()).cuda() for a in (p, g, m, v))
+    pn, mn, vn = p, m, v
+    for t in range(1, 4):
+        lr_t = float(R.adam_lr_t(0.01, t))
+        ops.adam_step_(tp, tg, tm, tv, lr_t, zero_grad=False)
+        pn, mn, vn = R.adam_dense(pn, g, mn, vn, lr_t, dtype=np.float64)
+    assert np.allclose(tm.cpu().numpy(), mn, rtol=1e-5, atol=1e-7)
+    assert np.allclose(tv.cpu().numpy(), vn, rtol=1e-5, atol=1e-9)
+    assert np.allclose(tp.cpu().numpy(), pn, rtol=1e-5, atol=1e-6)
+    ops.adam_step_(tp, tg, tm, tv, 0.01, zero_grad=True)
+    assert float(tg.abs().max()) == 0.0
+
+
+def test_adam_step_unaligned_views_use_the_scalar_path():
+    from deep_recommenders_b200 import ops
+    base = [torch.randn(1030, device="cuda") for _ in range(4)]
+    base[3].abs_()
+    p, g, m, v = (b[1:1026] for b in base)                          # 4-byte aligned only
+    ref = R.adam_dense(p.cpu().numpy(), g.cpu().numpy(), m.cpu().numpy(), v.cpu().numpy(), 0.01, dtype=np.float64)
+    ops.adam_step_(p, g, m, v, 0.01, zero_grad=False)
+    assert np.allclose(base[0][1:1026].cpu().numpy(), ref[0], rtol=1e-5, atol=1e-6)
+    assert np.allclose(base[2][1:1026].cpu().numpy(), ref[1], rtol=1e-5, atol=1e-7)
+
+
+# ---- row top-k ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nq,nc,k", [(1, 1, 1), (7, 5, 5), (33, 100, 10), (64, 1000, 100), (3, 4097, 17)])
+def test_topk_rows_matches_tf_top_k_order(nq, nc, k):
+    from deep_recommenders_b200 import ops
+    rng = np.random.default_rng(nq + nc)
+    s = rng.standard_normal((nq, nc)).astype(np.float32)
+    s[:, ::3] = np.round(s[:, ::3])                                 # plenty of exact ties
+    vals, idx = ops.topk_rows(torch.from_numpy(s).cuda(), k)
+    rv, ri = R.top_k(s, k)
+    assert np.array_equal(idx.cpu().numpy(), ri)
+    assert np.array_equal(vals.cpu().numpy(), rv)
+
+
+def test_topk_rows_rejects_k_larger_than_row():
+    from deep_recommenders_b200 import ops
+    with pytest.raises(ValueError, match="at least k columns"):
+        ops.topk_rows(torch.zeros(2, 3, device="cuda"), 4)
