@@ -53,7 +53,10 @@ _SIGS = {
     "dr_sgd_step": [_p, _p, _i64, _f, _p],
     "dr_bce_logits_fwd_bwd": [_p, _p, _p, _i64, _p, _p, _p, _p],
     # SURVEY 8(f) "next" rows
-    "dr_adam_step": [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _i, _p],
+    "dr_adam_step": [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _i, _p, _p],
+    "dr_adam_advance": [_p, _f, _f, _f, _p, _p],
+    "dr_lazy_adam_rows": [_p, _i, _i64, _i, _i, _p, _p, _p, _p, _p, _p, _i64, _i, _p, _p, _p, _p, _p, _p, _p,
+                          _f, _f, _f, _p],
     "dr_hash_bucket_i64": [_p, _i64, _i64, _p, _p],
     "dr_hash_bucket_bytes": [_p, _p, _i64, _i64, _p, _p],
     "dr_hash_bucket_i64_host": [_p, _i64, _i64, _p],

@@ -380,15 +380,51 @@ COMBINER_CODES = {"sum": 0, "mean": 1, "sqrtn": 2}
 
 
 def adam_step_(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, lr_t: float,
-               beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-7, zero_grad: bool = True) -> None:
-    """In-place dense Adam over a flat fp32 buffer (TensorFlow's ApplyAdam arithmetic; lr_t carries the bias correction)."""
+               beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-7, zero_grad: bool = True,
+               lr_t_dev: torch.Tensor = None) -> None:
+    """In-place dense Adam over a flat fp32 buffer (TensorFlow's ApplyAdam arithmetic; lr_t carries the bias
+    correction, or lr_t_dev -- a 1-element CUDA float kept by `AdamClock` -- overrides it)."""
     lib = _lib.load()
     for name, t in (("p", p), ("g", g), ("m", m), ("v", v)):
         _f32(t, name)
         if not t.is_contiguous() or t.numel() != p.numel():
             raise ValueError(f"adam_step_: {name} must be contiguous with {p.numel()} elements")
     check(lib.dr_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), float(lr_t),
-                           float(beta1), float(beta2), float(eps), int(bool(zero_grad)), _stream()), "dr_adam_step")
+                           float(beta1), float(beta2), float(eps), int(bool(zero_grad)), _ptr(lr_t_dev), _stream()),
+          "dr_adam_step")
+
+
+class AdamClock:
+    """Device-resident step counter t and bias-corrected rate lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t)
+    (Keras optimizer_v2 Adam._prepare_local), advanced by one kernel so a captured train step needs no host scalar."""
+
+    def __init__(self, lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-7, device="cuda"):
+        self.lr, self.beta1, self.beta2, self.eps = float(lr), float(beta1), float(beta2), float(eps)
+        self.step = torch.zeros((1,), dtype=torch.int64, device=device)
+        self.lr_t = torch.zeros((1,), dtype=torch.float32, device=device)
+
+    def advance(self) -> None:
+        lib = _lib.load()
+        check(lib.dr_adam_advance(self.step.data_ptr(), self.lr, self.beta1, self.beta2, self.lr_t.data_ptr(),
+                                  _stream()), "dr_adam_advance")
+
+
+def lazy_adam_rows_(ids: torch.Tensor, rows: torch.Tensor, slot_offsets: torch.Tensor, D: int, row_stride: int,
+                    flags: int, p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor,
+                    stamp: torch.Tensor, clock: AdamClock, lin=None) -> None:
+    """Row-sparse Adam over the rows `ids` [B, S] touch (see dr_lazy_adam_rows).  lin = (p, g, m, v) first-order
+    arrays for the split layout, None when the weight rides in the row."""
+    lib = _lib.load()
+    ids = _ids(ids)
+    B, S = ids.shape
+    if stamp.dtype != torch.int32 or not stamp.is_cuda:
+        raise TypeError("lazy_adam_rows_: stamp must be a CUDA int32 tensor [total rows]")
+    lp = [None] * 4 if lin is None else [_f32(t, "lin").data_ptr() for t in lin]
+    check(lib.dr_lazy_adam_rows(ids.data_ptr(), ids.element_size(), B, S, int(D), rows.data_ptr(),
+                                slot_offsets.data_ptr(), p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(),
+                                int(row_stride), int(flags), lp[0], lp[1], lp[2], lp[3], stamp.data_ptr(),
+                                clock.step.data_ptr(), clock.lr_t.data_ptr(), clock.beta1, clock.beta2, clock.eps,
+                                _stream()), "dr_lazy_adam_rows")
 
 
 def hash_bucket_i64(values: torch.Tensor, num_buckets: int) -> torch.Tensor:

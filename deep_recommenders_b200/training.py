@@ -9,9 +9,16 @@ model (reference: examples/train_deepfm_on_movielens_keras.py:38-54 -- compile(B
              -> dr_sgd_step on the flat dense-parameter buffer
 
 with every buffer preallocated, so the step is capturable in a CUDA graph (no allocator calls,
-no host sync).  The optimizer is plain SGD: row-sparse for the tables (only the rows a batch
-touches are read-modify-written), dense for the tower.  (The reference examples use Adam; a
-fused sparse Adam is the first "next" item of SURVEY.md section 8f.)
+no host sync).  Optimizers (`optimizer=`):
+  "sgd"       (default, the benchmarked step) row-sparse SGD fused into the embedding backward (only the rows
+              a batch touches are read-modify-written), dense SGD on the tower;
+  "adam"      what the reference examples train with (tf.keras.optimizers.Adam, eps 1e-7): TensorFlow applies
+              Adam DENSELY to embedding variables too, so this is dr_adam_step over the whole table arena
+              (gradient arena + m + v: 4x the table memory, 7 arena sweeps per step) -- parity-exact, slow;
+  "lazy_adam" row-sparse Adam (dr_lazy_adam_rows: tfa LazyAdam semantics, a stated deviation) on the tables,
+              dense Adam on the tower.
+The Adam step counter and bias-corrected rate live on the device (dr_adam_advance), so all three replay as one
+CUDA graph.
 
 `train_step_host` is the end-to-end entry: ids / labels arrive in (pinned) HOST memory, are
 copied H2D on a side stream one batch ahead (double buffered), and the loss is read back D2H.
@@ -27,8 +34,12 @@ from ._lib import check
 
 
 class DeepFMTrainStep:
-    def __init__(self, model, batch_size: int, lr: float = 0.01, id_dtype=torch.int64, use_graph: bool = True):
+    def __init__(self, model, batch_size: int, lr: float = 0.01, id_dtype=torch.int64, use_graph: bool = True,
+                 optimizer: str = "sgd", beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-7):
         self.lib = _lib.load()
+        if optimizer not in ("sgd", "adam", "lazy_adam"):
+            raise ValueError(f"optimizer must be 'sgd', 'adam' or 'lazy_adam', got {optimizer!r}")
+        self.optimizer = optimizer
         self.model = model
         coll = model.embeddings
         self.coll = coll
@@ -90,6 +101,17 @@ class DeepFMTrainStep:
         self.loss = torch.zeros((1,), **f)
         self.prob = torch.empty((B,), **f)
         self.tp, self.lp, self.rows = coll.pointers(coll.weight, coll.linear)
+        if optimizer != "sgd":
+            # optimizer state: gradient arena (all-zero between steps), m, v in the tables' own layout
+            self.clock = ops.AdamClock(lr, beta1, beta2, eps, device=dev)
+            z = lambda t: None if t is None else torch.zeros_like(t)
+            self.g_arena, self.m_arena, self.v_arena = z(coll.weight.data), z(coll.weight.data), z(coll.weight.data)
+            self.g_lin, self.m_lin, self.v_lin = z(coll.linear), z(coll.linear), z(coll.linear)
+            self.g_bias, self.m_bias, self.v_bias = (torch.zeros((1,), **f) for _ in range(3))
+            self.m_flat, self.v_flat = torch.zeros_like(self.flat), torch.zeros_like(self.flat)
+            self.gtp, self.glp, _ = coll.pointers(self.g_arena, self.g_lin, cache=False)
+            self.stamp = (torch.zeros((coll.total_rows,), device=dev, dtype=torch.int32)
+                          if optimizer == "lazy_adam" else None)
         kmax = max([S * D] + [l.units for l in layers])
         _lib.ensure_gemm_workspace(B, kmax, kmax, dev)
         # plane cache: x, every activation, every upstream gradient and every kernel, hi + lo
@@ -112,6 +134,8 @@ class DeepFMTrainStep:
         c = self.coll
         mark = mark or (lambda label: None)
         check(lib.dr_gemm_plane_cache(1), "dr_gemm_plane_cache")   # one split per tensor per step
+        if self.optimizer != "sgd":
+            self.clock.advance()                                  # t += 1, lr_t (device scalars)
         mark("start")
         check(lib.dr_embed_fm_fwd(self.tp.data_ptr(), self.lp.data_ptr(), self.rows.data_ptr(), self.ids.data_ptr(),
                                   self.ids.element_size(), c.bias.data_ptr(), B, S, D, c.row_stride, c.lin_stride,
@@ -147,17 +171,58 @@ class DeepFMTrainStep:
         main = torch.cuda.current_stream()
         side = self._side_stream
         side.wait_stream(main)
+        adam = self.optimizer != "sgd"
         with torch.cuda.stream(side):
-            check(lib.dr_embed_fm_bwd(self.ids.data_ptr(), self.ids.element_size(), self.rows.data_ptr(),
-                                      self.stack.data_ptr(), self.sum_e.data_ptr(), gz.data_ptr(),
-                                      self.g_stack.data_ptr(), B, S, D, c.row_stride, c.lin_stride, c.flags,
-                                      self.tp.data_ptr(), self.lp.data_ptr(), c.bias.data_ptr(), -self.lr,
-                                      side.cuda_stream), "dr_embed_fm_bwd")
+            sst = side.cuda_stream
+            if not adam:     # fused row-sparse SGD: the backward updates the parameter arena in place
+                check(lib.dr_embed_fm_bwd(self.ids.data_ptr(), self.ids.element_size(), self.rows.data_ptr(),
+                                          self.stack.data_ptr(), self.sum_e.data_ptr(), gz.data_ptr(),
+                                          self.g_stack.data_ptr(), B, S, D, c.row_stride, c.lin_stride, c.flags,
+                                          self.tp.data_ptr(), self.lp.data_ptr(), c.bias.data_ptr(), -self.lr,
+                                          sst), "dr_embed_fm_bwd")
+            else:            # Adam is not linear in g: accumulate the row gradients first (scale = 1), then update
+                ck = self.clock
+                check(lib.dr_embed_fm_bwd(self.ids.data_ptr(), self.ids.element_size(), self.rows.data_ptr(),
+                                          self.stack.data_ptr(), self.sum_e.data_ptr(), gz.data_ptr(),
+                                          self.g_stack.data_ptr(), B, S, D, c.row_stride, c.lin_stride, c.flags,
+                                          self.gtp.data_ptr(), self.glp.data_ptr(), self.g_bias.data_ptr(), 1.0,
+                                          sst), "dr_embed_fm_bwd")
+                lt = ck.lr_t.data_ptr()
+                if self.optimizer == "adam":
+                    w = c.weight.data
+                    check(lib.dr_adam_step(w.data_ptr(), self.g_arena.data_ptr(), self.m_arena.data_ptr(),
+                                           self.v_arena.data_ptr(), w.numel(), 0.0, ck.beta1, ck.beta2, ck.eps, 1, lt,
+                                           sst), "dr_adam_step(tables)")
+                    if c.linear is not None:
+                        check(lib.dr_adam_step(c.linear.data_ptr(), self.g_lin.data_ptr(), self.m_lin.data_ptr(),
+                                               self.v_lin.data_ptr(), c.linear.numel(), 0.0, ck.beta1, ck.beta2,
+                                               ck.eps, 1, lt, sst), "dr_adam_step(first order)")
+                else:
+                    has_lin = c.linear is not None
+                    check(lib.dr_lazy_adam_rows(self.ids.data_ptr(), self.ids.element_size(), B, S, D,
+                                                self.rows.data_ptr(), c._offsets.data_ptr(), c.weight.data_ptr(),
+                                                self.g_arena.data_ptr(), self.m_arena.data_ptr(),
+                                                self.v_arena.data_ptr(), c.row_stride, c.flags,
+                                                c.linear.data_ptr() if has_lin else None,
+                                                self.g_lin.data_ptr() if has_lin else None,
+                                                self.m_lin.data_ptr() if has_lin else None,
+                                                self.v_lin.data_ptr() if has_lin else None, self.stamp.data_ptr(),
+                                                ck.step.data_ptr(), lt, ck.beta1, ck.beta2, ck.eps, sst),
+                          "dr_lazy_adam_rows")
+                check(lib.dr_adam_step(c.bias.data_ptr(), self.g_bias.data_ptr(), self.m_bias.data_ptr(),
+                                       self.v_bias.data_ptr(), 1, 0.0, ck.beta1, ck.beta2, ck.eps, 1, lt, sst),
+                      "dr_adam_step(bias)")
         check(lib.dr_dense_bwd(self.stack.data_ptr(), self.w[0].data_ptr(), None, gz0.data_ptr(), B, S * D, l.units, 0,
                                None, None, self.gw[0].data_ptr(), None, st), "dr_dense_bwd(dw)")
         main.wait_stream(side)
         mark("dense_bwd_0_dw+embed_fm_bwd")
-        check(lib.dr_sgd_step(self.flat.data_ptr(), self.gflat.data_ptr(), self.flat.numel(), self.lr, st), "dr_sgd_step")
+        if not adam:
+            check(lib.dr_sgd_step(self.flat.data_ptr(), self.gflat.data_ptr(), self.flat.numel(), self.lr, st), "dr_sgd_step")
+        else:
+            ck = self.clock
+            check(lib.dr_adam_step(self.flat.data_ptr(), self.gflat.data_ptr(), self.m_flat.data_ptr(),
+                                   self.v_flat.data_ptr(), self.flat.numel(), 0.0, ck.beta1, ck.beta2, ck.eps, 0,
+                                   ck.lr_t.data_ptr(), st), "dr_adam_step(tower)")
         check(lib.dr_gemm_plane_cache(0), "dr_gemm_plane_cache")
         mark("sgd")
 

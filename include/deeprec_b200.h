@@ -251,8 +251,29 @@ int dr_bce_logits_fwd_bwd(const float* z, const float* z_add, const float* y, in
  * with lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t) computed by the caller (t = 1, 2, ...).
  * g holds the accumulated gradient (dr_embed_fm_bwd / dr_scatter_add with scale = 1, or a dense gradient);
  * zero_grad = 1 clears it in the same pass.  eps = 1e-7 (tf.keras) or 1e-8 (tf.train.AdamOptimizer).   */
+/* lr_t_dev (nullable): device float that overrides lr_t -- the bias-corrected rate dr_adam_advance maintains, so
+ * a captured CUDA graph needs no per-step scalar.                                                          */
 int dr_adam_step(float* p, float* g, float* m, float* v, int64_t n, float lr_t, float beta1, float beta2,
-                 float eps, int zero_grad, void* stream);
+                 float eps, int zero_grad, const float* lr_t_dev, void* stream);
+
+/* Step counter on the device (Keras optimizer_v2 Adam._prepare_local): *step_dev += 1 and
+ * *lr_t_dev = lr * sqrt(1 - beta2^t) / (1 - beta1^t) with t the incremented step (first call: t = 1).         */
+int dr_adam_advance(int64_t* step_dev, float lr, float beta1, float beta2, float* lr_t_dev, void* stream);
+
+/* Row-sparse ("lazy") Adam over the rows one batch touched: NOT tf.keras.optimizers.Adam (which decays m, v of
+ * every row every step = dr_adam_step over the arena) but tfa.optimizers.LazyAdam -- an opt-in deviation for
+ * tables where the dense pass (7 arena sweeps) would dominate the step.
+ * Arenas p, g, m, v share one layout: row (slot_offsets[s] + id) * row_stride floats, D embedding floats first and,
+ * with DR_EMBED_LIN_IN_ROW, the first-order weight at float D.  g must hold the batch's row gradients already summed
+ * over duplicate ids (dr_embed_fm_bwd with scale = 1 into g) and zeros elsewhere; on return the touched rows of g
+ * are zero again.  stamp: int32 [total rows], zero-initialised by the caller once; a row is updated exactly once
+ * per step no matter how many lookups hit it.  lin_p/g/m/v (nullable together): split-layout first-order arrays
+ * [total rows].  step_dev / lr_t_dev: maintained by dr_adam_advance.                                          */
+int dr_lazy_adam_rows(const void* ids, int id_bytes, int64_t B, int S, int D, const int64_t* rows,
+                      const int64_t* slot_offsets, float* p, float* g, float* m, float* v, int64_t row_stride,
+                      int flags, float* lin_p, float* lin_g, float* lin_m, float* lin_v, int32_t* stamp,
+                      const int64_t* step_dev, const float* lr_t_dev, float beta1, float beta2, float eps,
+                      void* stream);
 
 /* ---- 8(f) #2  id pipeline: raw feature value -> int64 row id, bit-exact with TensorFlow's columns.
  * categorical_column_with_hash_bucket = FarmHash Fingerprint64(bytes of str(value)) mod num_buckets

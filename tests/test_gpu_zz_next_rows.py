@@ -238,3 +238,144 @@ def test_topk_rows_rejects_k_larger_than_row():
     from deep_recommenders_b200 import ops
     with pytest.raises(ValueError, match="at least k columns"):
         ops.topk_rows(torch.zeros(2, 3, device="cuda"), 4)
+
+
+# ---- Adam inside the train step ------------------------------------------------------------------
+def _cpu_deepfm_grads(tables, lins, bias, ws, bs, ids, labels):
+    """float64 torch-CPU autograd of the reference composition (deepfm.py:36-47 + BCE mean): dense gradients."""
+    tt = [torch.tensor(t, dtype=torch.float64, requires_grad=True) for t in tables]
+    tl = [torch.tensor(l, dtype=torch.float64, requires_grad=True) for l in lins]
+    tb = torch.tensor([bias], dtype=torch.float64, requires_grad=True)
+    tw = [torch.tensor(w, dtype=torch.float64, requires_grad=True) for w in ws]
+    tbi = [torch.tensor(b, dtype=torch.float64, requires_grad=True) for b in bs]
+    B = ids.shape[0]
+    cols, lin = [], tb.expand(B)
+    for s, t in enumerate(tt):
+        ok = torch.from_numpy((ids[:, s] >= 0) & (ids[:, s] < t.shape[0]))
+        idx = torch.from_numpy(np.clip(ids[:, s], 0, t.shape[0] - 1))
+        cols.append(t[idx] * ok[:, None])
+        lin = lin + tl[s][idx] * ok
+    st = torch.stack(cols, 1)
+    fm = 0.5 * ((st.sum(1) ** 2) - (st ** 2).sum(1)).sum(1)
+    h = st.reshape(B, -1)
+    for i, (w, b) in enumerate(zip(tw, tbi)):
+        h = h @ w + b
+        if i < len(tw) - 1:
+            h = torch.relu(h)
+    z = lin + fm + h[:, 0]
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(z, torch.from_numpy(labels).double())
+    loss.backward()
+    g = lambda xs: [x.grad.numpy() for x in xs]
+    return float(loss), g(tt), g(tl), tb.grad.numpy(), g(tw), g(tbi)
+
+
+@pytest.mark.parametrize("optimizer", ["adam", "lazy_adam"])
+@pytest.mark.parametrize("D", [16, 32])                   # fused 128-B rows / split layout
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_train_step_adam_matches_apply_adam_oracle(optimizer, D, use_graph):
+    from deep_recommenders_b200 import feature_column as fc
+    from deep_recommenders_b200.keras.models.ranking import DeepFM
+    from deep_recommenders_b200.training import DeepFMTrainStep
+    rows, B, lr = [50, 7, 30], 96, 0.01
+    S = len(rows)
+    cols = [fc.categorical_column_with_identity(f"c{i}", r) for i, r in enumerate(rows)]
+    model = DeepFM([fc.indicator_column(c) for c in cols], [fc.embedding_column(c, D) for c in cols],
+                   dnn_units_size=[16, 8], seed=5, device="cuda")
+    coll = model.embeddings
+    with torch.no_grad():
+        coll.lin_view().normal_(0, 0.1)
+    tr = DeepFMTrainStep(model, batch_size=B, lr=lr, use_graph=use_graph, optimizer=optimizer)
+    snap = [p.detach().clone() for p in (coll.weight, tr.flat, coll.bias)] + ([coll.linear.detach().clone()] if coll.linear is not None else [])
+    if use_graph:
+        tr.capture()                  # the warm-up replay is a real step on the zero batch: restore the start state
+        with torch.no_grad():
+            coll.weight.copy_(snap[0]); tr.flat.copy_(snap[1]); coll.bias.copy_(snap[2])
+            if coll.linear is not None:
+                coll.linear.copy_(snap[3])
+            for t in (tr.m_arena, tr.v_arena, tr.g_arena, tr.m_flat, tr.v_flat, tr.m_bias, tr.v_bias, tr.g_bias,
+                      tr.m_lin, tr.v_lin, tr.g_lin, tr.stamp, tr.clock.step):
+                if t is not None:
+                    t.zero_()
+    tables = [coll.table(s).detach().cpu().numpy().astype(np.float64) for s in range(S)]
+    lins = [coll.linear_of(s).detach().cpu().numpy().astype(np.float64) for s in range(S)]
+    bias = float(coll.bias)
+    ws = [w.detach().cpu().numpy().astype(np.float64) for w in tr.w]
+    bs = [b.detach().cpu().numpy().astype(np.float64) for b in tr.b]
+    state = lambda xs: ([np.zeros_like(x) for x in xs], [np.zeros_like(x) for x in xs])
+    (mt, vt), (ml, vl), (mw, vw), (mb, vb) = state(tables), state(lins), state(ws), state(bs)
+    mbias = vbias = np.zeros(1)
+    rng = np.random.default_rng(11)
+    for t in range(1, 4):
+        ids = np.stack([rng.integers(-1, r + 1, size=B) for r in rows], axis=1).astype(np.int64)
+        ids[: B // 3] = ids[0]                                    # heavy duplicates
+        labels = rng.integers(0, 2, size=B).astype(np.float32)
+        loss_gpu = float(tr.step(torch.from_numpy(ids).cuda(), torch.from_numpy(labels).cuda()).item())
+        loss, gt, gl, gb, gw, gbi = _cpu_deepfm_grads(tables, lins, bias, ws, bs, ids, labels)
+        assert abs(loss_gpu - loss) <= (1e-5 if t == 1 else 2e-4) * abs(loss) + 1e-6
+        lr_t = R.adam_lr_t(lr, t)
+        for s in range(S):
+            if optimizer == "adam":
+                tables[s], mt[s], vt[s] = R.adam_dense(tables[s], gt[s], mt[s], vt[s], lr_t, dtype=np.float64)
+                lins[s], ml[s], vl[s] = R.adam_dense(lins[s], gl[s], ml[s], vl[s], lr_t, dtype=np.float64)
+            else:
+                tables[s], mt[s], vt[s] = R.adam_rows_lazy(tables[s], gt[s], mt[s], vt[s], ids[:, s], lr_t, dtype=np.float64)
+                lins[s], ml[s], vl[s] = R.adam_rows_lazy(lins[s], gl[s], ml[s], vl[s], ids[:, s], lr_t, dtype=np.float64)
+        b_, mbias, vbias = R.adam_dense(np.array([bias]), gb, mbias, vbias, lr_t, dtype=np.float64)
+        bias = float(b_[0])
+        for i in range(len(ws)):
+            ws[i], mw[i], vw[i] = R.adam_dense(ws[i], gw[i], mw[i], vw[i], lr_t, dtype=np.float64)
+            bs[i], mb[i], vb[i] = R.adam_dense(bs[i], gbi[i], mb[i], vb[i], lr_t, dtype=np.float64)
+    torch.cuda.synchronize()
+    assert int(tr.clock.step) == 3
+    assert abs(float(tr.clock.lr_t) - R.adam_lr_t(lr, 3)) <= 1e-6 * lr
+    # first moments are linear in the gradients: tight; parameters: Adam divides by sqrt(v) + eps, loose
+    RS = coll.row_stride
+    m_emb = tr.m_arena.view(-1, RS)[:, :D].cpu().numpy()
+    ref_m = np.concatenate(mt, 0)
+    assert np.abs(m_emb - ref_m).max() <= 1e-4 * np.abs(ref_m).max() + 1e-9
+    got_tables = np.concatenate([coll.table(s).detach().cpu().numpy() for s in range(S)], 0)
+    got_lins = np.concatenate([coll.linear_of(s).detach().cpu().numpy() for s in range(S)], 0)
+    assert np.abs(got_tables - np.concatenate(tables, 0)).max() <= 3e-2 * lr
+    assert np.abs(got_lins - np.concatenate(lins, 0)).max() <= 3e-2 * lr
+    assert abs(float(coll.bias) - bias) <= 3e-2 * lr
+    for i in range(len(ws)):
+        assert np.abs(tr.w[i].cpu().numpy() - ws[i]).max() <= 3e-2 * lr
+        assert np.abs(tr.b[i].cpu().numpy() - bs[i]).max() <= 3e-2 * lr
+    # the gradient arena is all-zero again after every step (both variants clear what they consumed)
+    assert float(tr.g_arena.abs().max()) == 0.0 and float(tr.g_bias.abs().max()) == 0.0
+    # and the parameters really moved by about lr per step where a gradient flowed
+    assert np.abs(got_tables - snap[0].view(-1, RS)[:, :D].cpu().numpy()).max() > 0.5 * lr
+
+
+def test_lazy_adam_rows_updates_each_touched_row_exactly_once():
+    """Standalone dr_lazy_adam_rows: a gradient arena with known rows, ids with many duplicates and OOV entries."""
+    from deep_recommenders_b200 import ops
+    rows, D, RS, B = [40, 9], 16, 32, 257
+    total = sum(rows)
+    rng = np.random.default_rng(3)
+    p = rng.standard_normal((total, RS)).astype(np.float32)
+    m = (rng.standard_normal((total, RS)) * 0.01).astype(np.float32)
+    v = (rng.random((total, RS)) * 0.01).astype(np.float32)
+    ids = np.stack([rng.integers(-2, r + 2, size=B) for r in rows], axis=1).astype(np.int64)
+    ids[:100, 0] = 3
+    offs = np.array([0, rows[0]], dtype=np.int64)
+    touched = np.unique(np.concatenate([offs[s] + ids[:, s][(ids[:, s] >= 0) & (ids[:, s] < rows[s])] for s in range(2)]))
+    g = np.zeros((total, RS), dtype=np.float32)
+    g[touched, :D + 1] = rng.standard_normal((touched.size, D + 1)).astype(np.float32)
+    tp, tg, tm, tv = (torch.from_numpy(a.copy()).cuda() for a in (p, g, m, v))
+    stamp = torch.zeros(total, dtype=torch.int32, device="cuda")
+    clock = ops.AdamClock(0.01, device="cuda")
+    clock.advance()
+    ops.lazy_adam_rows_(torch.from_numpy(ids).cuda(), torch.tensor(rows, device="cuda"), torch.from_numpy(offs).cuda(),
+                        D, RS, 1, tp, tg, tm, tv, stamp, clock)
+    torch.cuda.synchronize()
+    lr_t = R.adam_lr_t(0.01, 1)
+    rp, rm, rv = R.adam_rows_lazy(p[:, :D + 1], g[:, :D + 1], m[:, :D + 1], v[:, :D + 1], touched, lr_t, dtype=np.float64)
+    assert np.allclose(tp.cpu().numpy()[:, :D + 1], rp, rtol=1e-5, atol=1e-6)
+    assert np.allclose(tm.cpu().numpy()[:, :D + 1], rm, rtol=1e-5, atol=1e-8)
+    assert np.allclose(tv.cpu().numpy()[:, :D + 1], rv, rtol=1e-5, atol=1e-9)
+    assert np.array_equal(tp.cpu().numpy()[:, D + 1:], p[:, D + 1:])          # padding untouched
+    untouched = np.setdiff1d(np.arange(total), touched)
+    assert np.array_equal(tp.cpu().numpy()[untouched], p[untouched])
+    assert float(tg.abs().max()) == 0.0
+    assert np.array_equal(stamp.cpu().numpy() == 1, np.isin(np.arange(total), touched))
