@@ -66,6 +66,10 @@ _SIGS = {
     "dr_embed_bag_fwd": [_p, _i64, _i64, _p, _i, _p, _i64, _i, _i, _p, _i64, _p],
     "dr_embed_bag_bwd": [_p, _i, _p, _i64, _i, _i, _p, _i64, _i64, _i64, _p, _f, _p],
     "dr_topk_rows": [_p, _i64, _i64, _i64, _i, _p, _p, _p],
+    "dr_take_long_axis": [_p, _i, _i64, _i64, _i64, _p, _i, _p, _p],
+    "dr_exclude_adjust": [_p, _p, _p, _i64, _i64, _i64, _f, _p, _p],
+    "dr_rowwise_dot": [_p, _p, _i64, _i, _p, _p],
+    "dr_column_rank": [_p, _p, _i64, _i64, _i64, _p, _p],
 }
 _RESTYPES = {"dr_last_error": C.c_char_p, "dr_launch_count": C.c_uint64, "dr_fingerprint64_host": C.c_uint64}
 

@@ -646,3 +646,77 @@ def topk_rows(scores_: torch.Tensor, k: int):
     idx = torch.empty((nq, k), device=s.device, dtype=torch.int32)
     check(lib.dr_topk_rows(s.data_ptr(), nq, nc, nc, k, vals.data_ptr(), idx.data_ptr(), _stream()), "dr_topk_rows")
     return vals, idx
+
+
+def _idx32(indices: torch.Tensor) -> torch.Tensor:
+    if not indices.is_cuda:
+        raise _lib.DeepRecError("indices must be a CUDA tensor (no CPU fallback)")
+    if indices.dtype not in (torch.int32, torch.int64):
+        raise TypeError(f"indices: expected int32 / int64, got {indices.dtype}")
+    return indices.to(torch.int32).contiguous()
+
+
+def take_long_axis(arr: torch.Tensor, indices: torch.Tensor) -> torch.Tensor:
+    """out[i, j] = arr[i, indices[i, j]] (factorized_top_k.py:26-41) for any 4- or 8-byte dtype; a 1-D `arr` is one
+    shared row: tf.gather(identifiers, indices)."""
+    lib = _lib.load()
+    if not arr.is_cuda:
+        raise _lib.DeepRecError("take_long_axis: arr must be a CUDA tensor (no CPU fallback)")
+    if arr.element_size() not in (4, 8):
+        raise TypeError(f"take_long_axis: 4- or 8-byte elements only, got {arr.dtype}")
+    idx = _idx32(indices)
+    if idx.dim() != 2:
+        raise ValueError(f"take_long_axis: indices must be 2-D, got shape {tuple(idx.shape)}")
+    arr = arr.contiguous()
+    nq, k = idx.shape
+    if arr.dim() == 1:
+        ncols, ld = arr.shape[0], 0
+    elif arr.dim() == 2 and arr.shape[0] == nq:
+        ncols, ld = arr.shape[1], arr.shape[1]
+    else:
+        raise ValueError(f"take_long_axis: arr {tuple(arr.shape)} does not match indices {tuple(idx.shape)}")
+    out = torch.empty((nq, k), device=arr.device, dtype=arr.dtype)
+    if nq and k:
+        check(lib.dr_take_long_axis(arr.data_ptr(), arr.element_size(), nq, ncols, ld, idx.data_ptr(), k, out.data_ptr(),
+                                    _stream()), "dr_take_long_axis")
+    return out
+
+
+def exclude_adjust(scores_: torch.Tensor, identifiers: torch.Tensor, exclude: torch.Tensor,
+                   penalty: float = 1.0e5) -> torch.Tensor:
+    """scores - isin(identifiers, exclude) * 1e5 (factorized_top_k.py:58-62), integer identifiers."""
+    lib = _lib.load()
+    s = _f32(scores_, "scores")
+    ident = _ids(identifiers, "identifiers").to(torch.int64).contiguous()
+    ex = _ids(exclude, "exclude").to(torch.int64).contiguous()
+    if s.dim() != 2 or ident.shape != s.shape or ex.dim() != 2 or ex.shape[0] != s.shape[0]:
+        raise ValueError(f"exclude_adjust: scores {tuple(s.shape)}, identifiers {tuple(ident.shape)}, "
+                         f"exclude {tuple(ex.shape)} do not line up")
+    out = torch.empty_like(s)
+    check(lib.dr_exclude_adjust(s.data_ptr(), ident.data_ptr(), ex.data_ptr(), s.shape[0], s.shape[1], ex.shape[1],
+                                float(penalty), out.data_ptr(), _stream()), "dr_exclude_adjust")
+    return out
+
+
+def rowwise_dot(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """[n, 1] = reduce_sum(a * b, axis=1, keepdims=True)."""
+    lib = _lib.load()
+    a, b = _f32(a, "a"), _f32(b, "b")
+    if a.shape != b.shape or a.dim() != 2:
+        raise ValueError(f"rowwise_dot: shapes {tuple(a.shape)} vs {tuple(b.shape)}")
+    out = torch.empty((a.shape[0], 1), device=a.device, dtype=torch.float32)
+    check(lib.dr_rowwise_dot(a.data_ptr(), b.data_ptr(), a.shape[0], a.shape[1], out.data_ptr(), _stream()),
+          "dr_rowwise_dot")
+    return out
+
+
+def column_rank(positive: torch.Tensor, others: torch.Tensor) -> torch.Tensor:
+    """rank[i] = number of entries of others[i, :] strictly above positive[i] (int32)."""
+    lib = _lib.load()
+    p, o = _f32(positive, "positive").reshape(-1), _f32(others, "others")
+    if o.dim() != 2 or o.shape[0] != p.shape[0]:
+        raise ValueError(f"column_rank: positive {tuple(p.shape)} vs others {tuple(o.shape)}")
+    rank = torch.empty((p.shape[0],), device=p.device, dtype=torch.int32)
+    check(lib.dr_column_rank(p.data_ptr(), o.data_ptr(), p.shape[0], o.shape[1], o.shape[1], rank.data_ptr(), _stream()),
+          "dr_column_rank")
+    return rank

@@ -318,6 +318,23 @@ int dr_embed_bag_bwd(const void* ids, int id_bytes, const int64_t* row_splits, i
 int dr_topk_rows(const float* scores, int64_t nq, int64_t nc, int64_t ld, int k, float* out_vals,
                  int32_t* out_idx, void* stream);
 
+/* Companions of the selection (keras/models/retrieval/factorized_top_k.py):
+ *   dr_take_long_axis   _take_long_axis :26-41: out[i,j] = arr[i, indices[i,j]] for 4- or 8-byte elements (scores,
+ *                       int32/int64 identifiers); ld = row pitch in elements, ld == 0 = ONE shared row, i.e.
+ *                       tf.gather(identifiers, indices) (:211,:334).  An index outside [0, ncols) gives 0.
+ *   dr_exclude_adjust   _exclude :58-62: adjusted[i,j] = scores[i,j] - [identifiers[i,j] in exclude[i,:]] * penalty
+ *                       (penalty = 1.0e5 in the reference); the caller then takes dr_topk_rows of `adjusted`.
+ *   dr_rowwise_dot      FactorizedTopK.update_state :487-488: out[i] = sum_d a[i,d] * b[i,d].
+ *   dr_column_rank      TopKCategoricalAccuracy over [positive | others] with the true class in column 0:
+ *                       rank[i] = #{j : others[i,j] > positive[i]}; in_top_k(k) == rank < k.                    */
+int dr_take_long_axis(const void* arr, int elem_bytes, int64_t nq, int64_t ncols, int64_t ld, const int32_t* indices,
+                      int k, void* out, void* stream);
+int dr_exclude_adjust(const float* scores, const int64_t* identifiers, const int64_t* exclude, int64_t nq, int64_t n,
+                      int64_t e, float penalty, float* adjusted, void* stream);
+int dr_rowwise_dot(const float* a, const float* b, int64_t n, int D, float* out, void* stream);
+int dr_column_rank(const float* positive, const float* others, int64_t nq, int64_t n, int64_t ld, int32_t* rank,
+                   void* stream);
+
 /* Scratch for the tensor-core GEMM variant (hi/lo TF32 operand planes).  The caller owns the
  * buffer and keeps it alive until it registers another one (ptr = NULL unregisters).  One
  * workspace per process: GEMM entry points that use it must not run concurrently on two

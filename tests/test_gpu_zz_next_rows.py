@@ -379,3 +379,123 @@ def test_lazy_adam_rows_updates_each_touched_row_exactly_once():
     assert np.array_equal(tp.cpu().numpy()[untouched], p[untouched])
     assert float(tg.abs().max()) == 0.0
     assert np.array_equal(stamp.cpu().numpy() == 1, np.isin(np.arange(total), touched))
+
+
+# ---- top-k retrieval and the FactorizedTopK metric ------------------------------------------------
+@pytest.fixture
+def topk_variant():
+    from deep_recommenders_b200 import _lib
+    yield lambda v: _lib.tune("topk_variant", v)
+    _lib.tune("topk_variant", 0)
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("nq,nc,k", [(5, 40, 1), (9, 33, 33), (17, 2000, 50), (3, 70000, 128), (2, 5000, 1000)])
+def test_topk_variants_agree_with_oracle(topk_variant, variant, nq, nc, k):
+    from deep_recommenders_b200 import ops
+    if variant == 1 and k * nc > 10 ** 7:
+        pytest.skip("k-pass variant: quadratic, covered at smaller sizes")
+    topk_variant(variant)
+    rng = np.random.default_rng(nc + k)
+    s = rng.standard_normal((nq, nc)).astype(np.float32)
+    s[:, ::2] = np.round(s[:, ::2] * 2) / 2                        # exact ties across the row
+    s[0, :] = np.sort(s[0, :])                                      # ascending: every column is an insertion
+    s[-1, :] = 1.0                                                  # one value: index order decides
+    vals, idx = ops.topk_rows(torch.from_numpy(s).cuda(), k)
+    rv, ri = R.top_k(s, k)
+    assert np.array_equal(idx.cpu().numpy(), ri)
+    assert np.array_equal(vals.cpu().numpy(), rv)
+
+
+def test_take_long_axis_kat():                                     # reference tests/keras/test_factorized_top_k.py:17-23
+    from deep_recommenders.keras.models.retrieval import factorized_top_k
+    arr = torch.tensor([[0.1, 0.2, 0.3], [0.4, 0.5, 0.6]], device="cuda")
+    indices = torch.tensor([[0, 1], [2, 1]], device="cuda")
+    out = factorized_top_k._take_long_axis(arr, indices)
+    assert torch.equal(out.cpu(), torch.tensor([[0.1, 0.2], [0.6, 0.5]]))
+
+
+def test_exclude_kat():                                            # reference tests/keras/test_factorized_top_k.py:25-34
+    from deep_recommenders.keras.models.retrieval import factorized_top_k
+    scores = torch.tensor([[0.1, 0.2, 0.3], [0.4, 0.5, 0.6]], device="cuda")
+    identifiers = torch.tensor([[0, 1, 2], [3, 4, 5]], device="cuda")
+    exclude = torch.tensor([[1, 2], [3, 5]], device="cuda")
+    x, y = factorized_top_k._exclude(scores, identifiers, exclude, 1)
+    assert torch.equal(x.cpu(), torch.tensor([[0.1], [0.5]])) and y.cpu().tolist() == [[0], [4]]
+
+
+@pytest.mark.parametrize("layer", ["streaming", "brute_force", "brute_force_blocked", None])
+def test_factorized_topk_metrics(layer, monkeypatch):              # reference tests/keras/test_factorized_top_k.py:86-130
+    from deep_recommenders.keras.models.retrieval import FactorizedTopK, factorized_top_k
+    rng = np.random.RandomState(42)
+    num_candidates, num_queries, dim = 100, 10, 4
+    candidates = rng.normal(size=(num_candidates, dim)).astype(np.float32)
+    queries = rng.normal(size=(num_queries, dim)).astype(np.float32)
+    true_candidates = rng.normal(size=(num_queries, dim)).astype(np.float32)
+    positive = (queries * true_candidates).sum(axis=1, keepdims=True)
+    all_scores = np.concatenate([positive, queries @ candidates.T], axis=1)
+    ks = [1, 5, 10, 50]
+    batches = [torch.from_numpy(candidates[i:i + 32]).cuda() for i in range(0, num_candidates, 32)]   # .batch(32)
+    if layer == "streaming":
+        cand = factorized_top_k.Streaming().index(batches)
+    elif layer == "brute_force":
+        cand = factorized_top_k.BruteForce().index(batches)
+    elif layer == "brute_force_blocked":
+        monkeypatch.setattr(factorized_top_k, "_SCORE_BLOCK_BYTES", 4 * num_queries * 55)   # blocks of 55 candidates
+        cand = factorized_top_k.BruteForce().index(torch.from_numpy(candidates).cuda())
+    else:
+        cand = batches                                              # a raw dataset -> Streaming(k) inside the metric
+    metric = FactorizedTopK(candidates=cand,
+                            metrics=[factorized_top_k.TopKCategoricalAccuracy(k=x, name=f"top_{x}_categorical_accuracy")
+                                     for x in ks], k=max(ks))
+    metric.update_state(query_embeddings=torch.from_numpy(queries).cuda(),
+                        true_candidate_embeddings=torch.from_numpy(true_candidates).cuda())
+    for k, value in zip(ks, metric.result()):
+        in_top_k = ((all_scores > all_scores[:, :1]).sum(axis=1) < k)
+        assert value == pytest.approx(in_top_k.mean())
+
+
+@pytest.mark.parametrize("ident_dtype", [None, torch.int32, torch.int64, torch.float32, torch.float64])
+def test_streaming_and_brute_force_retrieve_the_oracles_candidates(ident_dtype):
+    from deep_recommenders.keras.models.retrieval import factorized_top_k
+    rng = np.random.default_rng(5)
+    nc, nq, dim, k = 1000, 37, 8, 10
+    cands = rng.standard_normal((nc, dim)).astype(np.float32)
+    q = rng.standard_normal((nq, dim)).astype(np.float32)
+    names = None if ident_dtype is None else (torch.arange(nc) * 3 + 7).to(ident_dtype)
+    ref_names = np.arange(nc) if names is None else names.numpy()
+    rs, ri = R.brute_force_topk(q, cands, ref_names, k, np.float64)
+    batches = [torch.from_numpy(cands[i:i + 96]).cuda() for i in range(0, nc, 96)]         # last batch has 40 rows
+    ident_batches = None if names is None else [names[i:i + 96] for i in range(0, nc, 96)]
+    tq = torch.from_numpy(q).cuda()
+    for index in (factorized_top_k.Streaming(k=k).index(batches, ident_batches),
+                  factorized_top_k.BruteForce(k=k).index(torch.from_numpy(cands).cuda(), names)):
+        s, i = index(tq)
+        assert np.array_equal(i.cpu().numpy(), ri)
+        assert np.allclose(s.cpu().numpy(), rs, rtol=1e-5, atol=1e-5)
+        s2, i2 = index(tq, k=3)
+        assert np.array_equal(i2.cpu().numpy(), ri[:, :3])
+
+
+def test_query_with_exclusions_and_error_paths():
+    from deep_recommenders.keras.models.retrieval import factorized_top_k
+    rng = np.random.default_rng(6)
+    cands = rng.standard_normal((200, 8)).astype(np.float32)
+    q = rng.standard_normal((11, 8)).astype(np.float32)
+    bf = factorized_top_k.BruteForce(k=5).index(torch.from_numpy(cands).cuda())
+    s, i = bf(torch.from_numpy(q).cuda())
+    excl = i[:, [0, 2]].to(torch.int64).contiguous()                 # ban the 1st and 3rd hit of every query
+    s2, i2 = bf.query_with_exclusions(torch.from_numpy(q).cuda(), excl, k=5)
+    full_s, full_i = R.brute_force_topk(q, cands, None, 7, np.float64)
+    xs, xi = R.exclude(full_s.astype(np.float32), full_i, excl.cpu().numpy(), 7)
+    assert np.array_equal(i2.cpu().numpy(), xi)
+    assert not np.isin(i2.cpu().numpy()[:, :5], excl.cpu().numpy()).any()
+    with pytest.raises(ValueError, match="index"):
+        factorized_top_k.BruteForce()(torch.from_numpy(q).cuda())
+    with pytest.raises(ValueError, match="ndim should be 2"):
+        factorized_top_k.BruteForce().index(torch.zeros(4, device="cuda"))
+    small = [torch.from_numpy(cands[:4]).cuda()]
+    with pytest.raises(ValueError, match="candidate batch too small"):
+        factorized_top_k.Streaming(k=10, handle_incomplete_batches=False).index(small)(torch.from_numpy(q).cuda())
+    with pytest.raises(NotImplementedError):
+        factorized_top_k.Faiss(k=10)
