@@ -65,13 +65,19 @@ _SIGS = {
     "dr_vocab_lookup_i64": [_p, _i64, _p, _p, _i64, _i64, _p, _p],
     "dr_embed_bag_fwd": [_p, _i64, _i64, _p, _i, _p, _i64, _i, _i, _p, _i64, _p],
     "dr_embed_bag_bwd": [_p, _i, _p, _i64, _i, _i, _p, _i64, _i64, _i64, _p, _f, _p],
+    "dr_crc32c_host": [_p, _i64],
+    "dr_masked_crc32c_host": [_p, _i64],
+    "dr_tfrecord_index": [_p, _i64, _i, _p, _p, _i64],
+    "dr_example_parse_feature": [_p, _p, _p, _i64, C.c_char_p, _i, _p, _p, _p, _p, _p, _p],
+    "dr_vocab_lookup_bytes_host": [_p, _p, _i64, _p, _p, _i64, _i64, _p],
     "dr_topk_rows": [_p, _i64, _i64, _i64, _i, _p, _p, _p],
     "dr_take_long_axis": [_p, _i, _i64, _i64, _i64, _p, _i, _p, _p],
     "dr_exclude_adjust": [_p, _p, _p, _i64, _i64, _i64, _f, _p, _p],
     "dr_rowwise_dot": [_p, _p, _i64, _i, _p, _p],
     "dr_column_rank": [_p, _p, _i64, _i64, _i64, _p, _p],
 }
-_RESTYPES = {"dr_last_error": C.c_char_p, "dr_launch_count": C.c_uint64, "dr_fingerprint64_host": C.c_uint64}
+_RESTYPES = {"dr_last_error": C.c_char_p, "dr_launch_count": C.c_uint64, "dr_fingerprint64_host": C.c_uint64,
+             "dr_crc32c_host": C.c_uint32, "dr_masked_crc32c_host": C.c_uint32, "dr_tfrecord_index": C.c_int64}
 
 
 class DeepRecError(RuntimeError):

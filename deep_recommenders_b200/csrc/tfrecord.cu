@@ -1,0 +1,294 @@
+// SURVEY.md 8(f) #4 -- the input format in front of the id pipeline: `movielens.tfrecords`, a TFRecord file of
+// serialized tf.train.Example protos (writer schema datasets/movielens.py:54-62, reader :116-125:
+// FixedLenFeature int64 / string per column, VarLenFeature string for "Genres").  In the reference both the record
+// framing and the proto parse are TensorFlow's C++ (tf.data.TFRecordDataset, tf.io.parse_example); here they are
+// host entry points of the same C-ABI library, so a batch goes  file bytes -> columnar (values | packed strings +
+// offsets | row_splits) -> dr_hash_bucket_bytes_host / dr_vocab_lookup_* -> int64 ids  without a Python loop.
+// Host-only code (no kernels): the formats are byte-exact public formats, restated from their specifications:
+//   TFRecord framing   uint64 length | uint32 masked_crc32c(length) | data | uint32 masked_crc32c(data), little endian,
+//                      mask(c) = rotr(c, 15) + 0xa282ead8
+//   CRC-32C            Castagnoli polynomial 0x1EDC6F41 (reflected 0x82F63B78), RFC 3720 appendix B.4 test vectors
+//   Example            protobuf wire format: Example{1: Features{1: map<string, Feature>}},
+//                      Feature{1: BytesList | 2: FloatList | 3: Int64List}, lists{1: repeated value}, scalars packed
+//                      or unpacked.
+#include <string.h>
+#include <string>
+#include <string_view>
+#include <unordered_map>
+#include "common.cuh"
+
+namespace dr {
+namespace tfr {
+
+static uint32_t g_crc_table[8][256];
+static bool g_crc_ready = false;
+
+static void crc_init() {
+  if (g_crc_ready) return;
+  for (uint32_t i = 0; i < 256; ++i) {
+    uint32_t c = i;
+    for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+    g_crc_table[0][i] = c;
+  }
+  for (uint32_t i = 0; i < 256; ++i)
+    for (int t = 1; t < 8; ++t) g_crc_table[t][i] = (g_crc_table[t - 1][i] >> 8) ^ g_crc_table[0][g_crc_table[t - 1][i] & 0xff];
+  g_crc_ready = true;
+}
+
+static uint32_t crc32c(const uint8_t* p, size_t n) {
+  crc_init();
+  uint32_t c = 0xffffffffu;
+  while (n >= 8) {   // slicing-by-8
+    uint64_t w;
+    memcpy(&w, p, 8);
+    w ^= c;
+    c = g_crc_table[7][w & 0xff] ^ g_crc_table[6][(w >> 8) & 0xff] ^ g_crc_table[5][(w >> 16) & 0xff] ^
+        g_crc_table[4][(w >> 24) & 0xff] ^ g_crc_table[3][(w >> 32) & 0xff] ^ g_crc_table[2][(w >> 40) & 0xff] ^
+        g_crc_table[1][(w >> 48) & 0xff] ^ g_crc_table[0][(w >> 56) & 0xff];
+    p += 8;
+    n -= 8;
+  }
+  while (n--) c = (c >> 8) ^ g_crc_table[0][(c ^ *p++) & 0xff];
+  return c ^ 0xffffffffu;
+}
+
+static inline uint32_t mask_crc(uint32_t c) { return ((c >> 15) | (c << 17)) + 0xa282ead8u; }
+
+// ---- protobuf wire helpers ------------------------------------------------------------------------------------
+struct Cursor {
+  const uint8_t* p;
+  const uint8_t* end;
+  bool ok = true;
+  bool more() const { return ok && p < end; }
+  uint64_t varint() {
+    uint64_t v = 0;
+    for (int shift = 0; shift < 64; shift += 7) {
+      if (p >= end) { ok = false; return 0; }
+      const uint8_t b = *p++;
+      v |= (uint64_t)(b & 0x7f) << shift;
+      if (!(b & 0x80)) return v;
+    }
+    ok = false;
+    return 0;
+  }
+  Cursor sub() {   // length-delimited payload
+    const uint64_t n = varint();
+    if (!ok || n > (uint64_t)(end - p)) { ok = false; return Cursor{p, p, false}; }
+    Cursor c{p, p + n, true};
+    p += n;
+    return c;
+  }
+  void skip(int wire) {
+    switch (wire) {
+      case 0: varint(); break;
+      case 1: if (end - p < 8) ok = false; else p += 8; break;
+      case 2: sub(); break;
+      case 5: if (end - p < 4) ok = false; else p += 4; break;
+      default: ok = false;
+    }
+  }
+};
+
+// Finds Feature `name` inside one serialized Example; returns its payload cursor (ok == false: malformed; empty
+// range with found == false: the feature is absent).
+static Cursor find_feature(const uint8_t* rec, int64_t len, const char* name, size_t name_len, bool* found) {
+  *found = false;
+  Cursor ex{rec, rec + len, true};
+  Cursor result{rec, rec, true};
+  while (ex.more()) {
+    const uint64_t tag = ex.varint();
+    if (!ex.ok) break;
+    if ((tag >> 3) == 1 && (tag & 7) == 2) {          // Example.features
+      Cursor feats = ex.sub();
+      while (feats.more()) {
+        const uint64_t t2 = feats.varint();
+        if (!feats.ok) break;
+        if ((t2 >> 3) == 1 && (t2 & 7) == 2) {        // Features.feature map entry
+          Cursor entry = feats.sub();
+          bool key_match = false;
+          Cursor value{entry.p, entry.p, true};
+          bool has_value = false;
+          while (entry.more()) {
+            const uint64_t t3 = entry.varint();
+            if (!entry.ok) break;
+            if ((t3 >> 3) == 1 && (t3 & 7) == 2) {
+              Cursor key = entry.sub();
+              key_match = key.ok && (size_t)(key.end - key.p) == name_len && memcmp(key.p, name, name_len) == 0;
+            } else if ((t3 >> 3) == 2 && (t3 & 7) == 2) {
+              value = entry.sub();
+              has_value = true;
+            } else {
+              entry.skip((int)(t3 & 7));
+            }
+          }
+          if (!entry.ok) { result.ok = false; return result; }
+          if (key_match) {       // later duplicates of a map key win (protobuf map semantics)
+            *found = true;
+            result = has_value ? value : Cursor{entry.end, entry.end, true};
+          }
+        } else {
+          feats.skip((int)(t2 & 7));
+        }
+      }
+      if (!feats.ok) { result.ok = false; return result; }
+    } else {
+      ex.skip((int)(tag & 7));
+    }
+  }
+  if (!ex.ok) result.ok = false;
+  return result;
+}
+
+enum { KIND_INT64 = 0, KIND_BYTES = 1, KIND_FLOAT = 2 };
+
+// Walks the values of one Feature payload.  on_scalar(bits) for int64 / float, on_bytes(ptr, len) for bytes.
+// Returns false on malformed input or a kind mismatch (a feature stored as another list type).
+template <typename FS, typename FB>
+static bool walk_values(Cursor feat, int kind, FS on_scalar, FB on_bytes) {
+  const uint64_t want_field = kind == KIND_BYTES ? 1 : (kind == KIND_FLOAT ? 2 : 3);
+  while (feat.more()) {
+    const uint64_t tag = feat.varint();
+    if (!feat.ok) return false;
+    if ((tag & 7) != 2) { feat.skip((int)(tag & 7)); continue; }
+    Cursor list = feat.sub();
+    if (!feat.ok) return false;
+    if ((tag >> 3) != want_field) {
+      if ((tag >> 3) >= 1 && (tag >> 3) <= 3 && list.p != list.end) return false;   // another, non-empty list kind
+      continue;
+    }
+    while (list.more()) {
+      const uint64_t t = list.varint();
+      if (!list.ok || (t >> 3) != 1) return false;
+      const int wire = (int)(t & 7);
+      if (kind == KIND_BYTES) {
+        if (wire != 2) return false;
+        Cursor b = list.sub();
+        if (!list.ok) return false;
+        on_bytes(b.p, (int64_t)(b.end - b.p));
+      } else if (kind == KIND_INT64) {
+        if (wire == 2) {          // packed
+          Cursor pk = list.sub();
+          if (!list.ok) return false;
+          while (pk.more()) { const uint64_t v = pk.varint(); if (!pk.ok) return false; on_scalar(v); }
+        } else if (wire == 0) {
+          const uint64_t v = list.varint();
+          if (!list.ok) return false;
+          on_scalar(v);
+        } else return false;
+      } else {
+        if (wire == 2) {
+          Cursor pk = list.sub();
+          if (!list.ok || ((pk.end - pk.p) & 3)) return false;
+          for (; pk.p < pk.end; pk.p += 4) { uint32_t v; memcpy(&v, pk.p, 4); on_scalar((uint64_t)v); }
+        } else if (wire == 5) {
+          if (list.end - list.p < 4) return false;
+          uint32_t v; memcpy(&v, list.p, 4); list.p += 4;
+          on_scalar((uint64_t)v);
+        } else return false;
+      }
+    }
+    if (!list.ok) return false;
+  }
+  return feat.ok;
+}
+
+}  // namespace tfr
+}  // namespace dr
+
+using namespace dr;
+
+extern "C" uint32_t dr_crc32c_host(const uint8_t* data, int64_t n) { return tfr::crc32c(data, n < 0 ? 0 : (size_t)n); }
+extern "C" uint32_t dr_masked_crc32c_host(const uint8_t* data, int64_t n) {
+  return tfr::mask_crc(tfr::crc32c(data, n < 0 ? 0 : (size_t)n));
+}
+
+extern "C" int64_t dr_tfrecord_index(const uint8_t* buf, int64_t nbytes, int verify_crc, int64_t* rec_off,
+                                     int64_t* rec_len, int64_t cap) {
+  DR_REQUIRE(nbytes >= 0 && (buf || nbytes == 0), DR_EINVAL, "dr_tfrecord_index: null buffer");
+  int64_t pos = 0, n = 0;
+  while (pos < nbytes) {
+    DR_REQUIRE(nbytes - pos >= 12, DR_EINVAL, "dr_tfrecord_index: truncated record header at byte %lld", (long long)pos);
+    uint64_t len;
+    uint32_t crc;
+    memcpy(&len, buf + pos, 8);
+    memcpy(&crc, buf + pos + 8, 4);
+    if (verify_crc)
+      DR_REQUIRE(tfr::mask_crc(tfr::crc32c(buf + pos, 8)) == crc, DR_EINVAL,
+                 "dr_tfrecord_index: corrupted record length at byte %lld (crc mismatch)", (long long)pos);
+    DR_REQUIRE(len <= (uint64_t)(nbytes - pos - 12) && (uint64_t)(nbytes - pos - 12) - len >= 4, DR_EINVAL,
+               "dr_tfrecord_index: truncated record %lld (length %llu)", (long long)n, (unsigned long long)len);
+    if (verify_crc) {
+      memcpy(&crc, buf + pos + 12 + len, 4);
+      DR_REQUIRE(tfr::mask_crc(tfr::crc32c(buf + pos + 12, (size_t)len)) == crc, DR_EINVAL,
+                 "dr_tfrecord_index: corrupted record %lld at byte %lld (crc mismatch)", (long long)n, (long long)pos);
+    }
+    if (rec_off && n < cap) rec_off[n] = pos + 12;
+    if (rec_len && n < cap) rec_len[n] = (int64_t)len;
+    ++n;
+    pos += 12 + (int64_t)len + 4;
+  }
+  return n;
+}
+
+// One feature of `n` serialized Examples -> columnar.  Call once with values == bytes == NULL to size the outputs
+// (row_splits, *total_values, *total_bytes are filled), then again with buffers of at least that size.
+extern "C" int dr_example_parse_feature(const uint8_t* buf, const int64_t* rec_off, const int64_t* rec_len, int64_t n,
+                                        const char* name, int kind, int64_t* row_splits, void* values,
+                                        uint8_t* bytes, int64_t* value_offsets, int64_t* total_values,
+                                        int64_t* total_bytes) {
+  DR_REQUIRE(n >= 0 && name && (n == 0 || (buf && rec_off && rec_len)), DR_EINVAL, "dr_example_parse_feature: null pointer");
+  DR_REQUIRE(kind >= 0 && kind <= 2, DR_EINVAL, "dr_example_parse_feature: kind=%d (0 int64, 1 bytes, 2 float)", kind);
+  const size_t name_len = strlen(name);
+  int64_t nv = 0, nb = 0;
+  if (row_splits) row_splits[0] = 0;
+  if (value_offsets) value_offsets[0] = 0;
+  for (int64_t r = 0; r < n; ++r) {
+    bool found = false;
+    tfr::Cursor feat = tfr::find_feature(buf + rec_off[r], rec_len[r], name, name_len, &found);
+    DR_REQUIRE(feat.ok, DR_EINVAL, "dr_example_parse_feature: record %lld is not a valid tf.train.Example", (long long)r);
+    if (found) {
+      const bool ok = tfr::walk_values(
+          feat, kind,
+          [&](uint64_t bits) {
+            if (values) {
+              if (kind == tfr::KIND_INT64) reinterpret_cast<int64_t*>(values)[nv] = (int64_t)bits;
+              else { const uint32_t b32 = (uint32_t)bits; memcpy(reinterpret_cast<float*>(values) + nv, &b32, 4); }
+            }
+            ++nv;
+          },
+          [&](const uint8_t* p, int64_t len) {
+            if (bytes) memcpy(bytes + nb, p, (size_t)len);
+            nb += len;
+            ++nv;
+            if (value_offsets) value_offsets[nv] = nb;
+          });
+      DR_REQUIRE(ok, DR_EINVAL, "dr_example_parse_feature: feature '%s' of record %lld is malformed or not of the requested kind",
+                 name, (long long)r);
+    }
+    if (row_splits) row_splits[r + 1] = nv;
+  }
+  if (total_values) *total_values = nv;
+  if (total_bytes) *total_bytes = nb;
+  return DR_OK;
+}
+
+// categorical_column_with_vocabulary_list on string keys: position in the list, out-of-vocabulary -> default_id.
+extern "C" int dr_vocab_lookup_bytes_host(const uint8_t* bytes, const int64_t* offsets, int64_t n,
+                                          const uint8_t* vocab_bytes, const int64_t* vocab_offsets, int64_t vocab_size,
+                                          int64_t default_id, int64_t* out_ids) {
+  DR_REQUIRE(n >= 0 && vocab_size >= 0, DR_EINVAL, "dr_vocab_lookup_bytes_host: n=%lld vocab_size=%lld", (long long)n,
+             (long long)vocab_size);
+  if (n == 0) return DR_OK;
+  DR_REQUIRE(offsets && out_ids && (vocab_offsets || vocab_size == 0), DR_EINVAL, "dr_vocab_lookup_bytes_host: null pointer");
+  std::unordered_map<std::string_view, int64_t> table;
+  table.reserve((size_t)vocab_size * 2);
+  for (int64_t i = 0; i < vocab_size; ++i)   // first occurrence wins (TF rejects duplicate vocabulary entries)
+    table.emplace(std::string_view(reinterpret_cast<const char*>(vocab_bytes) + vocab_offsets[i],
+                                   (size_t)(vocab_offsets[i + 1] - vocab_offsets[i])), i);
+  for (int64_t i = 0; i < n; ++i) {
+    DR_REQUIRE(offsets[i + 1] >= offsets[i], DR_EINVAL, "dr_vocab_lookup_bytes_host: offsets not monotone at %lld", (long long)i);
+    auto it = table.find(std::string_view(reinterpret_cast<const char*>(bytes) + offsets[i], (size_t)(offsets[i + 1] - offsets[i])));
+    out_ids[i] = it == table.end() ? default_id : it->second;
+  }
+  return DR_OK;
+}

@@ -31,6 +31,21 @@ class RaggedFeature:
         return len(self.row_splits) - 1
 
 
+@dataclass
+class PackedStrings:
+    """n byte strings as ONE uint8 buffer + int64 offsets [n+1] (numpy, host): what the native TFRecord parser emits
+    for a string feature and what the C-ABI hash / vocabulary entries consume -- no per-value Python objects."""
+    data: object
+    offsets: object
+
+    def __len__(self) -> int:
+        return len(self.offsets) - 1
+
+    def tolist(self):
+        d, o = bytes(memoryview(self.data)), self.offsets
+        return [d[int(o[i]):int(o[i + 1])] for i in range(len(self))]
+
+
 @dataclass(frozen=True)
 class CategoricalColumn:
     key: str

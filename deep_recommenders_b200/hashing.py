@@ -23,7 +23,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .feature_column import CategoricalColumn, RaggedFeature
+from .feature_column import CategoricalColumn, PackedStrings, RaggedFeature
 
 
 def _to_bytes(v) -> bytes:
@@ -47,6 +47,9 @@ def fingerprint64(s: bytes) -> int:
 
 def pack_strings(values: Iterable):
     """python values -> (uint8 buffer, int64 offsets [n+1]) in the layout the C-ABI hash entries take."""
+    if isinstance(values, PackedStrings):
+        data = np.ascontiguousarray(values.data, dtype=np.uint8)
+        return (data if data.size else np.zeros(1, dtype=np.uint8)), np.ascontiguousarray(values.offsets, dtype=np.int64)
     parts = [_to_bytes(v) for v in values]
     offsets = np.zeros(len(parts) + 1, dtype=np.int64)
     if parts:
@@ -75,8 +78,14 @@ def hash_bucket(values: Iterable, num_buckets: int) -> np.ndarray:
 def vocabulary_ids(col: CategoricalColumn, values: Sequence) -> np.ndarray:
     """categorical_column_with_vocabulary_list on host values: index in the list, OOV -> -1."""
     if col.dtype == "string":
-        table = {_to_bytes(k): i for i, k in enumerate(col.vocabulary_list)}
-        return np.asarray([table.get(_to_bytes(v), -1) for v in values], dtype=np.int64)
+        lib = _lib.load()
+        data, offsets = pack_strings(values)
+        vdata, voffsets = pack_strings(col.vocabulary_list)
+        out = np.empty(offsets.size - 1, dtype=np.int64)
+        _lib.check(lib.dr_vocab_lookup_bytes_host(data.ctypes.data, offsets.ctypes.data, out.size, vdata.ctypes.data,
+                                                  voffsets.ctypes.data, voffsets.size - 1, -1, out.ctypes.data),
+                   "dr_vocab_lookup_bytes_host")
+        return out
     table = {int(k): i for i, k in enumerate(col.vocabulary_list)}
     return np.asarray([table.get(int(v), -1) for v in values], dtype=np.int64)
 
@@ -111,6 +120,14 @@ def flat_ids(col: CategoricalColumn, values, device) -> torch.Tensor:
             keys, index = _vocab_device_tables(col, v.device)
             return ops.vocab_lookup_i64(v, keys, index, -1)
         raise TypeError(f"column {col.key!r} has a string vocabulary but received an integer tensor")
+    if isinstance(values, PackedStrings):
+        if col.kind == "hash":
+            ids = hash_bucket(values, col.num_buckets)
+        elif col.kind == "vocab" and col.dtype == "string":
+            ids = vocabulary_ids(col, values)
+        else:
+            raise TypeError(f"column {col.key!r} ({col.kind}, dtype {col.dtype}) received packed strings")
+        return torch.from_numpy(ids).to(device)
     arr = values.detach().cpu().numpy() if isinstance(values, torch.Tensor) else np.asarray(values)
     arr = arr.reshape(-1)
     if col.kind == "hash":
@@ -125,6 +142,8 @@ def flat_ids(col: CategoricalColumn, values, device) -> torch.Tensor:
 
 def column_ids(col: CategoricalColumn, value, device) -> torch.Tensor:
     """Single-valued categorical column -> int64 ids [B] on `device` (accepts [B] or [B, 1])."""
+    if isinstance(value, PackedStrings):
+        return flat_ids(col, value, device)
     shape = tuple(value.shape) if hasattr(value, "shape") else np.asarray(value).shape
     if len(shape) == 2 and shape[1] == 1:
         shape = shape[:1]

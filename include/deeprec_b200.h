@@ -311,6 +311,30 @@ int dr_embed_bag_bwd(const void* ids, int id_bytes, const int64_t* row_splits, i
                      const float* g_out, int64_t g_stride, int64_t rows, int64_t row_stride, float* grad_table,
                      float scale, void* stream);
 
+/* ---- 8(f) #4  input format: TFRecord file of serialized tf.train.Example (datasets/movielens.py:54-62 writer
+ * schema, :116-125 tf.io.parse_example reader).  HOST entry points (no GPU needed), the native replacement of
+ * tf.data.TFRecordDataset + tf.io.parse_example for this path; their outputs are exactly what the id pipeline above
+ * consumes (packed strings + offsets, int64 values, row_splits for VarLenFeature).
+ *   dr_crc32c_host / dr_masked_crc32c_host   CRC-32C (Castagnoli) and TFRecord's masked form rotr(c,15)+0xa282ead8.
+ *   dr_tfrecord_index   scans `buf`: returns the number of records (or a negative DR_E*), fills rec_off / rec_len
+ *                       (payload position and length) for the first `cap` records; verify_crc checks both CRCs.
+ *   dr_example_parse_feature   feature `name` of n records -> columnar.  kind 0 = int64_list (values int64),
+ *                       1 = bytes_list (bytes + value_offsets [total_values+1]), 2 = float_list (values float).
+ *                       row_splits [n+1]: values of record r are [row_splits[r], row_splits[r+1]) -- a
+ *                       FixedLenFeature([]) has exactly one, a VarLenFeature any number, an absent feature none.
+ *                       Two-pass: with values == bytes == NULL only row_splits / *total_values / *total_bytes are
+ *                       written, then the caller allocates and calls again.
+ *   dr_vocab_lookup_bytes_host   categorical_column_with_vocabulary_list on strings (position, OOV -> default_id). */
+uint32_t dr_crc32c_host(const uint8_t* data, int64_t n);
+uint32_t dr_masked_crc32c_host(const uint8_t* data, int64_t n);
+int64_t dr_tfrecord_index(const uint8_t* buf, int64_t nbytes, int verify_crc, int64_t* rec_off, int64_t* rec_len,
+                          int64_t cap);
+int dr_example_parse_feature(const uint8_t* buf, const int64_t* rec_off, const int64_t* rec_len, int64_t n,
+                             const char* name, int kind, int64_t* row_splits, void* values, uint8_t* bytes,
+                             int64_t* value_offsets, int64_t* total_values, int64_t* total_bytes);
+int dr_vocab_lookup_bytes_host(const uint8_t* bytes, const int64_t* offsets, int64_t n, const uint8_t* vocab_bytes,
+                               const int64_t* vocab_offsets, int64_t vocab_size, int64_t default_id, int64_t* out_ids);
+
 /* ---- 8(f) #3  row-wise top-k (factorized_top_k.py:58-62,196-226,330-334 tf.math.top_k):
  * out_vals [nq,k] descending, out_idx [nq,k] int32 column indices, ties -> lower index first.
  * scores is [nq, nc] with row pitch ld floats.  k > nc is rejected like TF ("input must have at least k

@@ -499,3 +499,66 @@ def test_query_with_exclusions_and_error_paths():
         factorized_top_k.Streaming(k=10, handle_incomplete_batches=False).index(small)(torch.from_numpy(q).cuda())
     with pytest.raises(NotImplementedError):
         factorized_top_k.Faiss(k=10)
+
+
+# ---- the real input path: TFRecord file -> dataset classes -> columns -> FM (BASELINE config C1) ------
+def test_c1_tfrecord_pipeline_matches_oracle(tmp_path):
+    import importlib.util
+    import pathlib
+    spec = importlib.util.spec_from_file_location(
+        "c1_tfrecords_example", pathlib.Path(__file__).resolve().parent.parent / "examples" / "train_fm_on_movielens_tfrecords.py")
+    ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ex)
+    from deep_recommenders.datasets.movielens import MovielensRanking, serialize_tfrecords
+    from deep_recommenders.estimator.models.feature_interaction import FM
+    d = ex.write_synthetic_ml1m(str(tmp_path / "ml-1m"), n_users=80, n_movies=60, n_ratings=700, seed=3)
+    rec = str(tmp_path / "movielens.tfrecords")
+    serialize_tfrecords(rec, datadir=d, seed=0)
+    ml = MovielensRanking(epochs=2, batch_size=256, filename=rec)
+    for fix in (False, True):           # the reference's always-OOV genre slot, and the genre vocabulary proper
+        ind, emb = ex.build_columns(ml, fix_genre_vocab=fix)
+        model = FM(ind, emb, seed=1, device="cuda")
+        coll = model.collection
+        with torch.no_grad():
+            coll.lin_view().normal_(0, 0.1)
+            coll.bias.fill_(-0.2)
+        feats, labels = next(iter(ml.input_fn()))
+        logits = model(feats)
+        assert logits.shape == (256, 1) and labels.shape == (256, 1)
+        # oracle ids from the raw strings with the Python FarmHash restatement and list.index
+        uid, mid = feats["user_id"].tolist(), feats["movie_id"].tolist()
+        gender = [s.decode() for s in feats["user_gender"].tolist()]
+        ids = np.stack([
+            np.asarray(F.hash_bucket_py(uid, ml.num_users)),
+            np.asarray([ml.gender_vocab.index(g) for g in gender]),
+            np.asarray([ml.age_vocab.index(int(a)) for a in feats["user_age"]]),
+            np.asarray([ml.occupation_vocab.index(int(o)) for o in feats["user_occupation"]]),
+            np.asarray(F.hash_bucket_py(mid, ml.num_movies)),
+            np.full(256, -1),
+        ], axis=1).astype(np.int64)
+        S = 6
+        tables = [coll.table(s).detach().cpu().numpy() for s in range(S)]
+        lins = [coll.linear_of(s).detach().cpu().numpy() for s in range(S)]
+        g = feats["movie_genres"]
+        gvocab = ml.genres_vocab if fix else ml.gender_vocab
+        gid = np.asarray([gvocab.index(s.decode()) if s.decode() in gvocab else -1 for s in g.values.tolist()])
+        stack = R.stack_embeddings(tables, ids).astype(np.float64)
+        stack[:, 5, :] = R.embedding_bag(tables[5], gid, g.row_splits, "mean", np.float64)
+        lin = R.linear_term(lins, float(coll.bias), ids, np.float64).reshape(-1)
+        lin = lin + R.embedding_bag(lins[5].reshape(-1, 1), gid, g.row_splits, "sum", np.float64).reshape(-1)
+        ref = lin + R.fm_second_order(stack, np.float64).reshape(-1)
+        assert np.allclose(logits.detach().cpu().numpy().reshape(-1), ref, rtol=1e-5, atol=2e-5)
+        if not fix:
+            assert float(np.abs(stack[:, 5]).max()) == 0.0
+        else:
+            assert float(np.abs(stack[:, 5]).max()) > 0.0
+        opt = torch.optim.Adam(model.parameters(), lr=0.01)
+        y = torch.from_numpy(labels).cuda()
+        first = None
+        for _ in range(10):
+            loss = torch.nn.functional.binary_cross_entropy_with_logits(model(feats), y)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            first = first if first is not None else float(loss)
+        assert float(loss) < first
