@@ -33,8 +33,8 @@ _SIGS = {
     "dr_debug_gemm": [_p, _p, _p, _i64, _i64, _i64, _i, _i, _p],
     "dr_embed_fm_fwd": [_p, _p, _p, _p, _i, _p, _i64, _i, _i, _i64, _i64, _i, _p, _p, _p, _p],
     "dr_embed_fm_bwd": [_p, _i, _p, _p, _p, _p, _p, _i64, _i, _i, _i64, _i64, _i, _p, _p, _p, _f, _p],
-    "dr_embed_fm_fwd_sharded": [_p, _i, _p, _p, _p, _i, _p, _i64, _i, _i, _i64, _i, _p, _p, _p, _p],
-    "dr_embed_fm_bwd_sharded": [_p, _i, _p, _p, _p, _i, _p, _p, _p, _p, _i64, _i, _i, _i64, _i, _p, _f, _p],
+    "dr_embed_fm_fwd_sharded": [_p, _i, _p, _p, _p, _i, _p, _i64, _i, _i, _i64, _i, _i64, _p, _p, _p, _p],
+    "dr_embed_fm_bwd_sharded": [_p, _i, _p, _p, _p, _i, _p, _p, _p, _p, _i64, _i, _i, _i64, _i, _i64, _p, _f, _p],
     "dr_gather_fwd": [_p, _i64, _p, _i, _i64, _i, _p, _p],
     "dr_scatter_add": [_p, _i64, _p, _i, _i64, _i, _p, _f, _p],
     "dr_fm_fwd": [_p, _i64, _i, _i, _p, _p],

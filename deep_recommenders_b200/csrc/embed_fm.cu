@@ -46,6 +46,7 @@ struct EmbedFwdParams {
   int shard_world;
   const float* const* peer_bases;
   const int64_t* slot_offsets;
+  int64_t shard_lin_off;   // > 0: first-order weights live at peer_bases[g] + shard_lin_off + local_row (wide rows)
   float* out_stack;
   float* out_sum;
   float* out_logit;
@@ -72,6 +73,7 @@ struct EmbedBwdParams {
   int shard_world;
   float* const* peer_bases;
   const int64_t* slot_offsets;
+  int64_t shard_lin_off;
 };
 
 constexpr int kMaxShardWorld = 64;
@@ -187,6 +189,17 @@ __global__ void __launch_bounds__(512) embed_fm_fwd_kernel(const EmbedFwdParams 
         for (int s = c; s < S; s += LPR) {   // the LPR lanes split the S scalar gathers
           const int64_t id = (int64_t)my[s];
           if ((uint64_t)id < (uint64_t)s_rows[s]) lin += __ldg(s_lin[s] + (size_t)id * p.lin_stride);
+        }
+      }
+      if (SHARD && p.shard_lin_off > 0 && ex_ok) {   // wide sharded rows: first-order weights trail the owner's shard
+        for (int s = c; s < S; s += LPR) {
+          const int64_t id = (int64_t)my[s];
+          if ((uint64_t)id < (uint64_t)s_rows[s]) {
+            const int64_t r = s_off[s] + id;
+            const int owner = sw_pow2 ? (int)(r & (SW - 1)) : (int)(r % SW);
+            const int64_t local = sw_pow2 ? (r >> sw_shift) : (r / SW);
+            lin += __ldg(s_peer[owner] + p.shard_lin_off + local);
+          }
         }
       }
       float t = (sum.x * sum.x - sq.x) + (sum.y * sum.y - sq.y) + (sum.z * sum.z - sq.z) +
@@ -429,6 +442,12 @@ __global__ void __launch_bounds__(256) embed_fm_bwd_sp_kernel(const EmbedBwdPara
             red_add_v4(row + c * 4, make_float4(scale * gl, 0.f, 0.f, 0.f));
           }
           if (has_lin && c == 0) red_add_f32(s_lin[s] + (size_t)id[u] * p.lin_stride, scale * gl);
+          if (SHARD && has_fm && p.shard_lin_off > 0 && c == 0) {
+            const int64_t r = s_off[s] + id[u];
+            const int owner = sw_pow2 ? (int)(r & (SW - 1)) : (int)(r % SW);
+            const int64_t local = sw_pow2 ? (r >> sw_shift) : (r / SW);
+            red_add_f32(s_peer[owner] + p.shard_lin_off + local, scale * gl);
+          }
         }
       }
     }
@@ -725,9 +744,12 @@ extern "C" int dr_scatter_add(float* grad_table, int64_t rows, const void* ids, 
 // ---- row-sharded entries: the gather / scatter IS the exchange (NVLink peer memory) -------------------
 extern "C" int dr_embed_fm_fwd_sharded(const float* const* peer_bases, int world, const int64_t* slot_offsets,
                                        const int64_t* rows, const void* ids, int id_bytes, const float* bias,
-                                       int64_t B, int S, int D, int64_t row_stride, int flags, float* out_stack,
-                                       float* out_sum, float* out_logit, void* stream) {
+                                       int64_t B, int S, int D, int64_t row_stride, int flags, int64_t lin_offset,
+                                       float* out_stack, float* out_sum, float* out_logit, void* stream) {
   if (int rc = check_dims("dr_embed_fm_fwd_sharded", B, S, D, id_bytes)) return rc;
+  DR_REQUIRE(lin_offset >= 0 && !((flags & DR_EMBED_LIN_IN_ROW) && lin_offset > 0), DR_EINVAL,
+             "dr_embed_fm_fwd_sharded: lin_offset=%lld (must be >= 0 and exclusive with DR_EMBED_LIN_IN_ROW)",
+             (long long)lin_offset);
   if (B == 0) return DR_OK;
   DR_REQUIRE(peer_bases && slot_offsets && rows && ids, DR_EINVAL, "dr_embed_fm_fwd_sharded: null pointer");
   DR_REQUIRE(world >= 1 && world <= kMaxShardWorld, DR_EINVAL, "dr_embed_fm_fwd_sharded: world=%d outside [1,%d]",
@@ -741,7 +763,7 @@ extern "C" int dr_embed_fm_fwd_sharded(const float* const* peer_bases, int world
   p.rows = rows; p.ids = ids; p.bias = bias; p.B = B; p.S = S; p.D = D;
   p.out_stack = out_stack; p.out_sum = out_sum; p.out_logit = out_logit;
   p.row_stride = row_stride; p.lin_stride = row_stride; p.lin_in_row = lin_in_row;
-  p.shard_world = world; p.peer_bases = peer_bases; p.slot_offsets = slot_offsets;
+  p.shard_world = world; p.peer_bases = peer_bases; p.slot_offsets = slot_offsets; p.shard_lin_off = lin_offset;
   cudaStream_t st = (cudaStream_t)stream;
   DR_DISPATCH_LPR(launch_fwd, p, st);
 }
@@ -749,9 +771,12 @@ extern "C" int dr_embed_fm_fwd_sharded(const float* const* peer_bases, int world
 extern "C" int dr_embed_fm_bwd_sharded(float* const* peer_bases, int world, const int64_t* slot_offsets,
                                        const int64_t* rows, const void* ids, int id_bytes, const float* stack,
                                        const float* sum_e, const float* g_logit, const float* g_stack, int64_t B,
-                                       int S, int D, int64_t row_stride, int flags, float* g_bias, float scale,
-                                       void* stream) {
+                                       int S, int D, int64_t row_stride, int flags, int64_t lin_offset, float* g_bias,
+                                       float scale, void* stream) {
   if (int rc = check_dims("dr_embed_fm_bwd_sharded", B, S, D, id_bytes)) return rc;
+  DR_REQUIRE(lin_offset >= 0 && !((flags & DR_EMBED_LIN_IN_ROW) && lin_offset > 0), DR_EINVAL,
+             "dr_embed_fm_bwd_sharded: lin_offset=%lld (must be >= 0 and exclusive with DR_EMBED_LIN_IN_ROW)",
+             (long long)lin_offset);
   if (B == 0) return DR_OK;
   DR_REQUIRE(peer_bases && slot_offsets && rows && ids, DR_EINVAL, "dr_embed_fm_bwd_sharded: null pointer");
   DR_REQUIRE(world >= 1 && world <= kMaxShardWorld, DR_EINVAL, "dr_embed_fm_bwd_sharded: world=%d outside [1,%d]",
@@ -765,7 +790,7 @@ extern "C" int dr_embed_fm_bwd_sharded(float* const* peer_bases, int world, cons
   p.ids = ids; p.rows = rows; p.stack = stack; p.sum_e = sum_e; p.g_logit = g_logit; p.g_stack = g_stack;
   p.B = B; p.S = S; p.D = D; p.g_bias = g_bias; p.scale = scale;
   p.row_stride = row_stride; p.lin_stride = row_stride; p.lin_in_row = lin_in_row;
-  p.shard_world = world; p.peer_bases = peer_bases; p.slot_offsets = slot_offsets;
+  p.shard_world = world; p.peer_bases = peer_bases; p.slot_offsets = slot_offsets; p.shard_lin_off = lin_offset;
   cudaStream_t st = (cudaStream_t)stream;
   const int saved_mode = g_tune_embed_bwd_mode;
   g_tune_embed_bwd_mode = 0;      // only the slot-parallel kernel implements sharded addressing

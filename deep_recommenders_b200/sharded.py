@@ -38,33 +38,50 @@ class ShardedEmbedding:
 
     def __init__(self, rows: Sequence[int], dim: int, rank: int, world: int, device, seed: Optional[int] = None,
                  exchange: str = "nccl", group=None):
-        if dim + 4 > 128:
-            raise NotImplementedError("sharded fused rows need D + 4 <= 128 in this round")
         self.rows_list = [int(r) for r in rows]
         self.dim, self.rank, self.world = int(dim), rank, world
-        self.vdim = self.dim + 4 if exchange == "nccl" else (self.dim + 4 + 31) // 32 * 32
         self.total_rows = sum(self.rows_list)
         self.local_rows = shard_plan.local_rows(self.total_rows, rank, world)
+        max_rows = shard_plan.local_rows(self.total_rows, 0, world)       # same size on every rank
+        # narrow rows (D <= 28): [emb | w | pad] = ONE 128-B line, the weight rides in the row (flags = LIN_IN_ROW).
+        # wide rows (BASELINE C3-C5, D = 32 ... 128): rows of exactly D floats (whole lines, no padding) and the
+        # first-order weights as a [max_rows] array trailing the shard in the same symmetric allocation.
+        self.lin_in_row = exchange == "nccl" or self.dim + 1 <= 32
+        if exchange == "nccl":
+            if dim + 4 > 128:
+                raise NotImplementedError("exchange='nccl' moves fused rows of D + 4 <= 128 floats; use exchange='p2p' "
+                                          "for wider rows")
+            self.vdim = self.dim + 4
+        else:
+            self.vdim = 32 if self.lin_in_row else self.dim
+        self.flags = 1 if self.lin_in_row else 0
+        self.lin_offset = 0 if self.lin_in_row else max_rows * self.vdim         # floats from the shard base
         self.device = device
         self.handle = None
         self.peer_ptrs = None
         std = 1.0 / self.dim ** 0.5
         if exchange == "p2p":
             import torch.distributed._symmetric_memory as symm_mem
-            max_rows = shard_plan.local_rows(self.total_rows, 0, world)       # same size on every rank
-            buf = symm_mem.empty((max_rows, self.vdim), dtype=torch.float32, device=device)
+            numel = max_rows * self.vdim + (0 if self.lin_in_row else (max_rows + 3) // 4 * 4)
+            buf = symm_mem.empty((numel,), dtype=torch.float32, device=device)
             self.handle = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
             buf.zero_()
-            w = buf[:self.local_rows]
+            w = buf[:max_rows * self.vdim].view(max_rows, self.vdim)[:self.local_rows]
             self._buf = buf
+            self.lin = None if self.lin_in_row else buf[self.lin_offset:self.lin_offset + max_rows][:self.local_rows]
             self.peer_ptrs = torch.tensor([int(p) for p in self.handle.buffer_ptrs], dtype=torch.int64, device=device)
         else:
             w = torch.zeros((self.local_rows, self.vdim), dtype=torch.float32, device=device)
+            self.lin = None
         gen = torch.Generator(device=device).manual_seed((seed or 0) * 1000 + rank)
         torch.nn.init.trunc_normal_(w[:, :self.dim], 0.0, std, -2 * std, 2 * std, generator=gen)
         self.weight = w
         self.slot_offsets = torch.tensor(shard_plan.slot_offsets(self.rows_list), dtype=torch.int64, device=device)
         self.rows = torch.tensor(self.rows_list, dtype=torch.int64, device=device)
+
+    def lin_view(self) -> torch.Tensor:
+        """[local_rows] first-order weights of this rank's shard (a column of the fused rows or the trailing array)."""
+        return self.weight[:, self.dim] if self.lin_in_row else self.lin
 
 
 class ShardedDeepFMTrainStep:
@@ -180,8 +197,9 @@ class ShardedDeepFMTrainStep:
             check(lib.dr_gemm_plane_cache(1), "dr_gemm_plane_cache")
             check(lib.dr_embed_fm_fwd_sharded(self.emb.peer_ptrs.data_ptr(), G, self.emb.slot_offsets.data_ptr(),
                                               self.emb.rows.data_ptr(), self.ids.data_ptr(), 8, self.bias.data_ptr(),
-                                              B, S, D, V, 1, self.stack.data_ptr(), self.sum_e.data_ptr(),
-                                              self.fm_logit.data_ptr(), st()), "dr_embed_fm_fwd_sharded")
+                                              B, S, D, V, self.emb.flags, self.emb.lin_offset, self.stack.data_ptr(),
+                                              self.sum_e.data_ptr(), self.fm_logit.data_ptr(), st()),
+                  "dr_embed_fm_fwd_sharded")
             mark("embed_fm_fwd_p2p")
             x, K = self.stack, S * D
             for i, l in enumerate(self.layers):
@@ -217,7 +235,8 @@ class ShardedDeepFMTrainStep:
             check(lib.dr_embed_fm_bwd_sharded(self.emb.peer_ptrs.data_ptr(), G, self.emb.slot_offsets.data_ptr(),
                                               self.emb.rows.data_ptr(), self.ids.data_ptr(), 8, self.stack.data_ptr(),
                                               self.sum_e.data_ptr(), gz.data_ptr(), self.g_stack.data_ptr(), B, S, D,
-                                              V, 1, None, -self.lr / G, st()), "dr_embed_fm_bwd_sharded")
+                                              V, self.emb.flags, self.emb.lin_offset, None, -self.lr / G, st()),
+                  "dr_embed_fm_bwd_sharded")
             mark("embed_fm_bwd_p2p")
             check(lib.dr_sgd_step(self.flat.data_ptr(), self.gflat.data_ptr(), self.flat.numel(), self.lr / G, st()),
                   "dr_sgd_step")
@@ -409,7 +428,8 @@ class ShardedDeepFMTrainStep:
                 ids = ids_pool[k % len(ids_pool)]
                 check(lib.dr_embed_fm_fwd_sharded(self.emb.peer_ptrs.data_ptr(), G, self.emb.slot_offsets.data_ptr(),
                                                   self.emb.rows.data_ptr(), ids.data_ptr(), 8, self.bias.data_ptr(),
-                                                  B, S, D, V, 1, self.stack.data_ptr(), self.sum_e.data_ptr(),
+                                                  B, S, D, V, self.emb.flags, self.emb.lin_offset,
+                                                  self.stack.data_ptr(), self.sum_e.data_ptr(),
                                                   self.fm_logit.data_ptr(), st), "dr_embed_fm_fwd_sharded")
             else:
                 check(lib.dr_embed_fm_fwd(self.tp.data_ptr(), self.lp.data_ptr(), self.trows.data_ptr(),

@@ -216,15 +216,19 @@ int dr_shard_bucket_ids(const void* ids, int id_bytes, int64_t n, int S,
  * gather and no all-to-all.  The backward issues its vector atomics (red.global.add.v4.f32)
  * straight into the owner's arena.  The caller separates a step's remote reads from its remote
  * updates with a collective on the tower gradients and ends the step with a barrier.
- * Same outputs / gradient formulas as dr_embed_fm_fwd / dr_embed_fm_bwd.                         */
+ * Same outputs / gradient formulas as dr_embed_fm_fwd / dr_embed_fm_bwd.
+ * First-order weights: with DR_EMBED_LIN_IN_ROW they ride in the row at float D (D <= 124, rows of 128-B lines);
+ * for wider rows (BASELINE config C5, D = 128) pass flags = 0 and lin_offset > 0: rank g keeps the weight of its
+ * local row l at peer_bases[g] + lin_offset + l (floats), i.e. a [local rows] array trailing the [local rows, D]
+ * shard in the same mapped allocation.  lin_offset = 0 and flags = 0: no first-order term.                  */
 int dr_embed_fm_fwd_sharded(const float* const* peer_bases, int world, const int64_t* slot_offsets,
                             const int64_t* rows, const void* ids, int id_bytes, const float* bias,
-                            int64_t B, int S, int D, int64_t row_stride, int flags,
+                            int64_t B, int S, int D, int64_t row_stride, int flags, int64_t lin_offset,
                             float* out_stack, float* out_sum, float* out_logit, void* stream);
 int dr_embed_fm_bwd_sharded(float* const* peer_bases, int world, const int64_t* slot_offsets,
                             const int64_t* rows, const void* ids, int id_bytes, const float* stack,
                             const float* sum_e, const float* g_logit, const float* g_stack,
-                            int64_t B, int S, int D, int64_t row_stride, int flags,
+                            int64_t B, int S, int D, int64_t row_stride, int flags, int64_t lin_offset,
                             float* g_bias, float scale, void* stream);
 
 int dr_permute_rows(const float* in, const int32_t* perm, int64_t n, int D, float* out, void* stream);

@@ -562,3 +562,55 @@ def test_c1_tfrecord_pipeline_matches_oracle(tmp_path):
             opt.step()
             first = first if first is not None else float(loss)
         assert float(loss) < first
+
+
+# ---- row-sharded wide rows (BASELINE configs C3-C5: D = 32 ... 128), world 1 ---------------------------------------
+@pytest.mark.parametrize("D", [32, 128])
+def test_world1_sharded_wide_rows_equal_single_gpu_step(D):
+    """The p2p sharded kernels with rows of exactly D floats and the first-order weights trailing the shard
+    (lin_offset addressing) against the single-GPU split-layout step; world 2 / 8 runs are the bench's job."""
+    import os
+    import socket
+    import torch.distributed as dist
+    from deep_recommenders_b200 import feature_column as fc
+    from deep_recommenders_b200.keras.models.ranking import DeepFM
+    from deep_recommenders_b200.sharded import ShardedDeepFMTrainStep
+    from deep_recommenders_b200.training import DeepFMTrainStep
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        rows, B = [300, 7, 50, 1000, 21], 384
+        cols = [fc.categorical_column_with_identity(f"c{i}", r) for i, r in enumerate(rows)]
+        sh = ShardedDeepFMTrainStep(cols, D, [32, 8], batch_size=B, lr=0.05, seed=3, device="cuda", exchange="p2p")
+        assert sh.emb.vdim == D and sh.emb.flags == 0 and sh.emb.lin_offset == sum(rows) * D
+        model = DeepFM([fc.indicator_column(c) for c in cols], [fc.embedding_column(c, D) for c in cols],
+                       dnn_units_size=[32, 8], seed=3, device="cuda", sparse_lr=0.05)
+        ref = DeepFMTrainStep(model, batch_size=B, lr=0.05, use_graph=False)
+        with torch.no_grad():
+            sh.emb.lin_view().normal_(0, 0.1)
+            model.embeddings.emb_view().copy_(sh.emb.weight[:, :D])
+            model.embeddings.lin_view().copy_(sh.emb.lin_view())
+            for i in range(len(ref.layers)):
+                ref.w[i].copy_(sh.w[i])
+                ref.b[i].copy_(sh.b[i])
+        gen = torch.Generator(device="cuda").manual_seed(0)
+        ids = torch.stack([torch.randint(-1, r + 1, (B,), device="cuda", generator=gen) for r in rows], dim=1)
+        lab = torch.randint(0, 2, (B,), device="cuda", generator=gen).float()
+        for it in range(3):
+            l_sh = float(sh.step(ids, lab).item())
+            l_ref = float(ref.step(ids, lab).item())
+            assert abs(l_sh - l_ref) <= 1e-5 * abs(l_ref) + 1e-6
+            if it == 0:
+                assert torch.equal(sh.stack, ref.stack)                   # gathered rows bit-exact
+                assert torch.allclose(sh.fm_logit, ref.fm_logit, rtol=1e-5, atol=1e-5)
+            else:
+                assert torch.allclose(sh.stack, ref.stack, rtol=1e-5, atol=1e-6)
+        assert torch.allclose(sh.emb.weight[:, :D], model.embeddings.emb_view(), rtol=1e-5, atol=1e-6)
+        assert torch.allclose(sh.emb.lin_view(), model.embeddings.lin_view(), rtol=1e-5, atol=1e-6)
+        assert torch.allclose(sh.bias, model.embeddings.bias, rtol=1e-5, atol=1e-6)
+    finally:
+        dist.destroy_process_group()
