@@ -58,6 +58,11 @@ __device__ __forceinline__ float4 ldg_nc_na(const float* p) {
                : "l"(p));
   return r;
 }
+__device__ __forceinline__ float ldg_nc_na_f32(const float* p) {
+  float r;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
 // 128-bit load through the normal (L1-allocating) path.
 __device__ __forceinline__ float4 ldg4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 

@@ -26,6 +26,9 @@ int g_tune_embed_block = 256;         // threads per CTA
 int g_tune_embed_ctas_per_sm = 0;     // 0 = as many as fit (2048 threads / SM)
 int g_tune_embed_bwd_agg = 1;         // example-parallel mode: warp-aggregate duplicate ids before the atomics
 int g_tune_embed_bwd_mode = 0;        // 0 = slot-parallel (default), 1 = example-parallel (+ optional aggregation)
+int g_tune_embed_fwd_linx = 0;        // 1 = LINX forward variant for in-row first-order weights (see the kernel)
+int g_tune_embed_fwd_minblocks = 0;   // forward register cap: 0 = none (ptxas picks, 108 regs -> 2 CTAs of 256 / SM),
+                                      // 3 / 4 = __launch_bounds__(256, n): <= 85 / 64 registers, 24 / 32 warps per SM
 
 struct EmbedFwdParams {
   const float* const* table_ptrs;
@@ -85,8 +88,11 @@ __host__ __device__ inline size_t embed_smem_bytes(int S, int warps, int G, int 
   return hdr + ((ids + 15) & ~(size_t)15);
 }
 
-template <int LPR, typename IdT, int U, bool SHARD>
-__global__ void __launch_bounds__(512) embed_fm_fwd_kernel(const EmbedFwdParams p) {
+// LINX (experiment, knob embed_fwd_linx): with the in-row first-order weight, size the lane group for the D/4
+// embedding chunks only (D = 16: 4 lanes, 8 examples per warp, no idle lanes) and let lane 0 of the group fetch
+// the weight with a second, scalar load issued right behind its 16-B chunk load (same 128-B line, in flight).
+template <int LPR, typename IdT, int U, bool SHARD, int MINB = 0, bool LINX = false>
+__global__ void __launch_bounds__(MINB ? 256 : 512, MINB ? MINB : 1) embed_fm_fwd_kernel(const EmbedFwdParams p) {
   constexpr int G = 32 / LPR;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int S = p.S, D = p.D;
@@ -118,8 +124,9 @@ __global__ void __launch_bounds__(512) embed_fm_fwd_kernel(const EmbedFwdParams 
   const bool chunk_ok = (c * 4) < D;
   // lin_in_row: the lane owning chunk D/4 fetches [w | pad] with the SAME LDG.128 as the embedding
   // chunks, so the first-order weight costs no extra request / DRAM line.
-  const bool lin_lane = p.lin_in_row && (c * 4 == D);
+  const bool lin_lane = !LINX && p.lin_in_row && (c * 4 == D);
   const bool has_lin = p.lin_ptrs != nullptr && !p.lin_in_row;
+  const bool linx_lane = LINX && p.lin_in_row && c == 0 && p.out_logit != nullptr;
   const float bias = p.bias ? __ldg(p.bias) : 0.f;
   const IdT* __restrict__ ids = reinterpret_cast<const IdT*>(p.ids);
 
@@ -146,10 +153,12 @@ __global__ void __launch_bounds__(512) embed_fm_fwd_kernel(const EmbedFwdParams 
 
     for (int s0 = 0; s0 < S; s0 += U) {
       float4 v[U];
+      float wv[LINX ? U : 1];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int s = s0 + u;
         v[u] = f4_zero();
+        if (LINX) wv[u] = 0.f;
         if (s < S && ex_ok && (chunk_ok || lin_lane)) {
           const int64_t id = (int64_t)my[s];
           if ((uint64_t)id < (uint64_t)s_rows[s]) {
@@ -163,6 +172,7 @@ __global__ void __launch_bounds__(512) embed_fm_fwd_kernel(const EmbedFwdParams 
               rowp = s_peer[owner] + (size_t)local * p.row_stride;
             }
             v[u] = ldg_nc_na(rowp + c * 4);
+            if (LINX && linx_lane) wv[u] = ldg_nc_na_f32(rowp + D);
           }
         }
       }
@@ -170,6 +180,7 @@ __global__ void __launch_bounds__(512) embed_fm_fwd_kernel(const EmbedFwdParams 
       for (int u = 0; u < U; ++u) {
         const int s = s0 + u;
         if (s < S) {
+          if (LINX) lin += wv[u];
           if (lin_lane) {
             lin += v[u].x;
           } else {
@@ -530,7 +541,7 @@ static LaunchGeom geom(int64_t B, int S, int LPR, int id_bytes) {
   return lg;
 }
 
-template <int LPR, typename IdT, int U>
+template <int LPR, typename IdT, int U, bool LINXSEL = false>
 static int launch_fwd_u(const EmbedFwdParams& p, cudaStream_t st) {
   LaunchGeom lg = geom(p.B, p.S, LPR, sizeof(IdT));
   if (p.shard_world > 0) {
@@ -538,12 +549,37 @@ static int launch_fwd_u(const EmbedFwdParams& p, cudaStream_t st) {
     if (lg.smem > 48 * 1024) DR_CUDA_CALL(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lg.smem));
     k<<<lg.ctas, lg.threads, lg.smem, st>>>(p);
   } else {
+    // experiment instantiations (same arithmetic, same results): narrow rows, U = 8 / 13 only
+    //   MINB 3 / 4: register cap via __launch_bounds__(256, n);  LINX: see the kernel comment
+    constexpr bool kExp = (LPR <= 8) && (U == 8 || U == 13);
+    constexpr int UU = kExp ? U : 8;
+    const int minb = (kExp && lg.threads <= 256 && lg.smem <= 48 * 1024) ? g_tune_embed_fwd_minblocks : 0;
+    if (kExp && lg.smem <= 48 * 1024 && (minb >= 3 || LINXSEL)) {
+      int per_sm = minb >= 4 ? 4 : (minb == 3 ? 3 : 2);
+      per_sm *= (lg.threads <= 256 ? 256 / lg.threads : 1);
+      if (g_tune_embed_ctas_per_sm > 0 && g_tune_embed_ctas_per_sm < per_sm) per_sm = g_tune_embed_ctas_per_sm;
+      const int64_t warps = lg.threads / 32, G = 32 / LPR;
+      int64_t ctas = ((p.B + G - 1) / G + warps - 1) / warps;
+      if (ctas > (int64_t)kNumSMs * per_sm) ctas = (int64_t)kNumSMs * per_sm;   // one resident wave
+      if (ctas < 1) ctas = 1;
+      if (minb >= 4) embed_fm_fwd_kernel<LPR, IdT, UU, false, 4, LINXSEL><<<(unsigned)ctas, lg.threads, lg.smem, st>>>(p);
+      else if (minb == 3) embed_fm_fwd_kernel<LPR, IdT, UU, false, 3, LINXSEL><<<(unsigned)ctas, lg.threads, lg.smem, st>>>(p);
+      else embed_fm_fwd_kernel<LPR, IdT, UU, false, 0, LINXSEL><<<(unsigned)ctas, lg.threads, lg.smem, st>>>(p);
+      DR_CUDA_LAUNCH_CHECK("embed_fm_fwd(experiment)");
+      return DR_OK;
+    }
     auto k = embed_fm_fwd_kernel<LPR, IdT, U, false>;
     if (lg.smem > 48 * 1024) DR_CUDA_CALL(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lg.smem));
     k<<<lg.ctas, lg.threads, lg.smem, st>>>(p);
   }
   DR_CUDA_LAUNCH_CHECK("embed_fm_fwd");
   return DR_OK;
+}
+
+template <int LPR, typename IdT>
+static int launch_fwd_linx(const EmbedFwdParams& p, cudaStream_t st) {
+  if (g_tune_embed_fwd_unroll == 13) return launch_fwd_u<LPR, IdT, 13, true>(p, st);
+  return launch_fwd_u<LPR, IdT, 8, true>(p, st);
 }
 
 template <int LPR, typename IdT>
@@ -670,6 +706,17 @@ extern "C" int dr_embed_fm_fwd(const float* const* table_ptrs, const float* cons
   p.B = B; p.S = S; p.D = D; p.out_stack = out_stack; p.out_sum = out_sum; p.out_logit = out_logit;
   p.row_stride = row_stride; p.lin_stride = lin_stride; p.lin_in_row = lin_in_row;
   cudaStream_t st = (cudaStream_t)stream;
+  if (g_tune_embed_fwd_linx && lin_in_row && out_logit && lpr_for(D, 0) <= 8) {
+    const int lpr = lpr_for(D, 0);     // lane group sized for the embedding chunks only
+#define DR_LINX(L) (id_bytes == 8 ? launch_fwd_linx<L, int64_t>(p, st) : launch_fwd_linx<L, int32_t>(p, st))
+    switch (lpr) {
+      case 1: return DR_LINX(1);
+      case 2: return DR_LINX(2);
+      case 4: return DR_LINX(4);
+      default: return DR_LINX(8);
+    }
+#undef DR_LINX
+  }
   DR_DISPATCH_LPR(launch_fwd, p, st);
 }
 

@@ -614,3 +614,44 @@ def test_world1_sharded_wide_rows_equal_single_gpu_step(D):
         assert torch.allclose(sh.bias, model.embeddings.bias, rtol=1e-5, atol=1e-6)
     finally:
         dist.destroy_process_group()
+
+
+# ---- scheduling variants of the headline forward kernel: identical results required -------------------------------
+@pytest.fixture
+def embed_knobs():
+    from deep_recommenders_b200 import _lib
+
+    def set_(**kw):
+        for k, v in kw.items():
+            _lib.tune(k, v)
+    yield set_
+    for k in ("embed_fwd_minblocks", "embed_fwd_linx", "embed_fwd_unroll", "embed_ctas_per_sm"):
+        _lib.tune(k, 0)
+
+
+@pytest.mark.parametrize("linx", [0, 1])
+@pytest.mark.parametrize("minb", [0, 3, 4])
+@pytest.mark.parametrize("unroll", [8, 13])
+@pytest.mark.parametrize("B,rows,D", [(257, [50, 60, 70, 2, 7, 21], 16), (1000, [1000] * 26, 16), (99, [64] * 4, 12),
+                                      (33, [19] * 2, 20), (65, [31] * 3, 28), (40, [9] * 5, 8), (7, [5] * 2, 4)])
+def test_forward_variants_bit_identical_to_default(embed_knobs, linx, minb, unroll, B, rows, D):
+    import importlib.util
+    import pathlib
+    spec = importlib.util.spec_from_file_location("t_embed", pathlib.Path(__file__).resolve().parent / "test_gpu_embed.py")
+    te = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(te)
+    tables, lins, bias, ids = te.make_problem(B, rows, D, seed=B + D, oov_frac=0.1)
+    coll = te.to_collection(tables, lins, bias, layout="fused")
+    idt = torch.from_numpy(ids).cuda()
+    with torch.no_grad():
+        stack0, logit0 = coll(idt)
+        embed_knobs(embed_fwd_minblocks=minb, embed_fwd_linx=linx, embed_fwd_unroll=unroll)
+        stack1, logit1 = coll(idt)
+        stack_only, _ = coll(idt, want_logit=False)
+    torch.cuda.synchronize()
+    assert torch.equal(stack0, stack1) and torch.equal(logit0, logit1) and torch.equal(stack0, stack_only)
+    ref_stack = R.stack_embeddings(tables, ids)
+    assert np.array_equal(stack1.cpu().numpy().view(np.uint32), ref_stack.view(np.uint32))
+    ref_logit, _ = R.fm_logit(tables, lins, bias, ids, np.float64)
+    err = np.abs(logit1.cpu().numpy().astype(np.float64) - ref_logit.reshape(-1))
+    assert (err <= 1e-5 * te.logit_scale(tables, lins, bias, ids) + 1e-6).all()
