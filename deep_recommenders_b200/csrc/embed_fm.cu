@@ -26,7 +26,9 @@ int g_tune_embed_block = 256;         // threads per CTA
 int g_tune_embed_ctas_per_sm = 0;     // 0 = as many as fit (2048 threads / SM)
 int g_tune_embed_bwd_agg = 1;         // example-parallel mode: warp-aggregate duplicate ids before the atomics
 int g_tune_embed_bwd_mode = 0;        // 0 = slot-parallel (default), 1 = example-parallel (+ optional aggregation)
-int g_tune_embed_fwd_linx = 0;        // 1 = LINX forward variant for in-row first-order weights (see the kernel)
+int g_tune_embed_fwd_linx = 1;        // 1 (default) = LINX forward mapping for in-row first-order weights: measured 70.0 us
+                                      // vs 86.0 us at C2 (tools/ab_embed_fwd.py, profiles/ab_embed_fwd_r01.json), bit-identical
+int g_tune_embed_fwd_linx_shard = 0;  // same mapping for the row-sharded (peer-memory) forward: off until measured at N > 1
 int g_tune_embed_fwd_minblocks = 0;   // forward register cap: 0 = none (ptxas picks, 108 regs -> 2 CTAs of 256 / SM),
                                       // 3 / 4 = __launch_bounds__(256, n): <= 85 / 64 registers, 24 / 32 warps per SM
 
@@ -545,16 +547,23 @@ template <int LPR, typename IdT, int U, bool LINXSEL = false>
 static int launch_fwd_u(const EmbedFwdParams& p, cudaStream_t st) {
   LaunchGeom lg = geom(p.B, p.S, LPR, sizeof(IdT));
   if (p.shard_world > 0) {
-    auto k = embed_fm_fwd_kernel<LPR, IdT, U, true>;
-    if (lg.smem > 48 * 1024) DR_CUDA_CALL(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lg.smem));
-    k<<<lg.ctas, lg.threads, lg.smem, st>>>(p);
+    if (LINXSEL && LPR <= 8 && U == 8) {
+      auto k = embed_fm_fwd_kernel<LPR, IdT, (LPR <= 8 && U == 8) ? U : 8, true, 0, LINXSEL>;
+      if (lg.smem > 48 * 1024) DR_CUDA_CALL(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lg.smem));
+      k<<<lg.ctas, lg.threads, lg.smem, st>>>(p);
+    } else {
+      auto k = embed_fm_fwd_kernel<LPR, IdT, U, true>;
+      if (lg.smem > 48 * 1024) DR_CUDA_CALL(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lg.smem));
+      k<<<lg.ctas, lg.threads, lg.smem, st>>>(p);
+    }
   } else {
     // experiment instantiations (same arithmetic, same results): narrow rows, U = 8 / 13 only
     //   MINB 3 / 4: register cap via __launch_bounds__(256, n);  LINX: see the kernel comment
     constexpr bool kExp = (LPR <= 8) && (U == 8 || U == 13);
     constexpr int UU = kExp ? U : 8;
+    static_assert(!LINXSEL || kExp, "LINX is instantiated for LPR <= 8 and U in {8, 13} only");
     const int minb = (kExp && lg.threads <= 256 && lg.smem <= 48 * 1024) ? g_tune_embed_fwd_minblocks : 0;
-    if (kExp && lg.smem <= 48 * 1024 && (minb >= 3 || LINXSEL)) {
+    if (kExp && (minb >= 3 || LINXSEL)) {
       int per_sm = minb >= 4 ? 4 : (minb == 3 ? 3 : 2);
       per_sm *= (lg.threads <= 256 ? 256 / lg.threads : 1);
       if (g_tune_embed_ctas_per_sm > 0 && g_tune_embed_ctas_per_sm < per_sm) per_sm = g_tune_embed_ctas_per_sm;
@@ -562,10 +571,16 @@ static int launch_fwd_u(const EmbedFwdParams& p, cudaStream_t st) {
       int64_t ctas = ((p.B + G - 1) / G + warps - 1) / warps;
       if (ctas > (int64_t)kNumSMs * per_sm) ctas = (int64_t)kNumSMs * per_sm;   // one resident wave
       if (ctas < 1) ctas = 1;
-      if (minb >= 4) embed_fm_fwd_kernel<LPR, IdT, UU, false, 4, LINXSEL><<<(unsigned)ctas, lg.threads, lg.smem, st>>>(p);
-      else if (minb == 3) embed_fm_fwd_kernel<LPR, IdT, UU, false, 3, LINXSEL><<<(unsigned)ctas, lg.threads, lg.smem, st>>>(p);
-      else embed_fm_fwd_kernel<LPR, IdT, UU, false, 0, LINXSEL><<<(unsigned)ctas, lg.threads, lg.smem, st>>>(p);
-      DR_CUDA_LAUNCH_CHECK("embed_fm_fwd(experiment)");
+      if (minb >= 4) {
+        embed_fm_fwd_kernel<LPR, IdT, UU, false, 4, LINXSEL><<<(unsigned)ctas, lg.threads, lg.smem, st>>>(p);
+      } else if (minb == 3) {
+        embed_fm_fwd_kernel<LPR, IdT, UU, false, 3, LINXSEL><<<(unsigned)ctas, lg.threads, lg.smem, st>>>(p);
+      } else {
+        auto k = embed_fm_fwd_kernel<LPR, IdT, UU, false, 0, LINXSEL>;
+        if (lg.smem > 48 * 1024) DR_CUDA_CALL(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lg.smem));
+        k<<<(unsigned)ctas, lg.threads, lg.smem, st>>>(p);
+      }
+      DR_CUDA_LAUNCH_CHECK("embed_fm_fwd(linx/capped)");
       return DR_OK;
     }
     auto k = embed_fm_fwd_kernel<LPR, IdT, U, false>;
@@ -578,8 +593,21 @@ static int launch_fwd_u(const EmbedFwdParams& p, cudaStream_t st) {
 
 template <int LPR, typename IdT>
 static int launch_fwd_linx(const EmbedFwdParams& p, cudaStream_t st) {
-  if (g_tune_embed_fwd_unroll == 13) return launch_fwd_u<LPR, IdT, 13, true>(p, st);
+  if (g_tune_embed_fwd_unroll == 13 && p.shard_world == 0) return launch_fwd_u<LPR, IdT, 13, true>(p, st);
   return launch_fwd_u<LPR, IdT, 8, true>(p, st);
+}
+
+// lane group sized for the embedding chunks only (LINX): D <= 32 with the weight in the row
+static int dispatch_fwd_linx(const EmbedFwdParams& p, int id_bytes, cudaStream_t st) {
+  const int lpr = lpr_for(p.D, 0);
+#define DR_LINX(L) (id_bytes == 8 ? launch_fwd_linx<L, int64_t>(p, st) : launch_fwd_linx<L, int32_t>(p, st))
+  switch (lpr) {
+    case 1: return DR_LINX(1);
+    case 2: return DR_LINX(2);
+    case 4: return DR_LINX(4);
+    default: return DR_LINX(8);
+  }
+#undef DR_LINX
 }
 
 template <int LPR, typename IdT>
@@ -706,17 +734,7 @@ extern "C" int dr_embed_fm_fwd(const float* const* table_ptrs, const float* cons
   p.B = B; p.S = S; p.D = D; p.out_stack = out_stack; p.out_sum = out_sum; p.out_logit = out_logit;
   p.row_stride = row_stride; p.lin_stride = lin_stride; p.lin_in_row = lin_in_row;
   cudaStream_t st = (cudaStream_t)stream;
-  if (g_tune_embed_fwd_linx && lin_in_row && out_logit && lpr_for(D, 0) <= 8) {
-    const int lpr = lpr_for(D, 0);     // lane group sized for the embedding chunks only
-#define DR_LINX(L) (id_bytes == 8 ? launch_fwd_linx<L, int64_t>(p, st) : launch_fwd_linx<L, int32_t>(p, st))
-    switch (lpr) {
-      case 1: return DR_LINX(1);
-      case 2: return DR_LINX(2);
-      case 4: return DR_LINX(4);
-      default: return DR_LINX(8);
-    }
-#undef DR_LINX
-  }
+  if (g_tune_embed_fwd_linx && lin_in_row && out_logit && lpr_for(D, 0) <= 8) return dispatch_fwd_linx(p, id_bytes, st);
   DR_DISPATCH_LPR(launch_fwd, p, st);
 }
 
@@ -812,6 +830,7 @@ extern "C" int dr_embed_fm_fwd_sharded(const float* const* peer_bases, int world
   p.row_stride = row_stride; p.lin_stride = row_stride; p.lin_in_row = lin_in_row;
   p.shard_world = world; p.peer_bases = peer_bases; p.slot_offsets = slot_offsets; p.shard_lin_off = lin_offset;
   cudaStream_t st = (cudaStream_t)stream;
+  if (g_tune_embed_fwd_linx_shard && lin_in_row && out_logit && lpr_for(D, 0) <= 8) return dispatch_fwd_linx(p, id_bytes, st);
   DR_DISPATCH_LPR(launch_fwd, p, st);
 }
 

@@ -318,20 +318,32 @@ def embedding_bag_grad(rows, flat_ids, row_splits, g_out, combiner="mean", dtype
     return gt
 
 
+def _f32_beta(b):
+    """The hyper-parameters reach TensorFlow's kernels as float32 tensors: 0.999 is 0.99900001287..., which moves
+    1 - beta2 by 1.3e-5 relative -- above the 1e-5 parity bar, so the oracle must round them the same way."""
+    return float(np.float32(b))
+
+
 def adam_lr_t(lr, step, beta1=0.9, beta2=0.999):
-    """Keras optimizer_v2 Adam / tf.train.AdamOptimizer: lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t), t = 1, 2, ..."""
-    return lr * np.sqrt(1.0 - beta2 ** step) / (1.0 - beta1 ** step)
+    """Keras optimizer_v2 Adam / tf.train.AdamOptimizer: lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t), t = 1, 2, ...
+    (betas as float32 values; evaluated in float64 here, in float32 by TF: the result is the same to ~1e-5 relative
+    for small t, where 1 - b2^t cancels)."""
+    b1, b2 = _f32_beta(beta1), _f32_beta(beta2)
+    return float(np.float32(lr)) * np.sqrt(1.0 - b2 ** step) / (1.0 - b1 ** step)
 
 
 def adam_dense(p, g, m, v, lr_t, beta1=0.9, beta2=0.999, eps=1e-7, dtype=np.float32):
     """TensorFlow's ApplyAdam functor (the optimizer both reference examples use:
     examples/train_deepfm_on_movielens_keras.py:44, examples/train_fm_on_movielens_estimator.py:51):
         m += (g - m)(1 - b1);  v += (g*g - v)(1 - b2);  p -= lr_t * m / (sqrt(v) + eps)
+    with (1 - b) formed in float32 like the functor's `T(1) - beta()`.
     Returns (p, m, v).  TF applies it densely to embedding variables too (module docstring of optim.cu)."""
     p, g, m, v = (np.asarray(a, dtype=dtype) for a in (p, g, m, v))
-    m = m + (g - m) * dtype(1.0 - dtype(beta1))
-    v = v + (g * g - v) * dtype(1.0 - dtype(beta2))
-    p = p - (m * dtype(lr_t)) / (np.sqrt(v) + dtype(eps))
+    omb1 = dtype(np.float32(1.0) - np.float32(beta1))
+    omb2 = dtype(np.float32(1.0) - np.float32(beta2))
+    m = m + (g - m) * omb1
+    v = v + (g * g - v) * omb2
+    p = p - (m * dtype(np.float32(lr_t))) / (np.sqrt(v) + dtype(np.float32(eps)))
     return p, m, v
 
 

@@ -64,7 +64,7 @@ def main():
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / nrep * 1e-3
 
-    knobs()
+    knobs(linx=0)
     fwd(0)
     torch.cuda.synchronize()
     ref = (stacks[0].clone(), sums[0].clone(), logits[0].clone())
@@ -84,7 +84,7 @@ def main():
                  bit_identical=same)
         print(json.dumps(r), flush=True)
         out.append(r)
-    knobs()
+    knobs(linx=1)      # library default
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(out, open("gpurun_out/ab_embed_fwd.json", "w"), indent=1)
 
