@@ -145,13 +145,16 @@ def set_workspace(nbytes: int, device=None):
     return _workspace
 
 
-def enable_tensor_core_gemm(workspace_bytes: int = 0, device=None) -> None:
-    """Route eligible GEMMs (Dense / Cross / scores) to the tcgen05 3xTF32 kernel."""
-    global _tc_enabled
+def enable_tensor_core_gemm(workspace_bytes: int = 0, device=None, variant: int = None) -> None:
+    """Route eligible GEMMs (Dense / Cross / scores) to a tcgen05 3xTF32 kernel: variant 1 = pre-split hi/lo planes
+    (needs the registered workspace), variant 2 = split in shared memory inside the GEMM (no workspace).
+    Default: the variant selected by DR_GEMM (tc -> 1, tc2 -> 2)."""
+    global _tc_enabled, _tc_applied
     if workspace_bytes:
         set_workspace(workspace_bytes, device)
-    tune("gemm_variant", 1)
+    tune("gemm_variant", int(variant) if variant is not None else _tc_variant)
     _tc_enabled = True
+    _tc_applied = True          # an explicit choice is not overridden by the lazy default
 
 
 def disable_tensor_core_gemm() -> None:
@@ -160,8 +163,11 @@ def disable_tensor_core_gemm() -> None:
     _tc_enabled = False
 
 
-# The tcgen05 3xTF32 GEMM is the default; DR_GEMM=ffma selects the FFMA variant.
-_tc_enabled = os.environ.get("DR_GEMM", "tc") != "ffma"
+# DR_GEMM selects the default GEMM core: tc = tcgen05 3xTF32 on pre-split planes, tc2 = tcgen05 3xTF32 with the split
+# inside the kernel, ffma = FFMA.
+_GEMM_ENV = os.environ.get("DR_GEMM", "tc")
+_tc_enabled = _GEMM_ENV != "ffma"
+_tc_variant = 2 if _GEMM_ENV == "tc2" else 1
 _tc_applied = False
 
 
@@ -172,7 +178,7 @@ def ensure_gemm_workspace(M: int, K: int, N: int, device=None) -> None:
     if not _tc_enabled:
         return
     if not _tc_applied:
-        tune("gemm_variant", 1)
+        tune("gemm_variant", _tc_variant)
         _tc_applied = True
     k4, n4, m4 = (K + 3) // 4 * 4, (N + 3) // 4 * 4, (M + 3) // 4 * 4
     need = 8 * max(M * k4 + N * k4, M * n4 + K * n4, K * m4 + N * m4) + (1 << 16)

@@ -16,6 +16,11 @@
 //               the epilogue ("tmem_full")
 //   warps 2-5   epilogue: tcgen05.ld (32 lanes x 32 columns per warp), fused epilogue (gemm.cuh
 //               Epi modes), vectorised global stores / split-K atomics
+// Variant 2 (INSPLIT, g_tune_gemm_variant == 2): no pre-split planes at all.  TMA stages the RAW fp32 tiles of A and B
+// (half the L2 -> SM operand bytes of variant 1, and no split kernel / plane traffic in HBM), four extra warps split
+// every staged tile in shared memory -- hi overwrites the raw tile in place, lo goes to the slot next to it; the pass
+// is elementwise on 16-B chunks, so it is oblivious to the TMA swizzle -- then fence.proxy.async and arrive on a
+// per-stage "split" mbarrier the MMA issuer waits on instead of the TMA "full" barrier.
 // Operand majors: K-major (row-major [rows, K]) or MN-major ([K, rows] row-major) per operand;
 // both are canonical SWIZZLE_128B UMMA layouts (32 tf32 = 128 B per swizzle row).
 #include "gemm.cuh"
@@ -43,6 +48,8 @@ static size_t g_bump = 0;     // floats used at the front of the workspace
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;          // 32 tf32 = 128 bytes = one SWIZZLE_128B row
 constexpr int TC_THREADS = 192;
+constexpr int TC_SPLIT_WARPS = 4;                              // variant 2: warps 6..9 split the staged fp32 tiles
+constexpr int TC_THREADS_INSPLIT = TC_THREADS + 32 * TC_SPLIT_WARPS;
 
 // ---- small PTX wrappers ----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -196,6 +203,35 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// Variant 2 splitter: elementwise over 16-B chunks of one staged tile (BYTES multiple of 16 * NT * 4 or smaller tail).
+template <int BYTES, int NT>
+__device__ __forceinline__ void split_tile_inplace(uint8_t* hi, uint8_t* lo, int tid) {
+  constexpr int CHUNKS = BYTES / 16;
+  constexpr int PER = (CHUNKS + NT - 1) / NT;
+#pragma unroll
+  for (int i0 = 0; i0 < PER; i0 += 4) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = (i0 + u) * NT + tid;
+      if (i0 + u < PER && c < CHUNKS) v[u] = *reinterpret_cast<const float4*>(hi + (size_t)c * 16);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = (i0 + u) * NT + tid;
+      if (i0 + u < PER && c < CHUNKS) {
+        float4 h, l;
+        h.x = __uint_as_float(__float_as_uint(v[u].x) & 0xFFFFE000u); l.x = v[u].x - h.x;
+        h.y = __uint_as_float(__float_as_uint(v[u].y) & 0xFFFFE000u); l.y = v[u].y - h.y;
+        h.z = __uint_as_float(__float_as_uint(v[u].z) & 0xFFFFE000u); l.z = v[u].z - h.z;
+        h.w = __uint_as_float(__float_as_uint(v[u].w) & 0xFFFFE000u); l.w = v[u].w - h.w;
+        *reinterpret_cast<float4*>(hi + (size_t)c * 16) = h;
+        *reinterpret_cast<float4*>(lo + (size_t)c * 16) = l;
+      }
+    }
+  }
+}
+
 // Work item = (m tile, n tile, k split).  Items are strided over the persistent grid.
 struct TcItem {
   int64_t m0, n0;
@@ -217,8 +253,8 @@ __device__ __forceinline__ TcItem tc_decode(int64_t item, int64_t n_tiles, int64
 
 // Persistent, warp-specialised: the accumulator is double buffered in TMEM (2 x BN columns) so the
 // epilogue of item j overlaps the TMA/MMA main loop of item j+1.
-template <int BN, int STAGES, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool INSPLIT = false>
+__global__ void __launch_bounds__(INSPLIT ? TC_THREADS_INSPLIT : TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                const GemmArgs a, const int64_t m_tiles, const int64_t n_tiles, const int64_t per,
@@ -228,7 +264,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], split_bar[STAGES], tmem_full_bar[2],
+      tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -242,6 +279,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+      mbar_init(&split_bar[s], 32 * TC_SPLIT_WARPS);   // every splitter thread arrives
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
@@ -271,27 +309,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           const int s = (int)(it % STAGES);
           const uint32_t ph = (it / STAGES) & 1u;
           mbar_wait(&empty_bar[s], ph ^ 1u);
-          mbar_expect_tx(&full_bar[s], (uint32_t)STAGE);
+          // INSPLIT: only the raw fp32 tiles travel (tmAh / tmBh map the source tensors); they land in the hi slots
+          mbar_expect_tx(&full_bar[s], (uint32_t)(INSPLIT ? (A_TILE + B_TILE) : STAGE));
           uint8_t* st = smem + (size_t)s * STAGE;
           const int k = (t.kb0 + i) * TC_BK;
           if (!A_MN) {
             tma_load_2d(st, &tmAh, &full_bar[s], k, (int)t.m0);
-            tma_load_2d(st + A_TILE, &tmAl, &full_bar[s], k, (int)t.m0);
+            if (!INSPLIT) tma_load_2d(st + A_TILE, &tmAl, &full_bar[s], k, (int)t.m0);
           } else {     // MN-major: one [32 k-rows x 32 floats] box per 32-wide MN atom
 #pragma unroll
             for (int jj = 0; jj < TC_BM / 32; ++jj) {
               tma_load_2d(st + jj * 4096, &tmAh, &full_bar[s], (int)t.m0 + jj * 32, k);
-              tma_load_2d(st + A_TILE + jj * 4096, &tmAl, &full_bar[s], (int)t.m0 + jj * 32, k);
+              if (!INSPLIT) tma_load_2d(st + A_TILE + jj * 4096, &tmAl, &full_bar[s], (int)t.m0 + jj * 32, k);
             }
           }
           if (!B_MN) {
             tma_load_2d(st + 2 * A_TILE, &tmBh, &full_bar[s], k, (int)t.n0);
-            tma_load_2d(st + 2 * A_TILE + B_TILE, &tmBl, &full_bar[s], k, (int)t.n0);
+            if (!INSPLIT) tma_load_2d(st + 2 * A_TILE + B_TILE, &tmBl, &full_bar[s], k, (int)t.n0);
           } else {
 #pragma unroll
             for (int jj = 0; jj < BN / 32; ++jj) {
               tma_load_2d(st + 2 * A_TILE + jj * 4096, &tmBh, &full_bar[s], (int)t.n0 + jj * 32, k);
-              tma_load_2d(st + 2 * A_TILE + B_TILE + jj * 4096, &tmBl, &full_bar[s], (int)t.n0 + jj * 32, k);
+              if (!INSPLIT) tma_load_2d(st + 2 * A_TILE + B_TILE + jj * 4096, &tmBl, &full_bar[s], (int)t.n0 + jj * 32, k);
             }
           }
         }
@@ -312,7 +351,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         for (int i = 0; i < t.nkb; ++i, ++it) {
           const int s = (int)(it % STAGES);
           const uint32_t ph = (it / STAGES) & 1u;
-          mbar_wait(&full_bar[s], ph);
+          mbar_wait(INSPLIT ? &split_bar[s] : &full_bar[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)s * STAGE);
           const uint32_t sb = sa + 2 * A_TILE;
@@ -340,6 +379,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       }
     }
     __syncwarp();
+  } else if (INSPLIT && warp >= 6) {
+    // ===== splitter warps 6..9 (variant 2): raw fp32 tile -> TF32 hi (in place) + lo (next slot) =====
+    const int tid = (int)threadIdx.x - TC_THREADS;
+    constexpr int NSPLIT = 32 * TC_SPLIT_WARPS;
+    uint32_t it = 0;
+    for (int64_t item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const TcItem t = tc_decode(item, n_tiles, m_tiles, kblocks, per, BN);
+      for (int i = 0; i < t.nkb; ++i, ++it) {
+        const int s = (int)(it % STAGES);
+        const uint32_t ph = (it / STAGES) & 1u;
+        mbar_wait(&full_bar[s], ph);          // TMA bytes of this stage have landed (visible to generic loads)
+        uint8_t* st = smem + (size_t)s * STAGE;
+        split_tile_inplace<A_TILE, NSPLIT>(st, st + A_TILE, tid);
+        split_tile_inplace<B_TILE, NSPLIT>(st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, tid);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
+        mbar_arrive(&split_bar[s]);
+      }
+    }
   } else {
     // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
     const int q = warp & 3;
@@ -446,6 +503,12 @@ static void plane_elems(const GemmArgs& a, bool ta, bool tb, size_t* ae, size_t*
 }
 
 bool gemm_tc_eligible(const GemmArgs& a, bool ta, bool tb) {
+  if (g_tune_gemm_variant == 2) {   // in-kernel split: raw operands by TMA, no workspace
+    if (a.N < g_tune_tc_min_n || (a.N & 3) || a.M < 64 || a.K < 32) return false;
+    if ((a.lda & 3) || !aligned16(a.A) || (a.ldb & 3) || !aligned16(a.B)) return false;
+    if (a.M >= ((int64_t)1 << 31) || a.K >= ((int64_t)1 << 31) || a.N >= ((int64_t)1 << 31)) return false;
+    return true;
+  }
   if (g_tune_gemm_variant != 1) return false;
   // measured (profiles/README.md): for N = 32 the extra hi/lo split of the activations costs more than the
   // 128 x 32 tensor-core tile saves over the FFMA kernel, so skinny layers stay on FFMA unless tc_min_n is lowered
@@ -474,11 +537,11 @@ bool gemm_tc_eligible(const GemmArgs& a, bool ta, bool tb) {
   return true;
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool INSPLIT = false>
 static int launch_tc(const CUtensorMap* tms, const GemmArgs& a, cudaStream_t st) {
   constexpr int STAGE = 2 * TC_BM * TC_BK * 4 + 2 * BN * TC_BK * 4;
   const size_t smem = (size_t)STAGES * STAGE + 1024;
-  auto k = gemm_tc_kernel<BN, STAGES, A_MN, B_MN>;
+  auto k = gemm_tc_kernel<BN, STAGES, A_MN, B_MN, INSPLIT>;
   DR_CUDA_CALL(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t m_tiles = (a.M + TC_BM - 1) / TC_BM, n_tiles = (a.N + BN - 1) / BN;
   const int64_t kblocks = (a.K + TC_BK - 1) / TC_BK;
@@ -486,7 +549,8 @@ static int launch_tc(const CUtensorMap* tms, const GemmArgs& a, cudaStream_t st)
   const int64_t splits = (kblocks + per - 1) / per;          // every split owns >= 1 k-block
   const int64_t total = m_tiles * n_tiles * splits;
   const int64_t ctas = total < (int64_t)kNumSMs ? total : (int64_t)kNumSMs;
-  k<<<(unsigned)ctas, TC_THREADS, smem, st>>>(tms[0], tms[1], tms[2], tms[3], a, m_tiles, n_tiles, per, total);
+  k<<<(unsigned)ctas, INSPLIT ? TC_THREADS_INSPLIT : TC_THREADS, smem, st>>>(tms[0], tms[1], tms[2], tms[3], a, m_tiles,
+                                                                               n_tiles, per, total);
   DR_CUDA_LAUNCH_CHECK("gemm_tc");
   return DR_OK;
 }
@@ -521,6 +585,35 @@ int gemm_tc_launch(const GemmArgs& a0, bool ta, bool tb, cudaStream_t st) {
   if (a.splitk < 1) a.splitk = 1;
   const int64_t kblocks = (a.K + TC_BK - 1) / TC_BK;
   if (a.splitk > kblocks) a.splitk = (int)kblocks;
+  if (g_tune_gemm_variant == 2) {
+    // Variant 2: tensor maps straight on the source operands (consumed as stored), split in shared memory.
+    const bool A_MN = ta, B_MN = !tb;
+    CUtensorMap tm2[4];
+    if (!A_MN) {
+      if (int rc = make_map(&tm2[0], a.A, a.K, a.M, a.lda, TC_BM)) return rc;
+    } else {
+      if (int rc = make_map(&tm2[0], a.A, a.M, a.K, a.lda, TC_BK, true)) return rc;
+    }
+    const int bn = a.N <= 32 ? 32 : (a.N <= 64 ? 64 : 128);
+    if (!B_MN) {
+      if (int rc = make_map(&tm2[2], a.B, a.K, a.N, a.ldb, bn)) return rc;
+    } else {
+      if (int rc = make_map(&tm2[2], a.B, a.N, a.K, a.ldb, TC_BK, true)) return rc;
+    }
+    tm2[1] = tm2[0];
+    tm2[3] = tm2[2];
+#define DR_TC2_LAUNCH(BN_, ST_)                                                             \
+    do {                                                                                    \
+      if (!A_MN && !B_MN) return launch_tc<BN_, ST_, false, false, true>(tm2, a, st);       \
+      if (!A_MN && B_MN) return launch_tc<BN_, ST_, false, true, true>(tm2, a, st);         \
+      if (A_MN && !B_MN) return launch_tc<BN_, ST_, true, false, true>(tm2, a, st);         \
+      return launch_tc<BN_, ST_, true, true, true>(tm2, a, st);                             \
+    } while (0)
+    if (bn == 32) DR_TC2_LAUNCH(32, 5);
+    if (bn == 64) DR_TC2_LAUNCH(64, 4);
+    DR_TC2_LAUNCH(128, 3);
+#undef DR_TC2_LAUNCH
+  }
   size_t ae, be;
   plane_elems(a, ta, tb, &ae, &be);
   const size_t need = (ae + be) * 2 * sizeof(float);

@@ -13,12 +13,15 @@ from oracle import reference_np as R
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["ffma", "tc"])
+@pytest.fixture(autouse=True, params=["ffma", "tc", "tc2"])
 def gemm_variant(request):
-    """Every test in this file runs under both GEMM variants: FFMA and tcgen05 3xTF32."""
+    """Every test in this file runs under all GEMM cores: FFMA, tcgen05 3xTF32 on pre-split planes (tc) and
+    tcgen05 3xTF32 with the hi/lo split inside the kernel (tc2)."""
     from deep_recommenders_b200 import _lib
     if request.param == "tc":
-        _lib.enable_tensor_core_gemm()
+        _lib.enable_tensor_core_gemm(variant=1)
+    elif request.param == "tc2":
+        _lib.enable_tensor_core_gemm(variant=2)
     else:
         _lib.disable_tensor_core_gemm()
     yield request.param

@@ -680,3 +680,39 @@ def test_forward_many_slots_needs_opt_in_shared_memory(embed_knobs, linx, S):
     ref_logit, _ = R.fm_logit(tables, lins, bias, ids, np.float64)
     err = np.abs(logit.cpu().numpy().astype(np.float64) - ref_logit.reshape(-1))
     assert (err <= 1e-5 * te.logit_scale(tables, lins, bias, ids) + 1e-6).all()
+
+
+def test_world1_sharded_forward_linx_mapping_equals_default(embed_knobs):
+    """Knob embed_fwd_linx_shard (off by default until measured at N > 1): the LINX lane mapping in the peer-memory
+    forward must give the same bits as the default sharded forward."""
+    import os
+    import socket
+    import torch.distributed as dist
+    from deep_recommenders_b200 import _lib, feature_column as fc
+    from deep_recommenders_b200.sharded import ShardedDeepFMTrainStep
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        rows, B, D = [300, 7, 50, 1000, 21], 384, 16
+        cols = [fc.categorical_column_with_identity(f"c{i}", r) for i, r in enumerate(rows)]
+        sh = ShardedDeepFMTrainStep(cols, D, [32, 8], batch_size=B, lr=0.0, seed=3, device="cuda", exchange="p2p",
+                                    use_graph=False)
+        with torch.no_grad():
+            sh.emb.lin_view().normal_(0, 0.1)
+        gen = torch.Generator(device="cuda").manual_seed(0)
+        ids = torch.stack([torch.randint(-1, r + 1, (B,), device="cuda", generator=gen) for r in rows], dim=1)
+        lab = torch.randint(0, 2, (B,), device="cuda", generator=gen).float()
+        sh.step(ids, lab)
+        torch.cuda.synchronize()
+        ref = (sh.stack.clone(), sh.fm_logit.clone(), sh.sum_e.clone())
+        _lib.tune("embed_fwd_linx_shard", 1)
+        sh.step(ids, lab)                       # lr = 0: parameters unchanged, forward must reproduce itself
+        torch.cuda.synchronize()
+        assert torch.equal(sh.stack, ref[0]) and torch.equal(sh.fm_logit, ref[1]) and torch.equal(sh.sum_e, ref[2])
+    finally:
+        _lib.tune("embed_fwd_linx_shard", 0)
+        dist.destroy_process_group()
