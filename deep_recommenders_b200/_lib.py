@@ -163,11 +163,12 @@ def disable_tensor_core_gemm() -> None:
     _tc_enabled = False
 
 
-# DR_GEMM selects the default GEMM core: tc = tcgen05 3xTF32 on pre-split planes, tc2 = tcgen05 3xTF32 with the split
-# inside the kernel, ffma = FFMA.
-_GEMM_ENV = os.environ.get("DR_GEMM", "tc")
+# DR_GEMM selects the default GEMM core: tc2 (default) = tcgen05 3xTF32 with the hi/lo split inside the kernel
+# (bit-identical outputs to tc, 17-23 % faster at the C2 layer shapes: profiles/check_gemm_insplit_r01.json),
+# tc = tcgen05 3xTF32 on pre-split planes, ffma = FFMA.
+_GEMM_ENV = os.environ.get("DR_GEMM", "tc2")
 _tc_enabled = _GEMM_ENV != "ffma"
-_tc_variant = 2 if _GEMM_ENV == "tc2" else 1
+_tc_variant = 1 if _GEMM_ENV == "tc" else 2
 _tc_applied = False
 
 
