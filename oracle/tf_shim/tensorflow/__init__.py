@@ -470,6 +470,187 @@ def _layers_dense(x, units, activation=None, **k):
 layers = types.SimpleNamespace(dense=_layers_dense)
 
 
+# ---- retrieval slice (reference keras/models/retrieval/factorized_top_k.py: _take_long_axis, _exclude, Streaming,
+# BruteForce, FactorizedTopK) -- TensorFlow's documented semantics of the ops that file calls ------------------------
+def zeros(shape, dtype=None, name=None):  # noqa: A002
+    return _t(_np.zeros(tuple(int(x) for x in shape), dtype=dtype or DEFAULT_DTYPE[0]))
+
+
+def ones(shape, dtype=None, name=None):  # noqa: A002
+    return _t(_np.ones(tuple(int(x) for x in _np.asarray(shape).reshape(-1)), dtype=dtype or DEFAULT_DTYPE[0]))
+
+
+def zeros_like(x, dtype=None, name=None):
+    return _t(_np.zeros_like(_np.asarray(x), dtype=dtype))
+
+
+def ones_like(x, dtype=None, name=None):
+    return _t(_np.ones_like(_np.asarray(x), dtype=dtype))
+
+
+def gather_nd(params, indices, name=None):
+    idx = _np.asarray(indices)
+    return _t(_np.asarray(params)[tuple(idx[..., i] for i in _builtin_range(idx.shape[-1]))])
+
+
+def rank(x, name=None):
+    return _np.asarray(x).ndim
+
+
+def group(*ops, **k):
+    return None
+
+
+def where(cond, x=None, y=None, name=None):
+    return _t(_np.where(_np.asarray(cond), _np.asarray(x), _np.asarray(y)))
+
+
+_builtin_range = __builtins__["range"] if isinstance(__builtins__, dict) else __builtins__.range
+_gather_axis0 = gather
+
+
+def gather(params, indices, axis=0, batch_dims=0, name=None):  # noqa: F811
+    if batch_dims == 0:
+        return _gather_axis0(params, indices, axis=axis)
+    assert batch_dims == 1
+    return _t(_np.take_along_axis(_np.asarray(params), _np.asarray(indices), axis=1))
+
+
+def _top_k_checked(x, k=1, sorted=True, name=None):  # noqa: A002
+    x = _np.asarray(x)
+    if int(k) > x.shape[-1]:
+        raise ValueError("input must have at least k columns. Had %d, needed %d" % (x.shape[-1], int(k)))
+    return _top_k(x, k, sorted, name)
+
+
+math.top_k = _top_k_checked
+math.reduce_any = lambda x, axis=None, keepdims=False, **k: _t(_np.any(_np.asarray(x), axis=axis, keepdims=keepdims))
+math.in_top_k = lambda targets, predictions, k, **kw: _t(
+    (_np.asarray(predictions) > _np.take_along_axis(_np.asarray(predictions), _np.asarray(targets).reshape(-1, 1), 1)).sum(1) < k)
+
+
+class _Variable:
+    """tf.Variable as created by Layer.add_weight: array-like, assign / assign_add / read_value."""
+
+    def __init__(self, value):
+        self._v = _np.array(value)
+
+    def assign(self, v):
+        self._v = _np.array(v).astype(self._v.dtype).reshape(_np.shape(v))
+        return self.read_value()
+
+    def assign_add(self, v):
+        self._v = self._v + _np.asarray(v).astype(self._v.dtype)
+        return self.read_value()
+
+    def read_value(self):
+        return _t(self._v.copy())
+
+    def __array__(self, dtype=None, copy=None):
+        return self._v if dtype is None else self._v.astype(dtype)
+
+    shape = property(lambda self: TensorShape(self._v.shape))
+    dtype = property(lambda self: self._v.dtype)
+
+
+class _Model(Layer):
+    """tf.keras.Model as far as the retrieval indexes use it: add_weight + __call__ -> call."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(**kwargs)
+
+    def add_weight(self, name=None, dtype=None, shape=(), initializer=None, trainable=True, **k):
+        return _Variable(_np.zeros(tuple(shape) if shape is not None else (), dtype=dtype or DEFAULT_DTYPE[0]))
+
+    def __call__(self, *args, **kwargs):
+        if not self.built:
+            first = args[0] if args else next(iter(kwargs.values()))
+            shp = TensorShape(_np.asarray(first).shape) if not isinstance(first, dict) else None
+            self.build(shp)
+            self.built = True
+        return self.call(*args, **kwargs)
+
+
+# Keras tracks metric objects assigned as attributes; FactorizedTopK reads them back through `self.metrics`
+Layer.metrics = property(lambda self: list(getattr(self, "_metrics", [])))
+
+
+class _TopKCategoricalAccuracy:
+    """tf.keras.metrics.TopKCategoricalAccuracy: mean over all seen rows of in_top_k(y_pred, argmax(y_true), k)."""
+
+    def __init__(self, k=5, name=None, **kw):
+        self.k, self.name = k, name
+        self.reset_states()
+
+    def reset_states(self):
+        self._hits, self._n = 0.0, 0
+
+    def update_state(self, y_true, y_pred, sample_weight=None):
+        y_true, y_pred = _np.asarray(y_true), _np.asarray(y_pred)
+        tgt = y_true.argmax(axis=1)
+        tv = _np.take_along_axis(y_pred, tgt[:, None], axis=1)
+        self._hits += float(((y_pred > tv).sum(axis=1) < self.k).sum())
+        self._n += y_pred.shape[0]
+
+    def result(self):
+        return _t(_np.asarray(self._hits / max(self._n, 1), dtype=DEFAULT_DTYPE[0]))
+
+
+class _Spec:
+    def __init__(self, dtype):
+        self.dtype = dtype
+
+
+class Dataset:
+    """tf.data.Dataset over in-memory numpy elements: from_tensor_slices / batch / map / zip / reduce / iteration."""
+
+    def __init__(self, elements):
+        self._e = list(elements)
+
+    @staticmethod
+    def from_tensor_slices(x):
+        return Dataset([_t(row) for row in _np.asarray(x)])
+
+    def batch(self, n, drop_remainder=False):
+        out = []
+        for i in _builtin_range(0, len(self._e), n):
+            chunk = self._e[i:i + n]
+            if drop_remainder and len(chunk) < n:
+                break
+            out.append(_t(_np.stack([_np.asarray(c) for c in chunk])))
+        return Dataset(out)
+
+    def map(self, fn, num_parallel_calls=None):  # noqa: A003
+        return Dataset([fn(*e) if isinstance(e, tuple) else fn(e) for e in self._e])
+
+    @staticmethod
+    def zip(datasets):  # noqa: A003
+        return Dataset(list(__builtins__["zip"](*[d._e for d in datasets]) if isinstance(__builtins__, dict)
+                            else __builtins__.zip(*[d._e for d in datasets])))
+
+    def reduce(self, initial_state, fn):
+        state = initial_state
+        for e in self._e:
+            state = fn(state, e)
+        return state
+
+    def __iter__(self):
+        return iter(self._e)
+
+    @property
+    def element_spec(self):
+        e = self._e[0]
+        return _Spec(_np.asarray(e[0] if isinstance(e, tuple) else e).dtype)
+
+
+data = types.SimpleNamespace(Dataset=Dataset, experimental=types.SimpleNamespace(AUTOTUNE=-1))
+keras.Model = _Model
+keras.metrics = types.SimpleNamespace(TopKCategoricalAccuracy=_TopKCategoricalAccuracy, Metric=object)
+keras.initializers.Zeros = lambda: "zeros"
+keras.initializers.Constant = lambda value=0: "constant"
+Operation = object
+
+
 def __getattr__(name):
     if name.startswith("__"):
         raise AttributeError(name)

@@ -14,6 +14,10 @@ What executes from the reference:
   estimator/models/feature_interaction/fm.py   fm (:10-26), FM.call (:41-56)
   estimator/models/feature_interaction/dnn.py  dnn (:9-31)
   estimator/models/ranking/deepfm.py           DeepFM.call (:30-43)
+and, into tests/golden/retrieval_golden.npz:
+  keras/models/retrieval/factorized_top_k.py   _take_long_axis (:26-41), _exclude (:44-67), Streaming.call (:180-262),
+                                               BruteForce.index / call (:277-334), TopK.query_with_exclusions (:113-131),
+                                               FactorizedTopK.update_state / result (:487-522)
 """
 import os
 import sys
@@ -220,7 +224,76 @@ def generate(dtype):
     return out
 
 
+def generate_retrieval():
+    """Executes the reference's factorized_top_k.py (float32, its own dtype) on seeded inputs."""
+    tf.set_default_dtype(np.float32)
+    import importlib
+    ftk = importlib.import_module("deep_recommenders.keras.models.retrieval.factorized_top_k")
+    out = {}
+    rng = np.random.RandomState(11)
+    # _take_long_axis / _exclude: the reference's own KATs (tests/keras/test_factorized_top_k.py:17-34) and random cases
+    arr = np.asarray([[0.1, 0.2, 0.3], [0.4, 0.5, 0.6]], np.float32)
+    out["tla_kat"] = np.asarray(ftk._take_long_axis(tf.constant(arr), tf.constant([[0, 1], [2, 1]])))
+    x, y = ftk._exclude(tf.constant(arr), tf.constant([[0, 1, 2], [3, 4, 5]]), tf.constant([[1, 2], [3, 5]]), 1)
+    out["exclude_kat_scores"], out["exclude_kat_ids"] = np.asarray(x), np.asarray(y)
+    scores = rng.standard_normal((9, 40)).astype(np.float32)
+    ident = np.stack([rng.permutation(200)[:40] for _ in range(9)]).astype(np.int64)
+    excl = np.stack([np.concatenate([ident[r, rng.permutation(40)[:3]], [100000 + r]]) for r in range(9)]).astype(np.int64)
+    idx = rng.randint(0, 40, size=(9, 7)).astype(np.int32)
+    out.update(tla_arr=scores, tla_idx=idx, tla_out=np.asarray(ftk._take_long_axis(tf.constant(scores), tf.constant(idx))))
+    for k in (5, 40, 60):
+        xs, xi = ftk._exclude(tf.constant(scores), tf.constant(ident), tf.constant(excl), k)
+        out[f"exclude_k{k}_scores"], out[f"exclude_k{k}_ids"] = np.asarray(xs), np.asarray(xi)
+    out.update(exclude_scores=scores, exclude_ident=ident, exclude_excl=excl)
+
+    # indexes: 100 candidates x 4 (the reference test's sizes, :90-96), batches of 32, with and without identifiers
+    rs = np.random.RandomState(42)
+    cand = rs.normal(size=(100, 4)).astype(np.float32)
+    queries = rs.normal(size=(10, 4)).astype(np.float32)
+    true_c = rs.normal(size=(10, 4)).astype(np.float32)
+    names = (np.arange(100) * 3 + 7).astype(np.int64)
+    out.update(idx_candidates=cand, idx_queries=queries, idx_true=true_c, idx_names=names)
+    cds = tf.data.Dataset.from_tensor_slices(cand).batch(32)
+    nds = tf.data.Dataset.from_tensor_slices(names).batch(32)
+    for tag, ids in (("noid", None), ("id", nds)):
+        st = ftk.Streaming(k=10).index(cds, ids)
+        s, i = st(tf.constant(queries))
+        out[f"streaming_{tag}_scores"], out[f"streaming_{tag}_ids"] = np.asarray(s), np.asarray(i)
+        bf = ftk.BruteForce(k=10).index(cds, ids)
+        s, i = bf(tf.constant(queries))
+        out[f"brute_{tag}_scores"], out[f"brute_{tag}_ids"] = np.asarray(s), np.asarray(i)
+        s, i = bf(tf.constant(queries), k=3)
+        out[f"brute_{tag}_k3_ids"] = np.asarray(i)
+    bf = ftk.BruteForce(k=5).index(tf.constant(cand), tf.constant(names))
+    s5, i5 = bf(tf.constant(queries))
+    ban = np.asarray(i5)[:, [0, 2]].astype(np.int64)
+    xs, xi = bf.query_with_exclusions(tf.constant(queries), tf.constant(ban), k=5)
+    out.update(qwe_ban=ban, qwe_scores=np.asarray(xs), qwe_ids=np.asarray(xi))
+    small = ftk.Streaming(k=50).index(tf.data.Dataset.from_tensor_slices(cand[:40]).batch(32))     # k > batch: clipped
+    s, i = small(tf.constant(queries))
+    out["streaming_small_scores"], out["streaming_small_ids"] = np.asarray(s), np.asarray(i)
+    try:
+        ftk.Streaming(k=50, handle_incomplete_batches=False).index(tf.data.Dataset.from_tensor_slices(cand[:40]).batch(32))(tf.constant(queries))
+        out["streaming_small_error"] = np.asarray("")
+    except ValueError as e:
+        out["streaming_small_error"] = np.asarray(str(e))
+    # FactorizedTopK metric (:464-522) with the reference test's ks
+    ks = [1, 5, 10, 50]
+    for tag, layer in (("streaming", ftk.Streaming), ("brute", ftk.BruteForce), ("dataset", None)):
+        c = cds if layer is None else layer().index(cds)
+        metric = ftk.FactorizedTopK(candidates=c, metrics=[tf.keras.metrics.TopKCategoricalAccuracy(k=x, name=f"top_{x}")
+                                                         for x in ks], k=max(ks))
+        metric.update_state(query_embeddings=tf.constant(queries), true_candidate_embeddings=tf.constant(true_c))
+        out[f"metric_{tag}"] = np.asarray([float(np.asarray(v)) for v in metric.result()], np.float64)
+    out["metric_ks"] = np.asarray(ks)
+    return out
+
+
 def main():
+    data = generate_retrieval()
+    path = os.path.join(HERE, "retrieval_golden.npz")
+    np.savez_compressed(path, **data)
+    print(path, len(data), "arrays", os.path.getsize(path), "bytes")
     for name, dt in (("f32", np.float32), ("f64", np.float64)):
         data = generate(dt)
         path = os.path.join(HERE, f"hotpath_golden_{name}.npz")

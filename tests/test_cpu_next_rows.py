@@ -130,3 +130,41 @@ def test_adam_oracle_matches_torch_adam():
     np.testing.assert_allclose(pn, p.detach().numpy(), rtol=5e-7, atol=1e-9)
     # float32 hyper-parameters: 1 - float32(0.999) differs from 0.001 by 1.3e-5 relative (why the oracle rounds them)
     assert abs((1.0 - b2) / 0.001 - 1.0) > 1e-5
+
+
+# ---- golden vectors produced by executing the reference's factorized_top_k.py under the TF stand-in -------------
+def _retrieval_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "retrieval_golden.npz"))
+
+
+def test_oracle_reproduces_reference_retrieval_golden():
+    g = _retrieval_golden()
+    np.testing.assert_array_equal(R.take_long_axis(g["tla_arr"], g["tla_idx"]), g["tla_out"])
+    np.testing.assert_allclose(g["tla_kat"], [[0.1, 0.2], [0.6, 0.5]], rtol=1e-6)
+    assert g["exclude_kat_ids"].tolist() == [[0], [4]]
+    for k in (5, 40, 60):
+        xs, xi = R.exclude(g["exclude_scores"], g["exclude_ident"], g["exclude_excl"], k)
+        np.testing.assert_array_equal(xi, g[f"exclude_k{k}_ids"])
+        np.testing.assert_array_equal(xs, g[f"exclude_k{k}_scores"])
+    q, c, names = g["idx_queries"], g["idx_candidates"], g["idx_names"]
+    batches = [c[i:i + 32] for i in range(0, 100, 32)]
+    nbatches = [names[i:i + 32] for i in range(0, 100, 32)]
+    for tag, nb, nm in (("noid", None, None), ("id", nbatches, names)):
+        s, i = R.streaming_topk(q, batches, nb, 10)
+        np.testing.assert_array_equal(i, g[f"streaming_{tag}_ids"])
+        np.testing.assert_allclose(s, g[f"streaming_{tag}_scores"], rtol=1e-6)
+        s, i = R.brute_force_topk(q, c, nm, 10)
+        np.testing.assert_array_equal(i, g[f"brute_{tag}_ids"])
+        np.testing.assert_allclose(s, g[f"brute_{tag}_scores"], rtol=1e-6)
+        np.testing.assert_array_equal(R.brute_force_topk(q, c, nm, 3)[1], g[f"brute_{tag}_k3_ids"])
+    s7, i7 = R.brute_force_topk(q, c, names, 7)                         # query_with_exclusions: k + 2 then _exclude
+    xs, xi = R.exclude(s7, i7, g["qwe_ban"], 7)
+    np.testing.assert_array_equal(xi, g["qwe_ids"])
+    s, i = R.streaming_topk(q, [c[:32], c[32:40]], None, 50)             # k clipped to what the stream holds
+    np.testing.assert_array_equal(i, g["streaming_small_ids"])
+    assert "candidate batch too small" in str(g["streaming_small_error"])
+    top, _ = R.brute_force_topk(q, c, None, 50)
+    want = R.factorized_topk_metric(q, g["idx_true"], top, g["metric_ks"].tolist())
+    for tag in ("streaming", "brute", "dataset"):
+        np.testing.assert_allclose(g[f"metric_{tag}"], want, rtol=1e-6)

@@ -716,3 +716,43 @@ def test_world1_sharded_forward_linx_mapping_equals_default(embed_knobs):
     finally:
         _lib.tune("embed_fwd_linx_shard", 0)
         dist.destroy_process_group()
+
+
+def test_retrieval_classes_reproduce_the_reference_source_golden():
+    """tests/golden/retrieval_golden.npz = the reference's own factorized_top_k.py executed under the TF stand-in
+    (tests/golden/make_golden.py): identifiers must match exactly, scores to 1e-5."""
+    import os
+    from deep_recommenders.keras.models.retrieval import FactorizedTopK, factorized_top_k as ftk
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "retrieval_golden.npz"))
+    cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    out = ftk._take_long_axis(cu(g["tla_arr"]), cu(g["tla_idx"]))
+    assert np.array_equal(out.cpu().numpy(), g["tla_out"])
+    for k in (5, 40, 60):
+        xs, xi = ftk._exclude(cu(g["exclude_scores"]), cu(g["exclude_ident"]), cu(g["exclude_excl"]), k)
+        assert np.array_equal(xi.cpu().numpy(), g[f"exclude_k{k}_ids"])
+        assert np.array_equal(xs.cpu().numpy(), g[f"exclude_k{k}_scores"])
+    q, c, names = cu(g["idx_queries"]), g["idx_candidates"], g["idx_names"]
+    batches = [cu(c[i:i + 32]) for i in range(0, 100, 32)]
+    nbatches = [torch.from_numpy(names[i:i + 32]) for i in range(0, 100, 32)]
+    for tag, nb in (("noid", None), ("id", nbatches)):
+        for cls, key in ((ftk.Streaming, "streaming"), (ftk.BruteForce, "brute")):
+            s, i = cls(k=10).index(batches, nb)(q)
+            assert np.array_equal(i.cpu().numpy(), g[f"{key}_{tag}_ids"])
+            assert np.allclose(s.cpu().numpy(), g[f"{key}_{tag}_scores"], rtol=1e-5, atol=1e-6)
+        s3, i3 = ftk.BruteForce(k=10).index(batches, nb)(q, k=3)
+        assert np.array_equal(i3.cpu().numpy(), g[f"brute_{tag}_k3_ids"])
+    bf = ftk.BruteForce(k=5).index(cu(c), torch.from_numpy(names))
+    xs, xi = bf.query_with_exclusions(q, cu(g["qwe_ban"]), k=5)
+    assert np.array_equal(xi.cpu().numpy(), g["qwe_ids"])
+    assert np.allclose(xs.cpu().numpy(), g["qwe_scores"], rtol=1e-5, atol=1e-6)
+    s, i = ftk.Streaming(k=50).index([cu(c[:32]), cu(c[32:40])])(q)
+    assert np.array_equal(i.cpu().numpy(), g["streaming_small_ids"])
+    with pytest.raises(ValueError) as ei:
+        ftk.Streaming(k=50, handle_incomplete_batches=False).index([cu(c[:32]), cu(c[32:40])])(q)
+    assert str(ei.value) == str(g["streaming_small_error"])
+    ks = g["metric_ks"].tolist()
+    for tag, cand in (("streaming", ftk.Streaming().index(batches)), ("brute", ftk.BruteForce().index(batches)),
+                      ("dataset", batches)):
+        m = FactorizedTopK(candidates=cand, metrics=[ftk.TopKCategoricalAccuracy(k=x) for x in ks], k=max(ks))
+        m.update_state(q, cu(g["idx_true"]))
+        assert np.allclose(m.result(), g[f"metric_{tag}"], rtol=1e-6)
