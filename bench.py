@@ -179,15 +179,25 @@ def main():
     if world > 1:
         from deep_recommenders_b200.sharded import ShardedDeepFMTrainStep
         exchange_note = None
+        def build_sharded(exchange):
+            return ShardedDeepFMTrainStep(cols, D, W["dnn"], batch_size=B, lr=0.01, seed=1, device=dev,
+                                          use_graph=not args.no_graph, exchange=exchange).capture()
         try:
-            trainer = ShardedDeepFMTrainStep(cols, D, W["dnn"], batch_size=B, lr=0.01, seed=1, device=dev,
-                                             use_graph=not args.no_graph, exchange=args.exchange).capture()
-        except Exception as e:      # symmetric memory unavailable on this box: NCCL all-to-all pipeline instead
-            if args.exchange != "p2p":
-                raise
-            exchange_note = f"p2p unavailable ({type(e).__name__}: {e}); used nccl"
-            trainer = ShardedDeepFMTrainStep(cols, D, W["dnn"], batch_size=B, lr=0.01, seed=1, device=dev,
-                                             use_graph=not args.no_graph, exchange="nccl").capture()
+            trainer = build_sharded(args.exchange)
+        except Exception as e:
+            trainer = None
+            if _lib._tc_variant == 2:       # newest GEMM core first suspect: retry the same exchange on the tc core
+                gemm_note = f"tc2 unavailable ({type(e).__name__}: {e}); used tc"
+                _lib.enable_tensor_core_gemm(variant=1)
+                try:
+                    trainer = build_sharded(args.exchange)
+                except Exception as e2:
+                    e = e2
+            if trainer is None:             # symmetric memory unavailable on this box: NCCL all-to-all pipeline instead
+                if args.exchange != "p2p":
+                    raise e
+                exchange_note = f"p2p unavailable ({type(e).__name__}: {e}); used nccl"
+                trainer = build_sharded("nccl")
     else:
         def build_single():
             model = DeepFM([fc.indicator_column(c) for c in cols], [fc.embedding_column(c, D) for c in cols],
