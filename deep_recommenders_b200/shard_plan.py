@@ -37,3 +37,18 @@ def capacity(n_lookups: int, world: int, slack: float = 0.04, floor: int = 4096)
     The overflow flag catches skew (the caller re-plans with a larger slack)."""
     mean = (n_lookups + world - 1) // world
     return min(n_lookups, mean + max(floor, int(mean * slack))) if world > 1 else n_lookups
+
+
+def own_first_order(rank: int, world: int) -> List[int]:
+    """Block order of the all-gathered candidate embeddings seen by `rank` in the sharded two-tower step: its OWN
+    block first (so the positive of local query i is candidate i and the in-batch-softmax kernel's eye(nq, nc)
+    labels hold unchanged), the other ranks' blocks after it in rank order."""
+    return [rank] + [r for r in range(world) if r != rank]
+
+
+def inverse_order(order: Sequence[int]) -> List[int]:
+    """inverse_order(o)[r] = position of block r in the order `o` (to bring gradients back to rank order)."""
+    inv = [0] * len(order)
+    for pos, r in enumerate(order):
+        inv[r] = pos
+    return inv
