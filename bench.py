@@ -145,6 +145,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly (for ncu launch lists)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
                     help="c2 (default, the headline config; weak scaling) or c5 (100M rows x D=128, global batch 65536)")
+    ap.add_argument("--tune", action="append", default=[], metavar="KNOB=VALUE",
+                    help="developer knob of libdeeprec_b200.so (dr_tune_set), e.g. --tune tc_min_n=32; recorded in the line")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: fused NVLink peer-memory gather/update (p2p) or NCCL all-to-all pipeline (nccl)")
     args = ap.parse_args()
@@ -172,6 +174,9 @@ def main():
     from deep_recommenders_b200.keras.models.ranking import DeepFM
     from deep_recommenders_b200.training import DeepFMTrainStep
 
+    for kv in args.tune:
+        k, v = kv.split("=")
+        _lib.tune(k, int(v))
     W = C5 if args.workload == "c5" else C2
     B, S, D = (W["batch"] // world if args.workload == "c5" else W["batch"]), W["slots"], W["dim"]
     gemm_note = None
@@ -314,6 +319,8 @@ def main():
         line["exchange_note"] = exchange_note
     if gemm_note:
         line["gemm_note"] = gemm_note
+    if args.tune:
+        line["tune"] = args.tune
     print(json.dumps(line), flush=True)
 
 

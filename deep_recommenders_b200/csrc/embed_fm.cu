@@ -28,6 +28,7 @@ int g_tune_embed_bwd_agg = 1;         // example-parallel mode: warp-aggregate d
 int g_tune_embed_bwd_mode = 0;        // 0 = slot-parallel (default), 1 = example-parallel (+ optional aggregation)
 int g_tune_embed_fwd_linx = 1;        // 1 (default) = LINX forward mapping for in-row first-order weights: measured 70.0 us
                                       // vs 86.0 us at C2 (tools/ab_embed_fwd.py, profiles/ab_embed_fwd_r01.json), bit-identical
+int g_tune_embed_bwd_linx = 0;        // LINX mapping for the slot-parallel backward (in-row weight, D <= 32): unmeasured
 int g_tune_embed_fwd_linx_shard = 0;  // same mapping for the row-sharded (peer-memory) forward: off until measured at N > 1
 int g_tune_embed_fwd_minblocks = 0;   // forward register cap: 0 = none (ptxas picks, 108 regs -> 2 CTAs of 256 / SM),
                                       // 3 / 4 = __launch_bounds__(256, n): <= 85 / 64 registers, 24 / 32 warps per SM
@@ -365,7 +366,9 @@ __global__ void __launch_bounds__(512) embed_fm_bwd_kernel(const EmbedBwdParams 
 //     are resolved by the L2 atomic unit),
 //   * no shared-memory staging and no cross-lane reduction: sum_e arrives precomputed.
 // U slot-steps are loaded before any atomic is issued (the red.global asm is a compiler barrier).
-template <int LPR, typename IdT, int U, bool SHARD>
+// LINX (knob embed_bwd_linx, off by default: unmeasured): lane group sized for the D/4 embedding chunks only, the
+// first-order gradient of an in-row weight issued by lane 0 as a scalar red.global.add behind its vector atomic.
+template <int LPR, typename IdT, int U, bool SHARD, bool LINX = false>
 __global__ void __launch_bounds__(256) embed_fm_bwd_sp_kernel(const EmbedBwdParams p) {
   constexpr int SPW = 32 / LPR;      // slots per warp-instruction
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -393,7 +396,8 @@ __global__ void __launch_bounds__(256) embed_fm_bwd_sp_kernel(const EmbedBwdPara
   const int c = lane % LPR, sg = lane / LPR;
   const bool chunk_ok = (c * 4) < D;
   const bool has_fm = p.g_logit != nullptr, has_gs = p.g_stack != nullptr;
-  const bool lin_lane = p.lin_in_row && has_fm && (c * 4 == D);
+  const bool lin_lane = !LINX && p.lin_in_row && has_fm && (c * 4 == D);
+  const bool linx_lane = LINX && p.lin_in_row && has_fm && c == 0;
   const bool has_lin = p.grad_lin_ptrs != nullptr && has_fm && !p.lin_in_row;
   const float scale = p.scale;
   const IdT* __restrict__ ids = reinterpret_cast<const IdT*>(p.ids);
@@ -451,6 +455,7 @@ __global__ void __launch_bounds__(256) embed_fm_bwd_sp_kernel(const EmbedBwdPara
             d.z = scale * fmaf(gl, sum.z - e[u].z, gs[u].z);
             d.w = scale * fmaf(gl, sum.w - e[u].w, gs[u].w);
             red_add_v4(row + c * 4, d);
+            if (LINX && linx_lane) red_add_f32(row + D, scale * gl);
           } else if (lin_lane) {
             red_add_v4(row + c * 4, make_float4(scale * gl, 0.f, 0.f, 0.f));
           }
@@ -640,7 +645,7 @@ static int launch_bwd_u(const EmbedBwdParams& p, cudaStream_t st) {
   return DR_OK;
 }
 
-template <int LPR, typename IdT, int U>
+template <int LPR, typename IdT, int U, bool LINX = false>
 static int launch_bwd_sp_u(const EmbedBwdParams& p, cudaStream_t st) {
   const int threads = 256, warps = threads / 32;
   const size_t smem = (size_t)p.S * (sizeof(void*) * 2 + sizeof(int64_t) * 2) + kMaxShardWorld * sizeof(void*);
@@ -649,6 +654,7 @@ static int launch_bwd_sp_u(const EmbedBwdParams& p, cudaStream_t st) {
   if (ctas > (int64_t)kNumSMs * per_sm) ctas = (int64_t)kNumSMs * per_sm;
   if (ctas < 1) ctas = 1;
   if (p.shard_world > 0) embed_fm_bwd_sp_kernel<LPR, IdT, U, true><<<(unsigned)ctas, threads, smem, st>>>(p);
+  else if (LINX) embed_fm_bwd_sp_kernel<LPR, IdT, U, false, LINX><<<(unsigned)ctas, threads, smem, st>>>(p);
   else embed_fm_bwd_sp_kernel<LPR, IdT, U, false><<<(unsigned)ctas, threads, smem, st>>>(p);
   DR_CUDA_LAUNCH_CHECK("embed_fm_bwd_sp");
   return DR_OK;
@@ -765,6 +771,17 @@ extern "C" int dr_embed_fm_bwd(const void* ids, int id_bytes, const int64_t* row
   p.g_bias = g_bias; p.scale = scale; p.row_stride = row_stride; p.lin_stride = lin_stride;
   p.lin_in_row = lin_in_row;
   cudaStream_t st = (cudaStream_t)stream;
+  if (g_tune_embed_bwd_linx && g_tune_embed_bwd_mode == 0 && lin_in_row && g_logit && lpr_for(D, 0) <= 8) {
+    const int lpr = lpr_for(D, 0);
+#define DR_BLINX(L) (id_bytes == 8 ? launch_bwd_sp_u<L, int64_t, 2, true>(p, st) : launch_bwd_sp_u<L, int32_t, 2, true>(p, st))
+    switch (lpr) {
+      case 1: return DR_BLINX(1);
+      case 2: return DR_BLINX(2);
+      case 4: return DR_BLINX(4);
+      default: return DR_BLINX(8);
+    }
+#undef DR_BLINX
+  }
   DR_DISPATCH_LPR(launch_bwd, p, st);
 }
 

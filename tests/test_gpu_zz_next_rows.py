@@ -801,3 +801,33 @@ def test_world1_sharded_two_tower_step_matches_oracle(temperature, accidental):
             assert np.abs(got - arena).max() <= 1e-5 * (np.abs(arena).max() + lr * (np.abs(gq).max() + np.abs(gc).max()) * b / 8)
     finally:
         dist.destroy_process_group()
+
+
+@unverified
+@pytest.mark.parametrize("B,rows,D", [(257, [50, 60, 70, 2, 7, 21], 16), (1000, [1000] * 26, 16), (99, [64] * 4, 12),
+                                      (65, [31] * 3, 28), (40, [9] * 5, 8)])
+def test_backward_linx_mapping_matches_default(B, rows, D):
+    """Knob embed_bwd_linx: same gradients as the default slot-parallel backward (up to the order of the atomics)."""
+    import importlib.util
+    import pathlib
+    from deep_recommenders_b200 import _lib
+    spec = importlib.util.spec_from_file_location("t_embed", pathlib.Path(__file__).resolve().parent / "test_gpu_embed.py")
+    te = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(te)
+    tables, lins, bias, ids = te.make_problem(B, rows, D, seed=B + D, oov_frac=0.1)
+    idt = torch.from_numpy(ids).cuda()
+    S = len(rows)
+    gs = torch.randn(B, S, D, device="cuda")
+    gl = torch.randn(B, device="cuda")
+    grads = []
+    try:
+        for linx in (0, 1):
+            _lib.tune("embed_bwd_linx", linx)
+            coll = te.to_collection(tables, lins, bias, layout="fused")
+            stack, logit = coll(idt)
+            ((stack * gs).sum() + (logit * gl).sum()).backward()
+            grads.append([g.detach().clone() for g in coll.grads()])
+    finally:
+        _lib.tune("embed_bwd_linx", 0)
+    for a, b in zip(*grads):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-5 * float(a.abs().max()) + 1e-7)
