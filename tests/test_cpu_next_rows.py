@@ -168,3 +168,41 @@ def test_oracle_reproduces_reference_retrieval_golden():
     want = R.factorized_topk_metric(q, g["idx_true"], top, g["metric_ks"].tolist())
     for tag in ("streaming", "brute", "dataset"):
         np.testing.assert_allclose(g[f"metric_{tag}"], want, rtol=1e-6)
+
+
+# ---- host side of the id pipeline: feature dict -> (ids [B, S], bags) without a GPU ----------------------------------
+def test_ids_and_bags_from_mixed_feature_dict_on_host():
+    import torch
+    from deep_recommenders_b200 import feature_column as fc
+    from deep_recommenders_b200.feature_column import PackedStrings, RaggedFeature
+    from deep_recommenders_b200.hashing import ids_and_bags, pack_strings
+    cols = [fc.categorical_column_with_hash_bucket("user_id", 6040),
+            fc.categorical_column_with_vocabulary_list("user_gender", ["F", "M"]),
+            fc.categorical_column_with_vocabulary_list("user_age", [1, 18, 25, 35, 45, 50, 56]),
+            fc.categorical_column_with_identity("slot", 10),
+            fc.categorical_column_with_vocabulary_list("movie_genres", ["Action", "Comedy", "Drama"])]
+    cats = {c.key: c for c in cols}
+    keys = [c.key for c in cols]
+    uid = [b"17", b"4711", b"1", b"6040"]
+    data, offs = pack_strings(uid)
+    gdata, goffs = pack_strings([b"Drama", b"Western", b"Action", b"Comedy", b"Drama"])
+    feats = {
+        "user_id": PackedStrings(data, offs),                          # what the TFRecord parser emits
+        "user_gender": np.asarray([["M"], ["F"], ["?"], ["M"]]),       # [B, 1] strings, one OOV
+        "user_age": np.asarray([18, 56, 2, 1]),
+        "slot": torch.tensor([0, 9, 10, -3]),                          # identity column: out of range -> -1
+        "movie_genres": RaggedFeature(PackedStrings(gdata, goffs), np.asarray([0, 2, 2, 3, 5])),
+    }
+    ids, bags = ids_and_bags(keys, cats, feats, torch.device("cpu"))
+    assert ids.shape == (4, 5) and ids.dtype == torch.int64
+    assert ids[:, 0].tolist() == F.hash_bucket_py(uid, 6040)
+    assert ids[:, 1].tolist() == [1, 0, -1, 1]
+    assert ids[:, 2].tolist() == [1, 6, -1, 0]
+    assert ids[:, 3].tolist() == [0, 9, -1, -1]
+    assert list(bags) == [4]
+    bag_ids, splits = bags[4]
+    assert bag_ids.tolist() == [2, -1, 0, 1, 2] and splits.tolist() == [0, 2, 2, 3, 5]
+    with pytest.raises(KeyError):
+        ids_and_bags(keys, cats, {k: v for k, v in feats.items() if k != "slot"}, torch.device("cpu"))
+    with pytest.raises(ValueError, match="one value per example"):
+        ids_and_bags(["user_age"], cats, {"user_age": np.zeros((4, 3), dtype=np.int64)}, torch.device("cpu"))
