@@ -272,6 +272,91 @@ extern "C" int dr_example_parse_feature(const uint8_t* buf, const int64_t* rec_o
   return DR_OK;
 }
 
+// All requested features of n records in ONE walk per record (the single-feature entry above walks a record once per
+// feature).  Same two-pass protocol: with values == NULL (or all its entries NULL) only row_splits[f][0..n],
+// total_values[f] and total_bytes[f] are written; then the caller allocates and calls again.
+extern "C" int dr_example_parse_batch(const uint8_t* buf, const int64_t* rec_off, const int64_t* rec_len, int64_t n,
+                                      int nfeat, const char* const* names, const int* kinds,
+                                      int64_t* const* row_splits, void* const* values, uint8_t* const* bytes,
+                                      int64_t* const* value_offsets, int64_t* total_values, int64_t* total_bytes) {
+  DR_REQUIRE(n >= 0 && nfeat >= 1 && nfeat <= 256 && names && kinds && row_splits && total_values && total_bytes,
+             DR_EINVAL, "dr_example_parse_batch: bad arguments (n=%lld nfeat=%d)", (long long)n, nfeat);
+  DR_REQUIRE(n == 0 || (buf && rec_off && rec_len), DR_EINVAL, "dr_example_parse_batch: null record index");
+  size_t name_len[256];
+  int64_t nv[256], nb[256], nv0[256], nb0[256];
+  for (int f = 0; f < nfeat; ++f) {
+    DR_REQUIRE(names[f] && kinds[f] >= 0 && kinds[f] <= 2 && row_splits[f], DR_EINVAL,
+               "dr_example_parse_batch: feature %d: null name / row_splits or kind outside 0..2", f);
+    name_len[f] = strlen(names[f]);
+    nv[f] = nb[f] = 0;
+    row_splits[f][0] = 0;
+    if (value_offsets && value_offsets[f]) value_offsets[f][0] = 0;
+  }
+  for (int64_t r = 0; r < n; ++r) {
+    for (int f = 0; f < nfeat; ++f) { nv0[f] = nv[f]; nb0[f] = nb[f]; }
+    tfr::Cursor ex{buf + rec_off[r], buf + rec_off[r] + rec_len[r], true};
+    while (ex.more()) {
+      const uint64_t tag = ex.varint();
+      if (!ex.ok) break;
+      if ((tag >> 3) != 1 || (tag & 7) != 2) { ex.skip((int)(tag & 7)); continue; }
+      tfr::Cursor feats = ex.sub();                       // Example.features
+      while (feats.more()) {
+        const uint64_t t2 = feats.varint();
+        if (!feats.ok) break;
+        if ((t2 >> 3) != 1 || (t2 & 7) != 2) { feats.skip((int)(t2 & 7)); continue; }
+        tfr::Cursor entry = feats.sub();                  // map entry {1: key, 2: Feature}
+        int f = -1;
+        tfr::Cursor value{entry.p, entry.p, true};
+        while (entry.more()) {
+          const uint64_t t3 = entry.varint();
+          if (!entry.ok) break;
+          if ((t3 >> 3) == 1 && (t3 & 7) == 2) {
+            tfr::Cursor key = entry.sub();
+            const size_t kl = key.ok ? (size_t)(key.end - key.p) : 0;
+            f = -1;
+            for (int g = 0; g < nfeat; ++g)
+              if (kl == name_len[g] && memcmp(key.p, names[g], kl) == 0) { f = g; break; }
+          } else if ((t3 >> 3) == 2 && (t3 & 7) == 2) {
+            value = entry.sub();
+          } else {
+            entry.skip((int)(t3 & 7));
+          }
+        }
+        DR_REQUIRE(entry.ok, DR_EINVAL, "dr_example_parse_batch: record %lld is not a valid tf.train.Example", (long long)r);
+        if (f < 0) continue;
+        nv[f] = nv0[f];                                   // a repeated map key: the later entry wins
+        nb[f] = nb0[f];
+        void* vals = values ? values[f] : nullptr;
+        uint8_t* by = bytes ? bytes[f] : nullptr;
+        int64_t* vo = value_offsets ? value_offsets[f] : nullptr;
+        const int kind = kinds[f];
+        const bool ok = tfr::walk_values(
+            value, kind,
+            [&](uint64_t bits) {
+              if (vals) {
+                if (kind == tfr::KIND_INT64) reinterpret_cast<int64_t*>(vals)[nv[f]] = (int64_t)bits;
+                else { const uint32_t b32 = (uint32_t)bits; memcpy(reinterpret_cast<float*>(vals) + nv[f], &b32, 4); }
+              }
+              ++nv[f];
+            },
+            [&](const uint8_t* p, int64_t len) {
+              if (by) memcpy(by + nb[f], p, (size_t)len);
+              nb[f] += len;
+              ++nv[f];
+              if (vo) vo[nv[f]] = nb[f];
+            });
+        DR_REQUIRE(ok, DR_EINVAL, "dr_example_parse_batch: feature '%s' of record %lld is malformed or not of the requested kind",
+                   names[f], (long long)r);
+      }
+      DR_REQUIRE(feats.ok, DR_EINVAL, "dr_example_parse_batch: record %lld is not a valid tf.train.Example", (long long)r);
+    }
+    DR_REQUIRE(ex.ok, DR_EINVAL, "dr_example_parse_batch: record %lld is not a valid tf.train.Example", (long long)r);
+    for (int f = 0; f < nfeat; ++f) row_splits[f][r + 1] = nv[f];
+  }
+  for (int f = 0; f < nfeat; ++f) { total_values[f] = nv[f]; total_bytes[f] = nb[f]; }
+  return DR_OK;
+}
+
 // categorical_column_with_vocabulary_list on string keys: position in the list, out-of-vocabulary -> default_id.
 extern "C" int dr_vocab_lookup_bytes_host(const uint8_t* bytes, const int64_t* offsets, int64_t n,
                                           const uint8_t* vocab_bytes, const int64_t* vocab_offsets, int64_t vocab_size,

@@ -139,15 +139,45 @@ class TFRecordFile:
                    "dr_example_parse_feature")
         return splits, vals[:nv]
 
+    def _columns(self, off, ln, items):
+        """All requested features in one native walk per record (dr_example_parse_batch), sizing pass then fill."""
+        import ctypes as C
+        n, nf = off.size, len(items)
+        names = (C.c_char_p * nf)(*[name.encode("utf-8") for name, _ in items])
+        kinds = (C.c_int * nf)(*[k for _, k in items])
+        splits = [np.empty(n + 1, dtype=np.int64) for _ in items]
+        tv, tb = np.zeros(nf, dtype=np.int64), np.zeros(nf, dtype=np.int64)
+        ptrs = lambda arrs: (C.c_void_p * nf)(*[None if a is None else a.ctypes.data for a in arrs])
+        head = (self._buf.ctypes.data, off.ctypes.data, ln.ctypes.data, n, nf, names, kinds, ptrs(splits))
+        _lib.check(self._lib.dr_example_parse_batch(*head, None, None, None, tv.ctypes.data, tb.ctypes.data),
+                   "dr_example_parse_batch")
+        vals, byts, voffs = [], [], []
+        for (_, k), nv, nb in zip(items, tv.tolist(), tb.tolist()):
+            if k == BYTES:
+                vals.append(None)
+                byts.append(np.empty(max(nb, 1), dtype=np.uint8))
+                voffs.append(np.empty(nv + 1, dtype=np.int64))
+            else:
+                vals.append(np.empty(max(nv, 1), dtype=np.int64 if k == INT64 else np.float32))
+                byts.append(None)
+                voffs.append(None)
+        _lib.check(self._lib.dr_example_parse_batch(*head, ptrs(vals), ptrs(byts), ptrs(voffs), tv.ctypes.data,
+                                                    tb.ctypes.data), "dr_example_parse_batch")
+        out = []
+        for (_, k), sp, v, b, vo, nv, nb in zip(items, splits, vals, byts, voffs, tv.tolist(), tb.tolist()):
+            out.append((sp, PackedStrings(b[:nb], vo) if k == BYTES else v[:nv]))
+        return out
+
     def parse(self, lo: int, hi: int, spec: Dict[str, Tuple[str, bool]]) -> Dict[str, object]:
         hi = min(hi, len(self))
         off = np.ascontiguousarray(self.offsets[lo:hi])
         ln = np.ascontiguousarray(self.lengths[lo:hi])
-        out = {}
-        for name, (dtype, fixed) in spec.items():
+        for name, (dtype, _) in spec.items():
             if dtype not in _KINDS:
                 raise ValueError(f"feature {name!r}: unsupported dtype {dtype!r}")
-            splits, vals = self._column(off, ln, name, _KINDS[dtype])
+        items = [(name, _KINDS[dtype]) for name, (dtype, _) in spec.items()]
+        out = {}
+        for (name, (dtype, fixed)), (splits, vals) in zip(spec.items(), self._columns(off, ln, items) if items else []):
             if fixed:
                 if not np.array_equal(splits, np.arange(off.size + 1)):
                     bad = int(np.flatnonzero(np.diff(splits) != 1)[0])

@@ -336,6 +336,14 @@ int64_t dr_tfrecord_index(const uint8_t* buf, int64_t nbytes, int verify_crc, in
 int dr_example_parse_feature(const uint8_t* buf, const int64_t* rec_off, const int64_t* rec_len, int64_t n,
                              const char* name, int kind, int64_t* row_splits, void* values, uint8_t* bytes,
                              int64_t* value_offsets, int64_t* total_values, int64_t* total_bytes);
+/* dr_example_parse_batch: the same for nfeat features in ONE walk per record (what the dataset classes use):
+ * names / kinds [nfeat]; row_splits / values / bytes / value_offsets are arrays of nfeat pointers with the per-feature
+ * meaning above (values entry for int64 / float features, bytes + value_offsets entries for string features, unused
+ * entries NULL); total_values / total_bytes [nfeat].  Sizing pass: values == bytes == value_offsets == NULL.      */
+int dr_example_parse_batch(const uint8_t* buf, const int64_t* rec_off, const int64_t* rec_len, int64_t n, int nfeat,
+                           const char* const* names, const int* kinds, int64_t* const* row_splits,
+                           void* const* values, uint8_t* const* bytes, int64_t* const* value_offsets,
+                           int64_t* total_values, int64_t* total_bytes);
 int dr_vocab_lookup_bytes_host(const uint8_t* bytes, const int64_t* offsets, int64_t n, const uint8_t* vocab_bytes,
                                const int64_t* vocab_offsets, int64_t vocab_size, int64_t default_id, int64_t* out_ids);
 

@@ -204,3 +204,33 @@ def test_movielens_classes_on_a_synthetic_ml1m(tmp_path):
     assert gids.tolist() == [ml.gender_vocab.index(s.decode()) for s in feats["user_gender"].tolist()]
     oov = vocabulary_ids(gender, feats["movie_genres"].values)          # the examples' always-OOV genre slot
     assert set(oov.tolist()) == {-1}
+
+
+def test_batch_parser_equals_single_feature_parser_and_later_map_entry_wins(tmp_path):
+    rng = np.random.default_rng(3)
+    recs = []
+    for i in range(64):
+        recs.append(serialize_example({"Age": [int(rng.integers(-9, 9))], "UserID": [bytes(rng.integers(65, 91, size=int(rng.integers(0, 9)), dtype=np.uint8))],
+                                       "Genres": [b"g%d" % j for j in range(int(rng.integers(0, 4)))],
+                                       "w": [float(x) for x in rng.standard_normal(int(rng.integers(0, 3)))]}))
+    # a record whose map repeats the key "Age": protobuf map semantics = the later entry wins
+    def ld(field, payload):
+        return bytes([(field << 3) | 2, len(payload)]) + payload
+    entry = lambda k, feat: ld(1, ld(1, k) + ld(2, feat))
+    recs.append(ld(1, entry(b"Age", ld(3, ld(1, bytes([7])))) + entry(b"UserID", ld(1, ld(1, b"u"))) + entry(b"Age", ld(3, ld(1, bytes([9]))))))
+    path = str(tmp_path / "b.tfrecords")
+    _write(path, recs)
+    f = TFRecordFile(path)
+    n = len(recs)
+    off, ln = np.ascontiguousarray(f.offsets), np.ascontiguousarray(f.lengths)
+    items = [("Age", 0), ("UserID", 1), ("Genres", 1), ("w", 2), ("absent", 0)]
+    batch = f._columns(off, ln, items)
+    for (name, kind), (sp_b, v_b) in zip(items, batch):
+        sp_s, v_s = f._column(off, ln, name, kind)
+        assert np.array_equal(sp_b, sp_s), name
+        if isinstance(v_b, PackedStrings):
+            assert v_b.tolist() == v_s.tolist(), name
+        else:
+            assert np.array_equal(v_b, v_s), name
+    out = f.parse(n - 1, n, {"Age": ("int64", True), "UserID": ("string", True)})
+    assert out["Age"].tolist() == [9] and out["UserID"].tolist() == [b"u"]
