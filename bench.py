@@ -145,6 +145,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly (for ncu launch lists)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
                     help="c2 (default, the headline config; weak scaling) or c5 (100M rows x D=128, global batch 65536)")
+    ap.add_argument("--ids", default="uniform", choices=["uniform", "zipf"],
+                    help="synthetic id distribution: uniform (headline) or Zipf(1.05) clipped to the table (SURVEY 8d second run)")
     ap.add_argument("--tune", action="append", default=[], metavar="KNOB=VALUE",
                     help="developer knob of libdeeprec_b200.so (dr_tune_set), e.g. --tune tc_min_n=32; recorded in the line")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
@@ -221,7 +223,13 @@ def main():
     # synthetic MovieLens-shaped batches: pool resident in HBM (value) and in pinned host memory (e2e)
     NP = 8
     gen = torch.Generator(device=dev).manual_seed(100 + rank)
-    ids_pool = [torch.randint(0, W["rows"], (B, S), device=dev, generator=gen) for _ in range(NP)]
+    if args.ids == "zipf":      # skewed ids: rank-1 rows are hit thousands of times per batch (L2 reuse, atomic contention)
+        import numpy as np
+        rng = np.random.default_rng(100 + rank)
+        ids_pool = [torch.from_numpy(np.minimum(rng.zipf(1.05, size=(B, S)) - 1, W["rows"] - 1).astype(np.int64)).to(dev)
+                    for _ in range(NP)]
+    else:
+        ids_pool = [torch.randint(0, W["rows"], (B, S), device=dev, generator=gen) for _ in range(NP)]
     lab_pool = [torch.randint(0, 2, (B,), device=dev, generator=gen).float() for _ in range(NP)]
     host_ids = [t.cpu().pin_memory() for t in ids_pool]
     host_lab = [t.cpu().pin_memory() for t in lab_pool]
@@ -307,7 +315,9 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": "examples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if args.workload == "c5" else "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world, args.workload),
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(workload_config(world, args.workload),
+                           ids="uniform int64" if args.ids == "uniform" else "Zipf(1.05) clipped to the table, int64"),
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(trainer.launches_per_step * args.steps),
             "launches_per_step": int(trainer.launches_per_step), "roofline": roofline, "kernel_ms": shares,
             "cpu_baseline": cpu, "final_loss": final_loss,
