@@ -12,7 +12,8 @@ $B                               > gpurun_out/r02_bench_default.log 2>&1
 $B --tune tc_min_n=32            > gpurun_out/r02_bench_tcmin32.log 2>&1      # N = 32 layers on the tcgen05 core
 $B --tune embed_bwd_linx=1       > gpurun_out/r02_bench_bwdlinx.log 2>&1
 DR_GEMM=tc $B                    > gpurun_out/r02_bench_tc1.log 2>&1          # pre-split planes, for the record
-for f in default tcmin32 bwdlinx tc1; do
+timeout 120 $B --ids zipf        > gpurun_out/r02_bench_zipf.log 2>&1         # SURVEY 8d second run (skewed ids)
+for f in default tcmin32 bwdlinx tc1 zipf; do
   python - "$f" <<'PY'
 import json, sys
 tag = sys.argv[1]
