@@ -97,3 +97,52 @@ def test_bench_reference_arm_json_contract():
     assert line["metric"].startswith("examples/sec (fwd+bwd) DeepFM")
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["higher_is_better"] is True
+
+
+def test_ctypes_signatures_match_the_header_arity_and_pointer_kinds():
+    """Every entry of _lib._SIGS must have exactly the parameters its declaration in include/deeprec_b200.h has, with
+    pointers bound as pointers, 64-bit integers as c_int64, ints as c_int and floats as c_float (an ABI drift here
+    corrupts arguments silently at run time)."""
+    import ctypes as C
+    import re
+    from deep_recommenders_b200 import _lib
+    text = re.sub(r"/\*.*?\*/", "", _lib.HEADER_PATH.read_text(), flags=re.S)
+    decls = {m.group(1): m.group(2) for m in re.finditer(r"\b(dr_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S)}
+    assert set(decls) == set(_lib._SIGS)
+    for name, params in decls.items():
+        plist = [p.strip() for p in params.split(",")] if params.strip() not in ("", "void") else []
+        sig = _lib._SIGS[name]
+        assert len(plist) == len(sig), f"{name}: header has {len(plist)} parameters, ctypes table {len(sig)}"
+        for p, ct in zip(plist, sig):
+            if "*" in p:
+                assert ct in (C.c_void_p, C.c_char_p), f"{name}: '{p}' must be bound as a pointer, got {ct}"
+            elif re.match(r"(const\s+)?(int64_t|uint64_t)\b", p):
+                assert ct in (C.c_int64, C.c_uint64), f"{name}: '{p}' must be 64-bit, got {ct}"
+            elif re.match(r"(const\s+)?float\b", p):
+                assert ct is C.c_float, f"{name}: '{p}' must be c_float, got {ct}"
+            elif re.match(r"(const\s+)?int\b", p):
+                assert ct is C.c_int, f"{name}: '{p}' must be c_int, got {ct}"
+            else:
+                raise AssertionError(f"{name}: unclassified parameter '{p}'")
+
+
+def test_every_call_site_passes_the_declared_number_of_arguments():
+    """Static check of all `lib.dr_*(...)` call sites in the package, tests and tools (GPU-only code paths cannot run
+    here; a wrong argument count would only surface on the GPU box)."""
+    import ast
+    import pathlib
+    from deep_recommenders_b200 import _lib
+    root = pathlib.Path(__file__).resolve().parent.parent
+    files = list((root / "deep_recommenders_b200").rglob("*.py")) + list((root / "tests").glob("*.py")) + \
+        list((root / "tools").glob("*.py")) + [root / "bench.py", root / "__graft_entry__.py"]
+    checked = 0
+    for f in files:
+        for node in ast.walk(ast.parse(f.read_text())):
+            if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and node.func.attr in _lib._SIGS:
+                if any(isinstance(a, ast.Starred) for a in node.args) or node.keywords:
+                    continue
+                want = len(_lib._SIGS[node.func.attr])
+                assert len(node.args) == want, f"{f.name}:{node.lineno}: {node.func.attr} called with {len(node.args)} " \
+                                               f"arguments, the C-ABI takes {want}"
+                checked += 1
+    assert checked > 60
