@@ -10,4 +10,6 @@ B="bench.py --gpus $N --steps 20 --warmup 5"
 $T --master-port 29511 $B                                   > gpurun_out/r02_n${N}_default.log 2>&1
 $T --master-port 29512 $B --tune embed_fwd_linx_shard=1     > gpurun_out/r02_n${N}_linxshard.log 2>&1
 $T --master-port 29513 $B --workload c5                     > gpurun_out/r02_n${N}_c5.log 2>&1
+$T --master-port 29514 tools/bench_two_tower.py             > gpurun_out/r02_n${N}_c4.log 2>&1
+grep '^{' gpurun_out/r02_n${N}_c4.log | tail -1 | cut -c1-300
 for f in default linxshard c5; do grep '^{' gpurun_out/r02_n${N}_$f.log | tail -1 | cut -c1-400; done
