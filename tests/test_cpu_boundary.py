@@ -146,3 +146,34 @@ def test_every_call_site_passes_the_declared_number_of_arguments():
                                                f"arguments, the C-ABI takes {want}"
                 checked += 1
     assert checked > 60
+
+
+def test_plain_c_program_links_and_calls_the_library(tmp_path):
+    """The boundary is a C ABI: a C99 program compiled with gcc against include/deeprec_b200.h links to the .so and
+    gets the same answers as the Python binding (host entry points only; no GPU, no torch, no Python)."""
+    import pathlib
+    import shutil
+    import subprocess
+    from deep_recommenders_b200 import _lib
+    from deep_recommenders_b200.hashing import hash_bucket
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    root = pathlib.Path(__file__).resolve().parent.parent
+    libdir = _lib.LIB_PATH.parent
+    exe = tmp_path / "c_abi_host_demo"
+    cmd = [gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", str(root / "include"),
+           str(root / "examples" / "c_abi_host_demo.c"), "-L", str(libdir), "-ldeeprec_b200",
+           f"-Wl,-rpath,{libdir}", "-o", str(exe)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = r.stdout.strip().splitlines()
+    assert lines[0] == "version 100"
+    assert lines[1] == "to_hash_bucket_fast 0 2 2"                       # TF API docs example
+    assert lines[2] == "fingerprint64(abc) 2640714258260161385"
+    assert lines[3] == "crc32c(123456789) e3069283"
+    want = hash_bucket(np.array([6040, -1], dtype=np.int64), 1000).tolist()
+    assert lines[4] == f"hash_bucket_i64 {want[0]} {want[1]}"
+    assert lines[5].startswith("dr_gather_fwd(D=6) rc=-1") and "D=6" in lines[5]
