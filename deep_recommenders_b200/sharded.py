@@ -177,6 +177,40 @@ class ShardedDeepFMTrainStep:
         self._copy_stream = torch.cuda.Stream(device=dev)
         self._staged = None
 
+    # ---- checkpoint: one file per rank + metadata on rank 0; loadable by any number of ranks (checkpoint.py) -------
+    def get_config(self) -> dict:
+        return {"class": "ShardedDeepFMTrainStep", "rows": list(self.emb.rows_list), "dim": self.D,
+                "dnn_units": [l.units for l in self.layers[:-1]], "batch_size": self.B, "lr": self.lr,
+                "exchange": self.exchange, "row_width": self.emb.vdim, "lin_in_row": bool(self.emb.lin_in_row)}
+
+    def save(self, prefix: str) -> None:
+        from . import checkpoint
+        torch.cuda.synchronize()
+        arrays = {"weight": self.emb.weight}
+        if not self.emb.lin_in_row:
+            arrays["lin"] = self.emb.lin
+        checkpoint.save_rows(prefix, self.rank, self.world, self.emb.total_rows, arrays)
+        if self.rank == 0:
+            checkpoint.save_meta(prefix, self.get_config(), {"flat": self.flat})
+        dist.barrier(group=self.group)
+
+    def load(self, prefix: str) -> None:
+        """Restore from a checkpoint of the same model written by ANY world size (rows are re-sharded while loading)."""
+        from . import checkpoint
+        meta = checkpoint.load_meta(prefix)
+        cfg, mine = meta["config"], self.get_config()
+        for k in ("rows", "dim", "dnn_units", "row_width", "lin_in_row"):
+            if cfg[k] != mine[k]:
+                raise ValueError(f"checkpoint {prefix!r} was written for {k}={cfg[k]}, this model has {k}={mine[k]}")
+        got = checkpoint.load_rows(prefix, self.rank, self.world)
+        with torch.no_grad():
+            self.emb.weight.copy_(got["weight"].to(self.dev))
+            if not self.emb.lin_in_row:
+                self.emb.lin.copy_(got["lin"].to(self.dev))
+            self.flat.copy_(meta["replicated"]["flat"].to(self.dev))
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+
     def _a2a(self, out, inp):
         dist.all_to_all_single(out, inp, group=self.group)
 

@@ -831,3 +831,43 @@ def test_backward_linx_mapping_matches_default(B, rows, D):
         _lib.tune("embed_bwd_linx", 0)
     for a, b in zip(*grads):
         assert torch.allclose(a, b, rtol=1e-5, atol=1e-5 * float(a.abs().max()) + 1e-7)
+
+
+@unverified
+@pytest.mark.parametrize("D", [16, 128])
+def test_world1_sharded_trainer_checkpoint_round_trip(tmp_path, D):
+    import socket
+    import torch.distributed as dist
+    from deep_recommenders_b200 import feature_column as fc
+    from deep_recommenders_b200.sharded import ShardedDeepFMTrainStep
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    _os.environ["MASTER_ADDR"], _os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        rows, B = [300, 7, 50], 128
+        cols = [fc.categorical_column_with_identity(f"c{i}", r) for i, r in enumerate(rows)]
+        mk = lambda seed: ShardedDeepFMTrainStep(cols, D, [32, 8], batch_size=B, lr=0.05, seed=seed, device="cuda",
+                                                 exchange="p2p", use_graph=False)
+        a = mk(3)
+        with torch.no_grad():
+            a.emb.lin_view().normal_(0, 0.1)
+        ids = torch.stack([torch.randint(0, r, (B,), device="cuda") for r in rows], dim=1)
+        lab = torch.randint(0, 2, (B,), device="cuda").float()
+        a.step(ids, lab)
+        prefix = str(tmp_path / "ckpt")
+        a.save(prefix)
+        b = mk(99)                                     # different initialisation, then restored
+        b.load(prefix)
+        assert torch.equal(a.emb.weight, b.emb.weight) and torch.equal(a.flat, b.flat)
+        assert torch.equal(a.emb.lin_view(), b.emb.lin_view())
+        assert a.get_config() == b.get_config()
+        la, lb = float(a.step(ids, lab).item()), float(b.step(ids, lab).item())
+        assert la == lb
+        with pytest.raises(ValueError, match="was written for"):
+            ShardedDeepFMTrainStep(cols, D, [16, 8], batch_size=B, lr=0.05, seed=1, device="cuda", exchange="p2p",
+                                   use_graph=False).load(prefix)
+    finally:
+        dist.destroy_process_group()
