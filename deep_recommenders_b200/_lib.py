@@ -70,6 +70,7 @@ _SIGS = {
     "dr_tfrecord_index": [_p, _i64, _i, _p, _p, _i64],
     "dr_example_parse_feature": [_p, _p, _p, _i64, C.c_char_p, _i, _p, _p, _p, _p, _p, _p],
     "dr_example_parse_batch": [_p, _p, _p, _i64, _i, _p, _p, _p, _p, _p, _p, _p, _p],
+    "dr_set_host_threads": [_i],
     "dr_vocab_lookup_bytes_host": [_p, _p, _i64, _p, _p, _i64, _i64, _p],
     "dr_topk_rows": [_p, _i64, _i64, _i64, _i, _p, _p, _p],
     "dr_take_long_axis": [_p, _i, _i64, _i64, _i64, _p, _i, _p, _p],

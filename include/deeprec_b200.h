@@ -344,6 +344,9 @@ int dr_example_parse_batch(const uint8_t* buf, const int64_t* rec_off, const int
                            const char* const* names, const int* kinds, int64_t* const* row_splits,
                            void* const* values, uint8_t* const* bytes, int64_t* const* value_offsets,
                            int64_t* total_values, int64_t* total_bytes);
+/* Host threads used by dr_example_parse_batch on large batches (tf.data num_parallel_calls): 1 = serial (default),
+ * 0 = min(hardware threads, 8), n = n threads.  The output does not depend on it.                              */
+int dr_set_host_threads(int n);
 int dr_vocab_lookup_bytes_host(const uint8_t* bytes, const int64_t* offsets, int64_t n, const uint8_t* vocab_bytes,
                                const int64_t* vocab_offsets, int64_t vocab_size, int64_t default_id, int64_t* out_ids);
 

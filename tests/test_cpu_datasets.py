@@ -234,3 +234,44 @@ def test_batch_parser_equals_single_feature_parser_and_later_map_entry_wins(tmp_
             assert np.array_equal(v_b, v_s), name
     out = f.parse(n - 1, n, {"Age": ("int64", True), "UserID": ("string", True)})
     assert out["Age"].tolist() == [9] and out["UserID"].tolist() == [b"u"]
+
+
+def test_threaded_batch_parse_is_identical_to_serial(tmp_path, lib):
+    rng = np.random.default_rng(9)
+    n = 20000
+    recs = [serialize_example({"Age": [int(rng.integers(-99, 99))],
+                               "UserID": [b"%d" % int(rng.integers(0, 10 ** 6))],
+                               "Genres": [b"g%d" % j for j in range(int(rng.integers(0, 4)))],
+                               "w": [float(i)] * int(rng.integers(0, 3))}) for i in range(n)]
+    path = str(tmp_path / "big.tfrecords")
+    _write(path, recs)
+    f = TFRecordFile(path)
+    spec = {"Age": ("int64", True), "UserID": ("string", True), "Genres": ("string", False), "w": ("float32", False)}
+    outs = []
+    try:
+        for threads in (1, 2, 7):
+            assert lib.dr_set_host_threads(threads) == 0
+            outs.append(f.parse(0, n, spec))
+    finally:
+        lib.dr_set_host_threads(1)
+    a = outs[0]
+    for b in outs[1:]:
+        assert np.array_equal(a["Age"], b["Age"])
+        assert np.array_equal(a["UserID"].data, b["UserID"].data) and np.array_equal(a["UserID"].offsets, b["UserID"].offsets)
+        assert np.array_equal(a["Genres"].row_splits, b["Genres"].row_splits)
+        assert np.array_equal(a["Genres"].values.offsets, b["Genres"].values.offsets)
+        assert np.array_equal(a["Genres"].values.data, b["Genres"].values.data)
+        assert np.array_equal(a["w"].values, b["w"].values) and np.array_equal(a["w"].row_splits, b["w"].row_splits)
+    assert a["UserID"].tolist()[:3] == [r for r in (TFRecordFile(path).parse(0, 3, {"UserID": ("string", True)})["UserID"].tolist())]
+    # an error in a later range is reported with its record number, whichever thread finds it
+    bad = list(recs)
+    bad[15000] = b"\x0a\x05abc"                                     # truncated length-delimited field
+    _write(path, bad)
+    g = TFRecordFile(path)
+    lib.dr_set_host_threads(4)
+    try:
+        with pytest.raises(ValueError, match="record 15000"):
+            g.parse(0, n, {"Age": ("int64", False)})
+    finally:
+        lib.dr_set_host_threads(1)
+    assert lib.dr_set_host_threads(-1) == -1

@@ -45,10 +45,19 @@ def main():
         hash_bucket(ex["UserID"], 6040)
         hash_bucket(ex["MovieID"], 3952)
     t_ids = time.perf_counter() - t0
+    lib = f._lib
+    big = {}
+    for threads in (1, 2, 4, 8):                          # one call over all records (batch 65536-style parsing)
+        lib.dr_set_host_threads(threads)
+        t0 = time.perf_counter()
+        f.parse(0, n, MovieLens._SPEC)
+        big[str(threads)] = round(n / (time.perf_counter() - t0))
+    lib.dr_set_host_threads(1)
     out = dict(records=n, file_mb=round(size / 1e6, 1), write_s=round(t_write, 2),
                index_crc_s=round(t_index, 3), index_gb_per_s=round(size / t_index / 1e9, 2),
                parse_all_10_features_s=round(t_parse, 3), parse_records_per_s=round(n / t_parse),
-               parse_two_ids_and_farmhash_s=round(t_ids, 3), ids_records_per_s=round(n / t_ids), threads=1)
+               parse_two_ids_and_farmhash_s=round(t_ids, 3), ids_records_per_s=round(n / t_ids),
+               batch_1024_threads=1, one_call_records_per_s_by_threads=big, host_cpus=os.cpu_count())
     try:        # context: the protobuf library's Python API on the same records (one Example at a time)
         sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
         from test_cpu_datasets import _example_classes
