@@ -26,6 +26,7 @@
 #include "gemm.cuh"
 #include <cuda.h>
 #include <float.h>
+#include <string.h>
 
 namespace dr {
 
@@ -71,6 +72,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       ::"r"(smem_u32(bar)), "r"(parity)
       : "memory");
 }
+// ---- per-role wait-time profile (diagnostic instantiation only: template flag PROF, knob gemm_prof) ------------------
+// slots: 0 producer waits for a free stage, 1 splitter waits for TMA data, 2 splitter splits, 3 MMA waits for operands,
+// 4 MMA waits for a free accumulator, 5 epilogue waits for the accumulator, 6 epilogue body, 7 kernel span (CTA 0..n
+// summed), 8 CTAs, 9 k-blocks issued.  Cycles of one representative thread per role, summed over CTAs.
+__device__ unsigned long long g_tc_prof[16];
+
+template <bool PROF>
+__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, unsigned long long& acc) {
+  if (PROF) {
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += (unsigned long long)(clock64() - t0);
+  } else {
+    mbar_wait(bar, parity);
+  }
+}
+
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -253,7 +271,7 @@ __device__ __forceinline__ TcItem tc_decode(int64_t item, int64_t n_tiles, int64
 
 // Persistent, warp-specialised: the accumulator is double buffered in TMEM (2 x BN columns) so the
 // epilogue of item j overlaps the TMA/MMA main loop of item j+1.
-template <int BN, int STAGES, bool A_MN, bool B_MN, bool INSPLIT = false>
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool INSPLIT = false, bool PROF = false>
 __global__ void __launch_bounds__(INSPLIT ? TC_THREADS_INSPLIT : TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
@@ -270,6 +288,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t kblocks = (a.K + TC_BK - 1) / TC_BK;
+  const long long prof_t0 = PROF ? clock64() : 0;
+  unsigned long long pw0 = 0, pw1 = 0, pw2 = 0;   // per-thread wait / work accumulators (PROF only)
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAh) : "memory");
@@ -308,7 +328,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         for (int i = 0; i < t.nkb; ++i, ++it) {
           const int s = (int)(it % STAGES);
           const uint32_t ph = (it / STAGES) & 1u;
-          mbar_wait(&empty_bar[s], ph ^ 1u);
+          mbar_wait_t<PROF>(&empty_bar[s], ph ^ 1u, pw0);
           // INSPLIT: only the raw fp32 tiles travel (tmAh / tmBh map the source tensors); they land in the hi slots
           mbar_expect_tx(&full_bar[s], (uint32_t)(INSPLIT ? (A_TILE + B_TILE) : STAGE));
           uint8_t* st = smem + (size_t)s * STAGE;
@@ -345,13 +365,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       for (int64_t item = blockIdx.x; item < total_items; item += gridDim.x, ++j) {
         const TcItem t = tc_decode(item, n_tiles, m_tiles, kblocks, per, BN);
         const uint32_t as = j & 1u, aph = (j >> 1) & 1u;
-        mbar_wait(&tmem_empty_bar[as], aph ^ 1u);      // epilogue has drained this accumulator
+        mbar_wait_t<PROF>(&tmem_empty_bar[as], aph ^ 1u, pw1);      // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * (uint32_t)BN;
         for (int i = 0; i < t.nkb; ++i, ++it) {
           const int s = (int)(it % STAGES);
           const uint32_t ph = (it / STAGES) & 1u;
-          mbar_wait(INSPLIT ? &split_bar[s] : &full_bar[s], ph);
+          mbar_wait_t<PROF>(INSPLIT ? &split_bar[s] : &full_bar[s], ph, pw0);
+          if (PROF) ++pw2;
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)s * STAGE);
           const uint32_t sb = sa + 2 * A_TILE;
@@ -389,12 +410,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       for (int i = 0; i < t.nkb; ++i, ++it) {
         const int s = (int)(it % STAGES);
         const uint32_t ph = (it / STAGES) & 1u;
-        mbar_wait(&full_bar[s], ph);          // TMA bytes of this stage have landed (visible to generic loads)
+        mbar_wait_t<PROF>(&full_bar[s], ph, pw0);   // TMA bytes of this stage have landed (visible to generic loads)
+        const long long ts0 = PROF ? clock64() : 0;
         uint8_t* st = smem + (size_t)s * STAGE;
         split_tile_inplace<A_TILE, NSPLIT>(st, st + A_TILE, tid);
         split_tile_inplace<B_TILE, NSPLIT>(st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, tid);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
         mbar_arrive(&split_bar[s]);
+        if (PROF) pw1 += (unsigned long long)(clock64() - ts0);
       }
     }
   } else {
@@ -405,7 +428,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     for (int64_t item = blockIdx.x; item < total_items; item += gridDim.x, ++j) {
       const TcItem t = tc_decode(item, n_tiles, m_tiles, kblocks, per, BN);
       const uint32_t as = j & 1u, aph = (j >> 1) & 1u;
-      mbar_wait(&tmem_full_bar[as], aph);
+      mbar_wait_t<PROF>(&tmem_full_bar[as], aph, pw0);
+      const long long te0 = PROF ? clock64() : 0;
       tc_fence_after();
       const int64_t m = t.m0 + q * 32 + lane;
 #pragma unroll 1
@@ -437,7 +461,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty_bar[as]);      // this thread is done reading accumulator stage `as`
+      if (PROF) pw1 += (unsigned long long)(clock64() - te0);
     }
+  }
+  if (PROF) {   // one representative thread per role adds its counters
+    if (warp == 0 && lane == 0) {
+      atomicAdd(&g_tc_prof[0], pw0);
+      atomicAdd(&g_tc_prof[7], (unsigned long long)(clock64() - prof_t0));
+      atomicAdd(&g_tc_prof[8], 1ull);
+    }
+    if (warp == 1 && lane == 0) { atomicAdd(&g_tc_prof[3], pw0); atomicAdd(&g_tc_prof[4], pw1); atomicAdd(&g_tc_prof[9], pw2); }
+    if (threadIdx.x == 64) { atomicAdd(&g_tc_prof[5], pw0); atomicAdd(&g_tc_prof[6], pw1); }
+    if (INSPLIT && threadIdx.x == TC_THREADS) { atomicAdd(&g_tc_prof[1], pw0); atomicAdd(&g_tc_prof[2], pw1); }
   }
   tc_fence_before();
   __syncthreads();
@@ -537,11 +572,15 @@ bool gemm_tc_eligible(const GemmArgs& a, bool ta, bool tb) {
   return true;
 }
 
+int g_tune_gemm_prof = 0;   // 1 = launch the instrumented instantiation (BN = 128 INSPLIT only); read with dr_gemm_prof_read
+
 template <int BN, int STAGES, bool A_MN, bool B_MN, bool INSPLIT = false>
 static int launch_tc(const CUtensorMap* tms, const GemmArgs& a, cudaStream_t st) {
   constexpr int STAGE = 2 * TC_BM * TC_BK * 4 + 2 * BN * TC_BK * 4;
   const size_t smem = (size_t)STAGES * STAGE + 1024;
-  auto k = gemm_tc_kernel<BN, STAGES, A_MN, B_MN, INSPLIT>;
+  constexpr bool kProfInst = INSPLIT && BN == 128;
+  auto k = (kProfInst && g_tune_gemm_prof) ? gemm_tc_kernel<BN, STAGES, A_MN, B_MN, INSPLIT, kProfInst>
+                                           : gemm_tc_kernel<BN, STAGES, A_MN, B_MN, INSPLIT, false>;
   DR_CUDA_CALL(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t m_tiles = (a.M + TC_BM - 1) / TC_BM, n_tiles = (a.N + BN - 1) / BN;
   const int64_t kblocks = (a.K + TC_BK - 1) / TC_BK;
@@ -690,6 +729,18 @@ int gemm_tc_launch(const GemmArgs& a0, bool ta, bool tb, cudaStream_t st) {
 }
 
 }  // namespace dr
+
+extern "C" int dr_gemm_prof_read(uint64_t* out16, int reset) {
+  DR_REQUIRE(out16, DR_EINVAL, "dr_gemm_prof_read: null output");
+  unsigned long long h[16];
+  DR_CUDA_CALL(cudaMemcpyFromSymbol(h, dr::g_tc_prof, sizeof(h)));
+  for (int i = 0; i < 16; ++i) out16[i] = (uint64_t)h[i];
+  if (reset) {
+    memset(h, 0, sizeof(h));
+    DR_CUDA_CALL(cudaMemcpyToSymbol(dr::g_tc_prof, h, sizeof(h)));
+  }
+  return DR_OK;
+}
 
 extern "C" int dr_gemm_plane_cache(int enable) {
   dr::g_nplanes = 0;

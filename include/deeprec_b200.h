@@ -390,6 +390,13 @@ int dr_gemm_plane_cache(int enable);
 /* Developer hook (not reference-facing): set a kernel tuning knob by name, e.g.
  * "embed_fwd_unroll", "embed_block", "embed_bwd_agg", "gemm_splitk".                     */
 int dr_tune_set(const char* key, int value);
+/* Developer hook: per-role wait cycles of the tcgen05 GEMM core, accumulated over the launches made while the knob
+ * `gemm_prof` is 1 (instrumented instantiation: BN = 128, split in kernel).  out16 (HOST pointer, 16 counters):
+ * 0 producer waits for a free stage, 1 splitter waits for TMA data, 2 splitter work, 3 MMA issuer waits for operands,
+ * 4 MMA issuer waits for a free accumulator, 5 epilogue waits for the accumulator, 6 epilogue work, 7 kernel span,
+ * 8 CTAs, 9 k-blocks issued (cycles of one thread per role, summed over CTAs).  reset != 0 clears the counters.  */
+int dr_gemm_prof_read(uint64_t* out16, int reset);
+
 /* Developer hook: C[M,N] = op(A) @ op(B); transA: A stored [K,M]; transB: B stored [N,K].  */
 int dr_debug_gemm(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
                   int transA, int transB, void* stream);

@@ -25,6 +25,8 @@ except Exception as e:
     print(tag, "FAILED", e)
 PY
 done
-# 3. launch list of the default step (shares, not absolutes)
+# 3. where the tcgen05 GEMM core waits (per-role mbarrier wait shares of the instrumented instantiation)
+timeout 120 python -u tools/gemm_prof.py > gpurun_out/r02_gemm_prof.log 2>&1; cat gpurun_out/r02_gemm_prof.log | cut -c1-600
+# 4. launch list of the default step (shares, not absolutes)
 bash tools/ncu_launches.sh r02a > /dev/null 2>&1; python -c "
 import json; [print(o) for o in sorted(json.load(open('gpurun_out/launches_r02a.json')), key=lambda o: -o['share'])[:12]]"
