@@ -17,9 +17,8 @@ The global loss (reference Retrieval.call, reduction SUM: sbcnm.py:100-102,151) 
 the collectives of this step also order every rank's remote reads before any remote update.
 Towers are the embedding tables themselves (plain DSSM); MLP towers stay single-GPU (TwoTower) in this round.
 
-STATUS: written at the end of round 1 after the GPU budget was spent -- the exchange plan is covered by the
-world-2 gloo test (tests/test_two_tower_protocol_cpu.py), the CUDA step by a test that only runs with
-DR_UNVERIFIED=1 until it has been run on a GPU (tests/test_gpu_zz_next_rows.py).
+Tests: the exchange plan by the world-2 gloo test (tests/test_two_tower_protocol_cpu.py); the CUDA step at world 1 by
+tests/test_gpu_zz_next_rows.py and at world 2 by tests/test_gpu_sharded.py (torchrun worker).
 """
 from __future__ import annotations
 

@@ -4,8 +4,9 @@
 N=${1:-2}
 mkdir -p gpurun_out
 T="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
-python -u -m pytest tests/test_gpu_sharded.py -m gpu -q --timeout=600 -rf --tb=short -p no:cacheprovider \
-    > gpurun_out/r02_world2_tests.log 2>&1; tail -2 gpurun_out/r02_world2_tests.log
+python -u -m pytest tests/test_gpu_sharded.py -m gpu -v --timeout=1000 -rfP --tb=short -p no:cacheprovider \
+    > gpurun_out/r02_world${N}_tests.log 2>&1; tail -2 gpurun_out/r02_world${N}_tests.log
+grep -a " ok: \|SHARDED_OK\|Error\|assert" gpurun_out/r02_world${N}_tests.log | tail -14
 B="bench.py --gpus $N --steps 20 --warmup 5"
 $T --master-port 29511 $B                                   > gpurun_out/r02_n${N}_default.log 2>&1
 $T --master-port 29512 $B --tune embed_fwd_linx_shard=1     > gpurun_out/r02_n${N}_linxshard.log 2>&1
