@@ -54,8 +54,10 @@ def load_rows(prefix: str, rank: int, world: int, names: Optional[Sequence[str]]
     out: Dict[str, torch.Tensor] = {}
     total = None
     mine = None
-    for s in range(ws):
-        blob = torch.load(shard_path(prefix, s, ws), map_location="cpu", weights_only=False)
+    # same world as the writer: this rank's rows are exactly saved shard `rank` (one file, no re-sharding);
+    # otherwise every saved shard holds some of them (memory-mapped: only the needed rows are paged in)
+    for s in ([rank] if ws == world else range(ws)):
+        blob = torch.load(shard_path(prefix, s, ws), map_location="cpu", weights_only=True, mmap=(ws != world))
         if blob.get("format") != FORMAT or blob["rank"] != s or blob["world"] != ws:
             raise ValueError(f"{shard_path(prefix, s, ws)}: not a shard {s} of {ws} in format {FORMAT}")
         if total is None:
@@ -87,7 +89,7 @@ def save_meta(prefix: str, config: dict, replicated: Dict[str, torch.Tensor]) ->
 
 
 def load_meta(prefix: str) -> dict:
-    blob = torch.load(prefix + ".meta.pt", map_location="cpu", weights_only=False)
+    blob = torch.load(prefix + ".meta.pt", map_location="cpu", weights_only=True)
     if blob.get("format") != FORMAT:
         raise ValueError(f"{prefix}.meta.pt: unknown checkpoint format {blob.get('format')}")
     return blob

@@ -99,7 +99,8 @@ extern "C" int dr_shard_bucket_ids(const void* ids, int id_bytes, int64_t n, int
   DR_REQUIRE(id_bytes == 8 || id_bytes == 4, DR_EINVAL, "dr_shard_bucket_ids: id_bytes=%d", id_bytes);
   cudaStream_t st = (cudaStream_t)stream;
   DR_CUDA_CALL(cudaMemsetAsync(send_counts, 0, sizeof(int64_t) * G, st));
-  DR_CUDA_CALL(cudaMemsetAsync(overflow, 0, sizeof(int32_t), st));
+  // `overflow` is STICKY: the kernel only ever sets it; the caller clears it after reading it (a per-call memset
+  // here would let a later, well-behaved batch erase the evidence of an earlier truncated one).
   DR_CUDA_CALL(cudaMemsetAsync(send_ids, 0xFF, sizeof(int64_t) * (size_t)G * cap, st));   // all -1
   if (n == 0) return DR_OK;
   int64_t ctas = (n + 255) / 256;

@@ -12,6 +12,8 @@
 //                      Feature{1: BytesList | 2: FloatList | 3: Int64List}, lists{1: repeated value}, scalars packed
 //                      or unpacked.
 #include <string.h>
+#include <atomic>
+#include <mutex>
 #include <string>
 #include <string_view>
 #include <thread>
@@ -23,10 +25,9 @@ namespace dr {
 namespace tfr {
 
 static uint32_t g_crc_table[8][256];
-static bool g_crc_ready = false;
+static std::once_flag g_crc_once;
 
-static void crc_init() {
-  if (g_crc_ready) return;
+static void crc_fill() {
   for (uint32_t i = 0; i < 256; ++i) {
     uint32_t c = i;
     for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
@@ -34,8 +35,9 @@ static void crc_init() {
   }
   for (uint32_t i = 0; i < 256; ++i)
     for (int t = 1; t < 8; ++t) g_crc_table[t][i] = (g_crc_table[t - 1][i] >> 8) ^ g_crc_table[0][g_crc_table[t - 1][i] & 0xff];
-  g_crc_ready = true;
 }
+// ctypes releases the GIL: two host threads may open files concurrently, so the table is built exactly once
+static void crc_init() { std::call_once(g_crc_once, crc_fill); }
 
 static uint32_t crc32c(const uint8_t* p, size_t n) {
   crc_init();
@@ -286,7 +288,7 @@ extern "C" int dr_example_parse_feature(const uint8_t* buf, const int64_t* rec_o
 namespace dr {
 namespace tfr {
 
-static int g_host_threads = 1;   // 1 = serial (default); 0 = min(hardware threads, 8)
+static std::atomic<int> g_host_threads{1};   // 1 = serial (default); 0 = min(hardware threads, 8)
 
 struct BatchCtx {
   const uint8_t* buf;

@@ -14,7 +14,7 @@ each rank trains on its own B examples:
        all-reduce of the flat tower gradient (+ the FM bias gradient), then dr_sgd_step.
 
 The exchanges are equal-split (fixed capacity, -1 padded) so there is no host round trip for
-split sizes; an overflow flag set by the bucket kernel is checked after the step.
+split sizes; a STICKY overflow flag set by the bucket kernel is checked by train_step_host() / check_overflow().
 """
 from __future__ import annotations
 
@@ -377,21 +377,37 @@ class ShardedDeepFMTrainStep:
         for fn, _ in self._segments(mark):
             fn()
 
+    def _persistent_state(self):
+        """Every tensor a step mutates and a later step reads (this rank's shard incl. trailing first-order weights,
+        the flat tower)."""
+        return [self.emb._buf if self.exchange == "p2p" else self.emb.weight, self.flat]
+
     def capture(self):
-        """Warm up eagerly, then record the whole step -- kernels AND the NCCL collectives -- into one
-        CUDA graph (falls back to eager launches if this NCCL/torch build cannot capture them)."""
+        """Warm up eagerly, then record the compute segments into CUDA graphs (collectives stay eager NCCL calls:
+        capturing the NCCL all-to-all itself dead-locked on this torch/NCCL build).
+
+        Side-effect free: the warm-up is a real step on the static warm-up ids (with remote atomics into the peers'
+        shards), so every rank snapshots its shard and the tower first and restores them once ALL ranks have finished
+        the warm-up (barrier on both sides of the restore)."""
         n0 = _lib.launch_count()
-        s = torch.cuda.Stream(device=self.dev)
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            self._enqueue()
-        torch.cuda.current_stream().wait_stream(s)
-        torch.cuda.synchronize()
+        with torch.no_grad():
+            state = self._persistent_state()
+            saved = [t.clone() for t in state]
+            s = torch.cuda.Stream(device=self.dev)
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._enqueue()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)          # every peer's remote updates of the warm-up step have landed
+            for t, keep in zip(state, saved):
+                t.copy_(keep)
+            del saved
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)          # nobody starts a real step before every shard is restored
         self.launches_per_step = _lib.launch_count() - n0
         self.check_overflow()
         if self.use_graph:
-            # compute segments -> CUDA graphs; collectives stay eager NCCL calls between the replays
-            # (capturing the NCCL all-to-all itself dead-locked on this torch/NCCL build)
             plan = []
             for fn, is_compute in self._segments(lambda label: None):
                 if is_compute:
@@ -405,11 +421,17 @@ class ShardedDeepFMTrainStep:
         return self
 
     def check_overflow(self):
+        """exchange='nccl' only: raise if ANY bucket call since the last check ran out of send slots (the flag is
+        sticky on the device; it is cleared here after it has been read).  Called by capture() and by
+        train_step_host() (which synchronises on the loss anyway); callers of the asynchronous step() / run() call it
+        whenever they synchronise."""
         if self.exchange == "p2p":
             return
         if int(self.overflow.item()) != 0:
-            raise _lib.DeepRecError(f"shard exchange overflow: a destination needed more than cap={self.cap} slots; "
-                                    "raise shard_plan.capacity slack (skewed ids)")
+            self.overflow.zero_()
+            raise _lib.DeepRecError(f"shard exchange overflow: a destination needed more than cap={self.cap} slots "
+                                    "(low-cardinality or skewed slot): lookups were dropped in a step since the last "
+                                    "check; rebuild the trainer with a larger shard_plan.capacity slack")
 
     def run(self):
         if self.graph is not None:
@@ -448,7 +470,9 @@ class ShardedDeepFMTrainStep:
             self._copy_stream.wait_event(done)
             self.stage_host(next_ids_host, next_labels_host)
         self.run()
-        return float(self.loss.item())
+        loss = float(self.loss.item())
+        self.check_overflow()
+        return loss
 
     def time_embed_fwd(self, ids_pool, iters: int = 30) -> float:
         """Mean duration (ms) of this rank's fused gather+FM forward alone (p2p: (G-1)/G of the rows are

@@ -275,14 +275,36 @@ class DeepFMTrainStep:
         shares = {k: v / count for k, v in sums.items()}
         return {"embed_fm_fwd_ms": shares["embed_fm_fwd"]}, shares
 
+    def _persistent_state(self) -> List[torch.Tensor]:
+        """Every tensor a step mutates AND a later step reads: parameters and optimizer state."""
+        c = self.coll
+        st = [c.weight.data, self.flat]
+        st += [t.data for t in (c.linear, c.bias) if t is not None]
+        if self.optimizer != "sgd":
+            st += [t for t in (self.g_arena, self.m_arena, self.v_arena, self.g_lin, self.m_lin, self.v_lin, self.g_bias,
+                               self.m_bias, self.v_bias, self.m_flat, self.v_flat, self.stamp, self.clock.step,
+                               self.clock.lr_t) if t is not None]
+        return st
+
     def capture(self):
-        """Warm up (sets kernel attributes) then record the step into a CUDA graph."""
+        """Warm up (sets kernel attributes) then record the step into a CUDA graph.
+
+        Side-effect free: the warm-up launch is a real step on whatever the static id / label buffers hold, so every
+        parameter and every piece of optimizer state (Adam clock, m, v, stamps) is snapshotted before it and restored
+        after it -- `capture()` leaves the trainer bit-identical to how it found it."""
         n0 = _lib.launch_count()
-        s = torch.cuda.Stream(device=self.dev)
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            self._enqueue()
-        torch.cuda.current_stream().wait_stream(s)
+        with torch.no_grad():
+            state = self._persistent_state()
+            saved = [t.clone() for t in state]
+            s = torch.cuda.Stream(device=self.dev)
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._enqueue()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            for t, keep in zip(state, saved):
+                t.copy_(keep)
+            del saved
         torch.cuda.synchronize()
         self.launches_per_step = _lib.launch_count() - n0
         if self.use_graph:

@@ -194,8 +194,9 @@ int dr_hard_negative_topk(const float* logits, int64_t nq, int64_t nc, int k,
  *     The send buffer is PADDED to a fixed capacity so the exchange is an equal-split
  *     all-to-all with no host synchronisation: segment g = send_ids[g*cap, (g+1)*cap) holds the
  *     local row ids (row div G) destined to rank g, -1 in unused slots.  inv[i] = slot of
- *     lookup i (-1 on overflow).  send_counts[G] = used slots per segment; overflow[0] = 1 if
- *     some segment needed more than cap slots (the caller must then re-run with a larger cap).
+ *     lookup i (-1 on overflow).  send_counts[G] = used slots per segment; overflow[0] is SET to 1 if
+ *     some segment needed more than cap slots and never cleared by the library (sticky: the caller zeroes it
+ *     before the first call and after each read, then re-runs the truncated batch with a larger cap).
  *     Order inside a segment is unspecified.  Requires G*cap < 2^31.
  *   The exchange (ids out, vectors back, gradients out) is an NCCL all-to-all issued by the
  *   host through torch.distributed.  Because inv IS a gather index, the returned vectors are

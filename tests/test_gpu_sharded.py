@@ -108,6 +108,11 @@ def test_bucket_kernel_against_numpy_twin():
                                        rows_t.data_ptr(), G, 8, counts.data_ptr(), send.data_ptr(),
                                        inv.data_ptr(), ovf.data_ptr(), torch.cuda.current_stream().cuda_stream), "bucket")
     assert int(ovf) == 1
+    # the flag is sticky: a later call that fits does not erase it (the host clears it after reading)
+    _lib.check(lib.dr_shard_bucket_ids(idt.data_ptr(), 8, B * S, S, offs_t.data_ptr(),
+                                       rows_t.data_ptr(), G, cap, counts.data_ptr(), send.data_ptr(),
+                                       inv.data_ptr(), ovf.data_ptr(), torch.cuda.current_stream().cuda_stream), "bucket")
+    assert int(ovf) == 1
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")

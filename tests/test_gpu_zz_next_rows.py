@@ -287,15 +287,12 @@ def test_train_step_adam_matches_apply_adam_oracle(optimizer, D, use_graph):
     tr = DeepFMTrainStep(model, batch_size=B, lr=lr, use_graph=use_graph, optimizer=optimizer)
     snap = [p.detach().clone() for p in (coll.weight, tr.flat, coll.bias)] + ([coll.linear.detach().clone()] if coll.linear is not None else [])
     if use_graph:
-        tr.capture()                  # the warm-up replay is a real step on the zero batch: restore the start state
-        with torch.no_grad():
-            coll.weight.copy_(snap[0]); tr.flat.copy_(snap[1]); coll.bias.copy_(snap[2])
-            if coll.linear is not None:
-                coll.linear.copy_(snap[3])
+        tr.capture()                  # must be side-effect free (round-1 advisor finding): parameters, Adam clock, m, v
+        assert all(torch.equal(a, b) for a, b in zip(snap, (coll.weight, tr.flat, coll.bias) + ((coll.linear,) if coll.linear is not None else ())))
+        if optimizer != "sgd":
             for t in (tr.m_arena, tr.v_arena, tr.g_arena, tr.m_flat, tr.v_flat, tr.m_bias, tr.v_bias, tr.g_bias,
                       tr.m_lin, tr.v_lin, tr.g_lin, tr.stamp, tr.clock.step):
-                if t is not None:
-                    t.zero_()
+                assert t is None or not bool(t.any()), "capture() left optimizer state behind"
     tables = [coll.table(s).detach().cpu().numpy().astype(np.float64) for s in range(S)]
     lins = [coll.linear_of(s).detach().cpu().numpy().astype(np.float64) for s in range(S)]
     bias = float(coll.bias.detach())
