@@ -95,6 +95,22 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
       ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// Epilogue output path: a [32 rows x 32 floats] slab staged in shared memory (SWIZZLE_128B layout) leaves as ONE TMA
+// store (or, for split-K partial sums, one TMA reduce-add: the fp32 additions happen at the L2, no per-element atomics).
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(tm), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tm, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(tm), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_group_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+constexpr int TC_EPI_STAGING = 4 * 2 * 4096;   // 4 epilogue warps x 2 slabs x (32 rows x 128 B)
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -275,6 +291,7 @@ template <int BN, int STAGES, bool A_MN, bool B_MN, bool INSPLIT = false, bool P
 __global__ void __launch_bounds__(INSPLIT ? TC_THREADS_INSPLIT : TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+               const __grid_constant__ CUtensorMap tmC, const int tma_out,
                const GemmArgs a, const int64_t m_tiles, const int64_t n_tiles, const int64_t per,
                const int64_t total_items) {
   constexpr int A_TILE = TC_BM * TC_BK * 4;   // 16 KB
@@ -296,6 +313,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAl) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBh) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBl) : "memory");
+    if (tma_out) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -422,22 +440,63 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     }
   } else {
     // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
+    // tcgen05.ld hands thread t row t of a 32 x 32 slab.  Stored straight from registers that is 32 rows x 16 B per
+    // instruction (every store touches 32 different lines; round 1 measured the kernel EPILOGUE-bound because of it).
+    // Instead the slab is written to shared memory in the TMA SWIZZLE_128B layout (16-B chunk c of row t at
+    // t*128 + ((c ^ (t & 7)) << 4): conflict-free for a row-per-thread writer) and one elected lane issues a TMA store
+    // -- or a TMA reduce-add for split-K partial sums -- which also clips the M / N edges.
     const int q = warp & 3;
     const bool vec_ok = ((a.ldc & 3) == 0) && aligned16(a.C);
-    uint32_t j = 0;
+    uint8_t* stg = smem + (size_t)STAGES * STAGE + (size_t)q * 8192;
+    uint32_t j = 0, slab = 0;
     for (int64_t item = blockIdx.x; item < total_items; item += gridDim.x, ++j) {
       const TcItem t = tc_decode(item, n_tiles, m_tiles, kblocks, per, BN);
       const uint32_t as = j & 1u, aph = (j >> 1) & 1u;
       mbar_wait_t<PROF>(&tmem_full_bar[as], aph, pw0);
       const long long te0 = PROF ? clock64() : 0;
       tc_fence_after();
-      const int64_t m = t.m0 + q * 32 + lane;
+      const int64_t mw = t.m0 + q * 32;          // first row of this warp's quarter
+      const int64_t m = mw + lane;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + as * (uint32_t)BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
         const int64_t nb = t.n0 + c * 32;
-        if (m < a.M && nb < a.N) {
+        if (tma_out) {
+          if (mw < a.M && nb < a.N) {            // warp-uniform
+            uint8_t* sb = stg + (slab & 1u) * 4096;
+            if (lane == 0) bulk_wait_group_read<1>();   // the store issued from this buffer two slabs ago has read it
+            __syncwarp();
+            const bool row_ok = m < a.M;
+            float o[32];
+            if (a.epi == EPI_STORE || a.epi == EPI_ATOMIC) {
+#pragma unroll
+              for (int jj = 0; jj < 32; ++jj) o[jj] = __uint_as_float(r[jj]);
+            } else if (a.epi == EPI_BIAS_ACT) {
+#pragma unroll
+              for (int jj = 0; jj < 32; ++jj) {
+                const float bv = (a.bias && nb + jj < a.N) ? __ldg(a.bias + nb + jj) : 0.f;
+                o[jj] = act_apply(__uint_as_float(r[jj]) + bv, a.act);
+              }
+            } else {
+#pragma unroll
+              for (int jj = 0; jj < 32; ++jj)
+                o[jj] = (row_ok && nb + jj < a.N) ? epi_scalar_tc(a, __uint_as_float(r[jj]), m, nb + jj) : 0.f;
+            }
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch)
+              *reinterpret_cast<float4*>(sb + lane * 128 + ((ch ^ (lane & 7)) << 4)) =
+                  make_float4(o[4 * ch], o[4 * ch + 1], o[4 * ch + 2], o[4 * ch + 3]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              if (a.epi == EPI_ATOMIC) tma_reduce_add_2d(&tmC, sb, (int)nb, (int)mw);
+              else tma_store_2d(&tmC, sb, (int)nb, (int)mw);
+              bulk_commit_group();
+            }
+            ++slab;
+          }
+        } else if (m < a.M && nb < a.N) {
           if (a.epi == EPI_ATOMIC) {
 #pragma unroll
             for (int jj = 0; jj < 32; ++jj)
@@ -463,6 +522,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       mbar_arrive(&tmem_empty_bar[as]);      // this thread is done reading accumulator stage `as`
       if (PROF) pw1 += (unsigned long long)(clock64() - te0);
     }
+    if (tma_out && lane == 0) bulk_wait_group_all();   // every TMA store / reduce of this warp has completed
   }
   if (PROF) {   // one representative thread per role adds its counters
     if (warp == 0 && lane == 0) {
@@ -572,24 +632,32 @@ bool gemm_tc_eligible(const GemmArgs& a, bool ta, bool tb) {
   return true;
 }
 
+int g_tune_tc_tma_out = 1;   // 1 (default) = epilogue through shared memory + TMA store / reduce-add; 0 = round-1 register stores
 int g_tune_gemm_prof = 0;   // 1 = launch the instrumented instantiation (BN = 128 INSPLIT only); read with dr_gemm_prof_read
 
 template <int BN, int STAGES, bool A_MN, bool B_MN, bool INSPLIT = false>
 static int launch_tc(const CUtensorMap* tms, const GemmArgs& a, cudaStream_t st) {
   constexpr int STAGE = 2 * TC_BM * TC_BK * 4 + 2 * BN * TC_BK * 4;
-  const size_t smem = (size_t)STAGES * STAGE + 1024;
+  constexpr size_t smem = (size_t)STAGES * STAGE + TC_EPI_STAGING + 1024;
+  static_assert(smem <= 232448, "operand ring + epilogue staging exceed the 227 KB of shared memory per CTA");
   constexpr bool kProfInst = INSPLIT && BN == 128;
   auto k = (kProfInst && g_tune_gemm_prof) ? gemm_tc_kernel<BN, STAGES, A_MN, B_MN, INSPLIT, kProfInst>
                                            : gemm_tc_kernel<BN, STAGES, A_MN, B_MN, INSPLIT, false>;
   DR_CUDA_CALL(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // output through TMA (store / reduce-add) whenever C is 16-B aligned with a 16-B multiple pitch
+  CUtensorMap tmC;
+  memset(&tmC, 0, sizeof(tmC));
+  int tma_out = (g_tune_tc_tma_out && (a.ldc & 3) == 0 && aligned16(a.C)) ? 1 : 0;
+  if (tma_out)
+    if (int rc = make_map(&tmC, a.C, a.N, a.M, a.ldc, 32)) return rc;
   const int64_t m_tiles = (a.M + TC_BM - 1) / TC_BM, n_tiles = (a.N + BN - 1) / BN;
   const int64_t kblocks = (a.K + TC_BK - 1) / TC_BK;
   const int64_t per = (kblocks + a.splitk - 1) / a.splitk;
   const int64_t splits = (kblocks + per - 1) / per;          // every split owns >= 1 k-block
   const int64_t total = m_tiles * n_tiles * splits;
   const int64_t ctas = total < (int64_t)kNumSMs ? total : (int64_t)kNumSMs;
-  k<<<(unsigned)ctas, INSPLIT ? TC_THREADS_INSPLIT : TC_THREADS, smem, st>>>(tms[0], tms[1], tms[2], tms[3], a, m_tiles,
-                                                                               n_tiles, per, total);
+  k<<<(unsigned)ctas, INSPLIT ? TC_THREADS_INSPLIT : TC_THREADS, smem, st>>>(tms[0], tms[1], tms[2], tms[3], tmC, tma_out, a,
+                                                                               m_tiles, n_tiles, per, total);
   DR_CUDA_LAUNCH_CHECK("gemm_tc");
   return DR_OK;
 }
@@ -648,7 +716,7 @@ int gemm_tc_launch(const GemmArgs& a0, bool ta, bool tb, cudaStream_t st) {
       if (A_MN && !B_MN) return launch_tc<BN_, ST_, true, false, true>(tm2, a, st);         \
       return launch_tc<BN_, ST_, true, true, true>(tm2, a, st);                             \
     } while (0)
-    if (bn == 32) DR_TC2_LAUNCH(32, 5);
+    if (bn == 32) DR_TC2_LAUNCH(32, 4);
     if (bn == 64) DR_TC2_LAUNCH(64, 4);
     DR_TC2_LAUNCH(128, 3);
 #undef DR_TC2_LAUNCH
@@ -708,7 +776,7 @@ int gemm_tc_launch(const GemmArgs& a0, bool ta, bool tb, cudaStream_t st) {
       if (A_MN && !B_MN) return launch_tc<BN_, ST_, true, false>(tms, a, st);               \
       return launch_tc<BN_, ST_, true, true>(tms, a, st);                                   \
     } while (0)
-    if (bn == 32) DR_TC_LAUNCH(32, 5);
+    if (bn == 32) DR_TC_LAUNCH(32, 4);
     if (bn == 64) DR_TC_LAUNCH(64, 4);
     DR_TC_LAUNCH(128, 3);
 #undef DR_TC_LAUNCH

@@ -429,6 +429,142 @@ __global__ void __launch_bounds__(WARPS * 32) k_tma(P p, const __grid_constant__
   if (lane == 0) bulk_wait0();
 }
 
+
+// ------------------------------------------------------------------------------------------ hybrid (round 2)
+// Rows arrive through REGISTER loads (the fastest way to ask for a row, see profiles/mb_gather_r02_*.jsonl), the stacked
+// output leaves through a per-warp shared-memory tile and ONE cp.async.bulk store per tile (13 KB contiguous) instead of
+// 26 x 8 scattered 64-B register stores.  V8: 256-bit loads -- lanes 0,1 of a 4-lane group fetch the two halves of the
+// 64-B row, lane 2 the [w | pad] sector of the same 128-B line IN THE SAME INSTRUCTION (one L2 request per lookup).
+// DYN: warps draw tiles from an atomic counter (no 3-vs-4-tiles tail).
+__device__ __forceinline__ void ld32(const float* p, float (&r)[8]) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]) : "l"(p));
+}
+__device__ unsigned int g_tile_counter;
+
+template <int F, bool V8, bool DYN, int WARPS, int U>
+__global__ void __launch_bounds__(WARPS * 32) k_hyb(P p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int WB = TILE_BYTES + LK * 4;       // stacked tile + int32 row indices
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
+  unsigned char* tile_s = smem + (size_t)warp * WB;
+  int* srow = reinterpret_cast<int*>(tile_s + TILE_BYTES);
+  const int64_t ntiles = (p.B + EX - 1) / EX;
+  const bool want_lin = p.lin != nullptr;
+  int64_t tile = DYN ? 0 : (int64_t)blockIdx.x * WARPS + warp;
+  const int64_t nw = (int64_t)gridDim.x * WARPS;
+  bool first = true;
+  for (;;) {
+    if (DYN) {
+      unsigned int t = 0;
+      if (lane == 0) t = atomicAdd(&g_tile_counter, 1u);
+      tile = __shfl_sync(0xffffffffu, t, 0);
+    }
+    if (tile >= ntiles) break;
+    const int64_t b0 = tile * EX;
+    const int nex = (int)min((int64_t)EX, p.B - b0);
+    // the previous tile's bulk store must have read the tile buffer before it is overwritten
+    if (!first && p.stack && lane == 0) bulk_wait_read0();
+    first = false;
+    for (int i = lane; i < LK; i += 32) {
+      int r = -1;
+      if (i < nex * S) {
+        const int64_t id = __ldg(p.ids + b0 * S + i);
+        if ((uint64_t)id < (uint64_t)ROWS) r = (int)((i % S) * ROWS + id);
+      }
+      srow[i] = r;
+    }
+    __syncwarp();
+    const bool ok = g < nex;
+    const int64_t b = b0 + g;
+    float lin = 0.f;
+    if (!V8) {
+      float4 a = make_float4(0, 0, 0, 0);
+      for (int s0 = 0; s0 < S; s0 += U) {
+        float4 v[U];
+        float w[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int s = s0 + u;
+          v[u] = make_float4(0, 0, 0, 0);
+          w[u] = 0.f;
+          if (s < S) {
+            const int r = srow[g * S + s];
+            if (r >= 0) {
+              const float* row = p.arena + (int64_t)r * p.stride;
+              v[u] = ld16<F>(row + c * 4);
+              if (want_lin && c == 0) w[u] = ld4<F>(row + D);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int s = s0 + u;
+          if (s < S) {
+            a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w;
+            lin += w[u];
+            if (p.stack) *reinterpret_cast<float4*>(tile_s + (g * S + s) * 64 + c * 16) = v[u];
+          }
+        }
+      }
+      if (ok) *reinterpret_cast<float4*>(p.sum + b * D + c * 4) = a;
+      if (ok && want_lin && c == 0) p.lin[b] = lin;
+    } else {
+      float a[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] = 0.f;
+      const bool ld_lane = c < 2 || (c == 2 && want_lin);
+      for (int s0 = 0; s0 < S; s0 += U) {
+        float v[U][8];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int s = s0 + u;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[u][k] = 0.f;
+          if (s < S && ld_lane) {
+            const int r = srow[g * S + s];
+            if (r >= 0) ld32(p.arena + (int64_t)r * p.stride + c * 8, v[u]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int s = s0 + u;
+          if (s < S) {
+            if (c < 2) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) a[k] += v[u][k];
+              if (p.stack) {
+                float4* d = reinterpret_cast<float4*>(tile_s + (g * S + s) * 64 + c * 32);
+                d[0] = make_float4(v[u][0], v[u][1], v[u][2], v[u][3]);
+                d[1] = make_float4(v[u][4], v[u][5], v[u][6], v[u][7]);
+              }
+            } else {
+              lin += v[u][0];
+            }
+          }
+        }
+      }
+      if (ok && c < 2) {
+        float4* d = reinterpret_cast<float4*>(p.sum + b * D + c * 8);
+        d[0] = make_float4(a[0], a[1], a[2], a[3]);
+        d[1] = make_float4(a[4], a[5], a[6], a[7]);
+      }
+      if (ok && want_lin && c == 2) p.lin[b] = lin;
+    }
+    if (p.stack) {
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        bulk_store(p.stack + b0 * S * D, smem_u32(tile_s), (uint32_t)nex * S * 64);
+        bulk_commit();
+      }
+    }
+    __syncwarp();
+    if (!DYN) tile += nw;
+  }
+  if (p.stack && lane == 0) bulk_wait0();
+}
+
 // ------------------------------------------------------------------------------------------ host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -547,7 +683,7 @@ int main(int argc, char** argv) {
   const bool has_lin = stride > D;
   // algorithmic bytes / example: ids 8S + rows 64S (+ 4S weights) + stack 64S + sum 64 (+ 4 logit)
   auto alg = [&](bool stack, bool lin) { return (double)S * (8 + 64 + (lin ? 4 : 0)) + (stack ? S * 64 : 0) + 64 + (lin ? 4 : 0); };
-  auto want = [&](const char* n) { return only.empty() || only == n; };
+  auto want = [&](const char* n) { return only.empty() || strncmp(n, only.c_str(), only.size()) == 0; };   // prefix match
 
 #define RUN_REG(F, U, NAME)                                                                                       \
   if (want(NAME)) {                                                                                               \
@@ -584,6 +720,33 @@ int main(int argc, char** argv) {
   RUN_CPA(8, 2, "cpasync_w8_b2")
   RUN_CPA(2, 4, "cpasync_w2_b4")
 
+
+#define RUN_HYB(F, V8, DYN, W, U, NAME)                                                                           \
+  if (want(NAME) && (!(V8) || stride == 32)) {                                                                    \
+    size_t sm = (size_t)W * (TILE_BYTES + LK * 4);                                                                \
+    CK(cudaFuncSetAttribute(k_hyb<F, V8, DYN, W, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));      \
+    int occ = 0;                                                                                                  \
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_hyb<F, V8, DYN, W, U>, W * 32, sm));                 \
+    fprintf(stderr, "%s: %zu B smem / CTA, %d CTAs / SM\n", NAME, sm, occ);                                       \
+    for (int st = 0; st < 2; ++st)                                                                                \
+      for (int li = 0; li < (has_lin ? 2 : 1); ++li)                                                              \
+        run(NAME, c, st, li, [&](const P& p) {                                                                    \
+          if (DYN) { unsigned int z = 0; CK(cudaMemcpyToSymbolAsync(g_tile_counter, &z, 4, 0, cudaMemcpyHostToDevice, 0)); } \
+          k_hyb<F, V8, DYN, W, U><<<148 * occ, W * 32, sm>>>(p); }, alg(st, li));                                 \
+  }
+  RUN_HYB(0, false, false, 8, 13, "hyb_v4_nc")
+  RUN_HYB(1, false, false, 8, 13, "hyb_v4_L2_64B")
+  RUN_HYB(0, false, true, 8, 13, "hyb_v4_nc_dyn")
+  RUN_HYB(1, false, true, 8, 13, "hyb_v4_L2_64B_dyn")
+  RUN_HYB(0, false, true, 8, 9, "hyb_v4_nc_dyn_u9")
+  RUN_HYB(0, false, true, 8, 7, "hyb_v4_nc_dyn_u7")
+  RUN_HYB(0, true, false, 8, 13, "hyb_v8_w8")
+  RUN_HYB(0, true, false, 12, 13, "hyb_v8_w12")
+  RUN_HYB(0, true, true, 12, 13, "hyb_v8_w12_dyn")
+  RUN_HYB(0, true, true, 14, 9, "hyb_v8_w14_u9_dyn")
+  RUN_HYB(0, true, true, 16, 7, "hyb_v8_w16_u7_dyn")
+  RUN_HYB(0, true, true, 8, 13, "hyb_v8_w8_dyn")
+
   CUtensorMap tm1, tm4;
   bool m1 = make_map(&tm1, arena, total_rows, stride, 1, CU_TENSOR_MAP_L2_PROMOTION_NONE);
   bool m4 = make_map(&tm4, arena, total_rows, stride, 4, CU_TENSOR_MAP_L2_PROMOTION_NONE);
@@ -601,7 +764,6 @@ int main(int argc, char** argv) {
   RUN_TMA(4, 2, 0, tm1, "bulk64_w4_b2", (has_lin ? 2 : 1))
   RUN_TMA(2, 3, 0, tm1, "bulk64_w2_b3", (has_lin ? 2 : 1))
   if (m1) { RUN_TMA(4, 2, 1, tm1, "gather4_box1_w4_b2", 1) }
-  if (m4) { RUN_TMA(4, 2, 1, tm4, "gather4_box4_w4_b2", 1) }
   if (m1) { RUN_TMA(2, 3, 1, tm1, "gather4_box1_w2_b3", 1) }
   return 0;
 }
