@@ -157,8 +157,12 @@ class Layer(nn.Module):
         return []
 
 
-class Model(Layer):
-    """tf.keras.Model stand-in: a Layer with ``predict`` and config-based save / load."""
+from ..engine import TrainingLoopMixin  # noqa: E402
+
+
+class Model(TrainingLoopMixin, Layer):
+    """tf.keras.Model stand-in: a Layer with ``predict``, ``compile`` / ``fit`` / ``evaluate`` (keras/engine.py) and
+    config-based save / load."""
 
     @torch.no_grad()
     def predict(self, inputs, **kwargs):

@@ -175,6 +175,7 @@ class ShardedDeepFMTrainStep:
         self.graph_error = None
         self.launches_per_step = None
         self._copy_stream = torch.cuda.Stream(device=dev)
+        self._side_stream = torch.cuda.Stream(device=dev)
         self._staged = None
 
     # ---- checkpoint: one file per rank + metadata on rank 0; loadable by any number of ranks (checkpoint.py) -------
@@ -227,14 +228,23 @@ class ShardedDeepFMTrainStep:
         def st():
             return torch.cuda.current_stream().cuda_stream
 
-        def seg_main():
-            check(lib.dr_gemm_plane_cache(1), "dr_gemm_plane_cache")
+        def seg_gather():
             check(lib.dr_embed_fm_fwd_sharded(self.emb.peer_ptrs.data_ptr(), G, self.emb.slot_offsets.data_ptr(),
                                               self.emb.rows.data_ptr(), self.ids.data_ptr(), 8, self.bias.data_ptr(),
                                               B, S, D, V, self.emb.flags, self.emb.lin_offset, self.stack.data_ptr(),
                                               self.sum_e.data_ptr(), self.fm_logit.data_ptr(), st()),
                   "dr_embed_fm_fwd_sharded")
             mark("embed_fm_fwd_p2p")
+
+        def col_reads_done():
+            # every rank has finished reading every shard: from here on remote updates may land (this barrier, not the
+            # tower all-reduce, is what orders a step's remote reads before its remote updates -- so the update can
+            # overlap the layer-0 weight gradient and the all-reduce instead of waiting for them)
+            self.emb.handle.barrier(channel=1)
+            mark("barrier_reads")
+
+        def seg_tower():
+            check(lib.dr_gemm_plane_cache(1), "dr_gemm_plane_cache")
             x, K = self.stack, S * D
             for i, l in enumerate(self.layers):
                 check(lib.dr_dense_fwd(x.data_ptr(), self.w[i].data_ptr(), self.b[i].data_ptr(), B, K, l.units,
@@ -246,41 +256,55 @@ class ShardedDeepFMTrainStep:
                                             self.labels.data_ptr(), B, self.prob.data_ptr(), self.loss.data_ptr(),
                                             gz.data_ptr(), st()), "dr_bce")
             mark("bce")
-            for i in range(len(self.layers) - 1, -1, -1):
+            for i in range(len(self.layers) - 1, 0, -1):
                 l = self.layers[i]
-                xin = self.stack if i == 0 else self.acts[i - 1]
-                Kin = S * D if i == 0 else self.layers[i - 1].units
-                gx = self.g_stack if i == 0 else self.g_acts[i - 1]
+                xin, Kin, gx = self.acts[i - 1], self.layers[i - 1].units, self.g_acts[i - 1]
                 check(lib.dr_dense_bwd(xin.data_ptr(), self.w[i].data_ptr(), self.acts[i].data_ptr(),
                                        self.g_acts[i].data_ptr(), B, Kin, l.units, l._act, ops._ptr(self.gz_ws[i]),
                                        gx.data_ptr(), self.gw[i].data_ptr(), self.gb[i].data_ptr(), st()),
                       "dr_dense_bwd")
                 mark(f"dense_bwd_{i}")
-            check(lib.dr_gemm_plane_cache(0), "dr_gemm_plane_cache")
-            torch.sum(gz.view(-1), dim=0, keepdim=True, out=self.g_bias)      # FM bias gradient (tiny)
-            mark("bias_grad")
+            l = self.layers[0]      # layer 0: the input gradient first (the embedding update needs it) ...
+            check(lib.dr_dense_bwd(self.stack.data_ptr(), self.w[0].data_ptr(), self.acts[0].data_ptr(),
+                                   self.g_acts[0].data_ptr(), B, S * D, l.units, l._act, ops._ptr(self.gz_ws[0]),
+                                   self.g_stack.data_ptr(), None, self.gb[0].data_ptr(), st()), "dr_dense_bwd(dx)")
+            mark("dense_bwd_0_dx")
 
-        def col_allreduce():
-            dist.all_reduce(self.gflat, group=self.group)      # also: every rank has finished its remote reads
-            mark("allreduce_dense")
-
-        def seg_update():
+        def seg_update():           # replayed on the SIDE stream: remote vector atomics into the owners' shards
             gz = self.g_acts[-1]
             check(lib.dr_embed_fm_bwd_sharded(self.emb.peer_ptrs.data_ptr(), G, self.emb.slot_offsets.data_ptr(),
                                               self.emb.rows.data_ptr(), self.ids.data_ptr(), 8, self.stack.data_ptr(),
                                               self.sum_e.data_ptr(), gz.data_ptr(), self.g_stack.data_ptr(), B, S, D,
                                               V, self.emb.flags, self.emb.lin_offset, None, -self.lr / G, st()),
                   "dr_embed_fm_bwd_sharded")
-            mark("embed_fm_bwd_p2p")
+
+        def seg_dw():               # ... meanwhile, on the main stream: layer-0 weight gradient + FM bias gradient
+            l = self.layers[0]
+            gz0 = self.gz_ws[0] if l._act != 0 else self.g_acts[0]
+            check(lib.dr_dense_bwd(self.stack.data_ptr(), self.w[0].data_ptr(), None, gz0.data_ptr(), B, S * D, l.units,
+                                   0, None, None, self.gw[0].data_ptr(), None, st()), "dr_dense_bwd(dw)")
+            check(lib.dr_gemm_plane_cache(0), "dr_gemm_plane_cache")
+            mark("dense_bwd_0_dw")
+            torch.sum(self.g_acts[-1].view(-1), dim=0, keepdim=True, out=self.g_bias)      # FM bias gradient (tiny)
+            mark("bias_grad")
+
+        def col_allreduce():
+            dist.all_reduce(self.gflat, group=self.group)
+            mark("allreduce_dense")
+
+        def seg_sgd():
             check(lib.dr_sgd_step(self.flat.data_ptr(), self.gflat.data_ptr(), self.flat.numel(), self.lr / G, st()),
                   "dr_sgd_step")
             mark("sgd")
 
         def col_barrier():
+            mark("embed_fm_bwd_p2p_tail")               # what was left of the side-stream update after the join
             self.emb.handle.barrier(channel=0)          # all remote atomics of this step have been issued
             mark("barrier")
 
-        return [(seg_main, True), (col_allreduce, False), (seg_update, True), (col_barrier, False)]
+        return [(seg_gather, "graph"), (col_reads_done, "eager"), (seg_tower, "graph"), (seg_update, "graph_side"),
+                (seg_dw, "graph"), (col_allreduce, "eager"), (seg_sgd, "graph"), (None, "join_side"),
+                (col_barrier, "eager")]
 
     def _segments(self, mark):
         if self.exchange == "p2p":
@@ -368,14 +392,28 @@ class ShardedDeepFMTrainStep:
                   "dr_sgd_step")
             mark("sgd")
 
-        return [(seg_bucket, True), (col_ids, False), (seg_gather, True), (col_vec, False), (seg_main, True),
-                (col_grads, False), (seg_scatter, True), (col_allreduce, False), (seg_sgd, True)]
+        return [(seg_bucket, "graph"), (col_ids, "eager"), (seg_gather, "graph"), (col_vec, "eager"), (seg_main, "graph"),
+                (col_grads, "eager"), (seg_scatter, "graph"), (col_allreduce, "eager"), (seg_sgd, "graph")]
+
+    # segment kinds: "graph" = compute on the main stream (captured as a CUDA graph), "eager" = a collective issued
+    # between replays, "graph_side" = compute replayed on the side stream after it has waited for the main stream
+    # (runs concurrently with what follows), "join_side" = the main stream waits for the side stream.
+    def _run_plan(self, plan):
+        main = torch.cuda.current_stream()
+        for fn, kind in plan:
+            if kind == "graph_side":
+                self._side_stream.wait_stream(main)
+                with torch.cuda.stream(self._side_stream):
+                    fn()
+            elif kind == "join_side":
+                main.wait_stream(self._side_stream)
+            else:
+                fn()
 
     def _enqueue(self, mark=None):
         mark = mark or (lambda label: None)
         mark("start")
-        for fn, _ in self._segments(mark):
-            fn()
+        self._run_plan(self._segments(mark))
 
     def _persistent_state(self):
         """Every tensor a step mutates and a later step reads (this rank's shard incl. trailing first-order weights,
@@ -409,14 +447,14 @@ class ShardedDeepFMTrainStep:
         self.check_overflow()
         if self.use_graph:
             plan = []
-            for fn, is_compute in self._segments(lambda label: None):
-                if is_compute:
+            for fn, kind in self._segments(lambda label: None):
+                if kind in ("graph", "graph_side"):
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g):
                         fn()
-                    plan.append(g.replay)
+                    plan.append((g.replay, kind))
                 else:
-                    plan.append(fn)
+                    plan.append((fn, kind))
             self.graph = plan
         return self
 
@@ -435,8 +473,7 @@ class ShardedDeepFMTrainStep:
 
     def run(self):
         if self.graph is not None:
-            for fn in self.graph:
-                fn()
+            self._run_plan(self.graph)
         else:
             self._enqueue()
 

@@ -175,3 +175,35 @@ def test_c1_movielens_shaped_fm_matches_oracle():
         opt.step()
         first = first if first is not None else float(loss)
     assert float(loss) < first
+
+
+def test_keras_compile_fit_evaluate_like_reference_example():
+    """/root/reference/examples/train_deepfm_on_movielens_keras.py:38-54: compile(loss, Adam, [AUC, Precision, Recall]) +
+    fit(input_fn, epochs, steps_per_epoch, validation_data, validation_steps, [EarlyStopping(patience=3)])."""
+    import importlib.util
+    import pathlib
+    from deep_recommenders_b200.keras import engine as K
+    from deep_recommenders.keras.models.ranking import DeepFM
+    spec = importlib.util.spec_from_file_location(
+        "ex_keras", pathlib.Path(__file__).resolve().parents[1] / "examples" / "train_deepfm_on_movielens_keras.py")
+    ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ex)
+    ind, emb = ex.build_columns()
+    model = DeepFM(ind, emb, dnn_units_size=[32, 8], seed=0, device="cuda")
+    model.compile(loss=K.binary_crossentropy, optimizer=K.Adam(learning_rate=0.01), metrics=[K.AUC(), K.Precision(), K.Recall()])
+    hist = model.fit(ex.synthetic_input_fn(1, 512), epochs=4, steps_per_epoch=25, validation_data=ex.synthetic_input_fn(2, 512),
+                     validation_steps=4, callbacks=[K.EarlyStopping(patience=3)])
+    assert len(hist["loss"]) == 4 and hist["loss"][-1] < hist["loss"][0]
+    assert set(hist) >= {"loss", "auc", "precision", "recall", "val_loss", "val_auc"}
+    assert hist["val_auc"][-1] > 0.55                      # the synthetic labels depend on the ids: better than chance
+    # metric arithmetic against numpy on one batch
+    y = np.asarray([0, 0, 1, 1, 1, 0], np.float32)
+    p = np.asarray([0.1, 0.6, 0.8, 0.4, 0.9, 0.2], np.float32)
+    m = [K.AUC(), K.Precision(), K.Recall()]
+    for x in m:
+        x.update_state(torch.from_numpy(y).cuda(), torch.from_numpy(p).cuda())
+    assert abs(m[1].result() - 2 / 3) < 1e-6 and abs(m[2].result() - 2 / 3) < 1e-6
+    assert abs(m[0].result() - 8 / 9) < 0.02               # exact ROC AUC of this batch = 8/9 (200-threshold trapezoid)
+    # EarlyStopping: stops after `patience` epochs without improvement
+    es = K.EarlyStopping(patience=2)
+    assert [es.on_epoch_end(i, {"val_loss": v}) for i, v in enumerate([1.0, 0.9, 0.95, 0.97])] == [False, False, False, True]

@@ -430,6 +430,80 @@ __global__ void __launch_bounds__(WARPS * 32) k_tma(P p, const __grid_constant__
 }
 
 
+
+// ------------------------------------------------------------------------------------------ pair mapping
+// 8 lanes per example cover TWO adjacent slots (2j, 2j+1): their 8 x 16 B = one whole, line-aligned 128-B line of the
+// stacked output, so every store instruction writes 4 full lines instead of 8 half lines.  4 examples per warp,
+// 13 iterations (all 26 slots of the 4 examples in flight at U = 13).  ST: 0 plain, 1 st.global.cs, 2 L1::no_allocate
+template <int ST>
+__device__ __forceinline__ void st16(float* p, float4 v) {
+  if (ST == 0) *reinterpret_cast<float4*>(p) = v;
+  if (ST == 1) asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+  if (ST == 2) asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+template <int F, int ST, int U, bool PAIR>
+__global__ void __launch_bounds__(256) k_reg2(P p) {
+  constexpr int EXW = PAIR ? 4 : 8;          // examples per warp tile
+  constexpr int NIT = PAIR ? S / 2 : S;      // iterations over slots (slot pairs)
+  __shared__ int srow[8][EXW * S];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = PAIR ? lane >> 3 : lane >> 2, h = PAIR ? (lane >> 2) & 1 : 0, c = lane & 3;
+  const int64_t ntiles = (p.B + EXW - 1) / EXW;
+  const bool want_lin = p.lin != nullptr && c == 0;
+  for (int64_t tile = blockIdx.x * 8 + warp; tile < ntiles; tile += (int64_t)gridDim.x * 8) {
+    const int64_t b0 = tile * EXW;
+    const int nex = (int)min((int64_t)EXW, p.B - b0);
+    for (int i = lane; i < EXW * S; i += 32) {
+      int r = -1;
+      if (i < nex * S) {
+        const int64_t id = __ldg(p.ids + b0 * S + i);
+        if ((uint64_t)id < (uint64_t)ROWS) r = (int)((i % S) * ROWS + id);
+      }
+      srow[warp][i] = r;
+    }
+    __syncwarp();
+    const bool ok = g < nex;
+    const int64_t b = b0 + g;
+    float4 a = make_float4(0, 0, 0, 0);
+    float lin = 0.f;
+    for (int j0 = 0; j0 < NIT; j0 += U) {
+      float4 v[U];
+      float w[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int s = PAIR ? 2 * (j0 + u) + h : j0 + u;
+        v[u] = make_float4(0, 0, 0, 0);
+        w[u] = 0.f;
+        if (j0 + u < NIT) {
+          const int r = srow[warp][g * S + s];
+          if (r >= 0) {
+            const float* row = p.arena + (int64_t)r * p.stride;
+            v[u] = ld16<F>(row + c * 4);
+            if (want_lin) w[u] = ld4<F>(row + D);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int s = PAIR ? 2 * (j0 + u) + h : j0 + u;
+        if (j0 + u < NIT) {
+          a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w;
+          lin += w[u];
+          if (p.stack && ok) st16<ST>(p.stack + (b * S + s) * D + c * 4, v[u]);
+        }
+      }
+    }
+    if (PAIR) {   // even-slot + odd-slot partial sums
+      a.x += __shfl_xor_sync(0xffffffffu, a.x, 4); a.y += __shfl_xor_sync(0xffffffffu, a.y, 4);
+      a.z += __shfl_xor_sync(0xffffffffu, a.z, 4); a.w += __shfl_xor_sync(0xffffffffu, a.w, 4);
+      lin += __shfl_xor_sync(0xffffffffu, lin, 4);
+    }
+    if (ok && h == 0) *reinterpret_cast<float4*>(p.sum + b * D + c * 4) = a;
+    if (ok && h == 0 && want_lin) p.lin[b] = lin;
+    __syncwarp();
+  }
+}
+
 // ------------------------------------------------------------------------------------------ hybrid (round 2)
 // Rows arrive through REGISTER loads (the fastest way to ask for a row, see profiles/mb_gather_r02_*.jsonl), the stacked
 // output leaves through a per-warp shared-memory tile and ONE cp.async.bulk store per tile (13 KB contiguous) instead of
@@ -720,6 +794,29 @@ int main(int argc, char** argv) {
   RUN_CPA(8, 2, "cpasync_w8_b2")
   RUN_CPA(2, 4, "cpasync_w2_b4")
 
+
+
+#define RUN_REG2(F, ST, U, PAIR, CARVE, DUMMY, NAME)                                                              \
+  if (want(NAME)) {                                                                                               \
+    if (CARVE >= 0) CK(cudaFuncSetAttribute(k_reg2<F, ST, U, PAIR>, cudaFuncAttributePreferredSharedMemoryCarveout, CARVE)); \
+    if (DUMMY) CK(cudaFuncSetAttribute(k_reg2<F, ST, U, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, DUMMY)); \
+    int occ = 0;                                                                                                  \
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_reg2<F, ST, U, PAIR>, 256, DUMMY));                  \
+    fprintf(stderr, "%s: %d CTAs / SM\n", NAME, occ);                                                             \
+    for (int st = 0; st < 2; ++st)                                                                                \
+      for (int li = (has_lin ? 1 : 0); li < (has_lin ? 2 : 1); ++li)                                              \
+        run(NAME, c, st, li, [&](const P& p) { k_reg2<F, ST, U, PAIR><<<148 * occ, 256, DUMMY>>>(p); }, alg(st, li)); \
+  }
+  RUN_REG2(0, 0, 13, false, -1, 0, "r2_base")
+  RUN_REG2(0, 0, 13, true, -1, 0, "r2_pair")
+  RUN_REG2(0, 1, 13, true, -1, 0, "r2_pair_cs")
+  RUN_REG2(0, 2, 13, true, -1, 0, "r2_pair_na")
+  RUN_REG2(0, 1, 13, false, -1, 0, "r2_base_cs")
+  RUN_REG2(1, 0, 13, true, -1, 0, "r2_pair_L2_64B")
+  RUN_REG2(0, 0, 7, true, -1, 0, "r2_pair_u7")
+  RUN_REG2(0, 0, 13, false, 0, 0, "r2_base_carve0")
+  RUN_REG2(0, 0, 13, false, -1, 100 * 1024, "r2_base_dummy100k")
+  RUN_REG2(0, 0, 13, true, 0, 0, "r2_pair_carve0")
 
 #define RUN_HYB(F, V8, DYN, W, U, NAME)                                                                           \
   if (want(NAME) && (!(V8) || stride == 32)) {                                                                    \
