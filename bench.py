@@ -149,6 +149,9 @@ def main():
                     help="synthetic id distribution: uniform (headline) or Zipf(1.05) clipped to the table (SURVEY 8d second run)")
     ap.add_argument("--tune", action="append", default=[], metavar="KNOB=VALUE",
                     help="developer knob of libdeeprec_b200.so (dr_tune_set), e.g. --tune tc_min_n=32; recorded in the line")
+    ap.add_argument("--optimizer", default="sgd", choices=["sgd", "adam", "lazy_adam", "adam_rows"],
+                    help="N=1: sgd (default, fused row-sparse SGD), adam (TF-exact dense ApplyAdam over the arena), lazy_adam "
+                         "(row-sparse, two kernels), adam_rows (row-sparse Adam fused into the backward scatter)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: fused NVLink peer-memory gather/update (p2p) or NCCL all-to-all pipeline (nccl)")
     args = ap.parse_args()
@@ -209,7 +212,8 @@ def main():
         def build_single():
             model = DeepFM([fc.indicator_column(c) for c in cols], [fc.embedding_column(c, D) for c in cols],
                            dnn_units_size=W["dnn"], seed=1, device=dev, sparse_lr=0.01)
-            return DeepFMTrainStep(model, batch_size=B, lr=0.01, use_graph=not args.no_graph).capture()
+            return DeepFMTrainStep(model, batch_size=B, lr=0.01, use_graph=not args.no_graph,
+                                   optimizer=args.optimizer).capture()
         try:
             trainer = build_single()
         except Exception as e:      # the newest GEMM core failing to launch must not cost the measurement: say so, use tc
@@ -290,7 +294,10 @@ def main():
 
     # ---- roofline of the headline kernel (fused gather+FM forward) ---------------------------------
     peaks, peak_kind = measured_peaks()
-    alg_bytes = B * (S * (8 + 4 * D + 4) + 4 * S * D + 4 * D + 4)      # ids + rows + w + stack + sum_e + logit
+    # ids + rows + first-order weights + stacked write + logit (3 644 B / example at C2); the kernel also
+    # writes the sum_e side output the backward reads (4 D B / example) -- reported separately, not in `frac`
+    alg_bytes = B * (S * (8 + 4 * D + 4) + 4 * S * D + 4)
+    alg_bytes_with_sum = alg_bytes + B * 4 * D
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "embed_fwd_traffic.json")))["dram_bytes_per_launch"]
@@ -301,8 +308,13 @@ def main():
                 "how": "mean of back-to-back launches between two CUDA events on the launching stream, id pool of 8 "
                        "batches; the same kernel inside the eager per-kernel pass is kernel_ms.embed_fm_fwd",
                 "achieved": alg_bytes / fwd_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": alg_bytes / fwd_s / 1e9 / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_kind,
-                "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": fwd_s * 1e6}
+                "frac": alg_bytes / fwd_s / 1e9 / peaks["hbm_gbs"], "traffic": traffic,
+                "traffic_source": "profiles/embed_fwd_traffic.json (ncu --set full capture of this kernel at this config; "
+                                  "not re-measured inside this run)",
+                "peak_source": peak_kind, "algorithmic_bytes_per_launch": alg_bytes,
+                "bytes_convention": "SURVEY 8(d): S*(8+4D+4) + 4*S*D + 4 per example",
+                "frac_incl_sum_e_output": alg_bytes_with_sum / fwd_s / 1e9 / peaks["hbm_gbs"],
+                "us_per_launch": fwd_s * 1e6}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1 and args.workload == "c2":     # CPU arm on rank 0 at N=1 only (torchrun pins OMP threads to 1)
@@ -324,7 +336,8 @@ def main():
             "cuda_graph": trainer.graph is not None,
             "gemm_core": {0: "ffma", 1: "tcgen05 3xTF32, pre-split planes (tc)",
                           2: "tcgen05 3xTF32, hi/lo split in kernel (tc2)"}[_lib._tc_variant if _lib._tc_enabled and not gemm_note else (1 if gemm_note else 0)],
-            "exchange": getattr(trainer, "exchange", None) if world > 1 else None}
+            "exchange": getattr(trainer, "exchange", None) if world > 1 else None,
+            "optimizer": args.optimizer if world == 1 else "sgd"}
     if world > 1 and exchange_note:
         line["exchange_note"] = exchange_note
     if gemm_note:

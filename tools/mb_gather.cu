@@ -504,6 +504,92 @@ __global__ void __launch_bounds__(256) k_reg2(P p) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------ L2 software prefetch
+// Hypothesis under test: the register gather is capped by outstanding L1 misses per SM (~256 lines x ~1 us DRAM latency),
+// not by DRAM.  prefetch.global.L2 is fire-and-forget (no register, no L1 miss entry): every warp prefetches the rows of
+// its NEXT tile into L2 while it processes the current one, whose loads then are L2 hits (~0.3 us).
+template <int PF>
+__device__ __forceinline__ void pf_l2(const void* p) {
+  if (PF == 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+  if (PF == 2) asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(p));
+}
+template <int F, int PF, int U, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_pf(P p) {
+  __shared__ int srow[WARPS][2][LK];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
+  const int64_t ntiles = (p.B + EX - 1) / EX;
+  const int64_t nw = (int64_t)gridDim.x * WARPS;
+  const bool want_lin = p.lin != nullptr && c == 0;
+  int64_t idr[7];
+  auto load_ids = [&](int64_t t) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      const int j = lane + 32 * k;
+      idr[k] = -1;
+      if (t < ntiles && j < LK && t * EX * S + j < p.B * S) idr[k] = __ldg(p.ids + t * EX * S + j);
+    }
+  };
+  auto emit = [&](int buf) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      const int j = lane + 32 * k;
+      if (j < LK) {
+        int r = -1;
+        if ((uint64_t)idr[k] < (uint64_t)ROWS) r = (int)((j % S) * ROWS + idr[k]);
+        srow[warp][buf][j] = r;
+        if (PF && r >= 0) pf_l2<PF>(p.arena + (int64_t)r * p.stride);
+      }
+    }
+  };
+  int64_t tile = (int64_t)blockIdx.x * WARPS + warp;
+  load_ids(tile);
+  emit(0);
+  load_ids(tile + nw);
+  for (int it = 0; tile < ntiles; tile += nw, ++it) {
+    emit((it + 1) & 1);            // rows of the NEXT tile: staged + prefetched into L2
+    load_ids(tile + 2 * nw);       // ids two tiles ahead travel during this iteration
+    __syncwarp();
+    const int* rows = srow[warp][it & 1];
+    const int64_t b0 = tile * EX;
+    const int nex = (int)min((int64_t)EX, p.B - b0);
+    const bool ok = g < nex;
+    const int64_t b = b0 + g;
+    float4 a = make_float4(0, 0, 0, 0);
+    float lin = 0.f;
+    for (int s0 = 0; s0 < S; s0 += U) {
+      float4 v[U];
+      float w[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int s = s0 + u;
+        v[u] = make_float4(0, 0, 0, 0);
+        w[u] = 0.f;
+        if (s < S) {
+          const int r = rows[g * S + s];
+          if (r >= 0) {
+            const float* row = p.arena + (int64_t)r * p.stride;
+            v[u] = ld16<F>(row + c * 4);
+            if (want_lin) w[u] = ld4<F>(row + D);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int s = s0 + u;
+        if (s < S) {
+          a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w;
+          lin += w[u];
+          if (p.stack && ok) *reinterpret_cast<float4*>(p.stack + (b * S + s) * D + c * 4) = v[u];
+        }
+      }
+    }
+    if (ok) *reinterpret_cast<float4*>(p.sum + b * D + c * 4) = a;
+    if (ok && want_lin) p.lin[b] = lin;
+    __syncwarp();
+  }
+}
+
 // ------------------------------------------------------------------------------------------ hybrid (round 2)
 // Rows arrive through REGISTER loads (the fastest way to ask for a row, see profiles/mb_gather_r02_*.jsonl), the stacked
 // output leaves through a per-warp shared-memory tile and ONE cp.async.bulk store per tile (13 KB contiguous) instead of
@@ -659,6 +745,7 @@ static bool make_map(CUtensorMap* tm, const float* base, int64_t rows, int strid
   return r == CUDA_SUCCESS;
 }
 
+static int g_sms = 148;   // --sms N: size every grid for N SMs (per-SM cap vs DRAM experiment)
 struct Ctx {
   P p[4];
   float *ref_stack, *ref_sum, *ref_lin;
@@ -725,6 +812,7 @@ int main(int argc, char** argv) {
     if (!strcmp(argv[i], "--iters")) iters = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--stride")) stride = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--only")) only = argv[++i];
+    else if (!strcmp(argv[i], "--sms")) g_sms = atoi(argv[++i]);
   }
   const int64_t B = 65536, total_rows = (int64_t)S * ROWS;
   Ctx c;
@@ -766,7 +854,7 @@ int main(int argc, char** argv) {
     fprintf(stderr, "%s: %d CTAs / SM\n", NAME, occ);                                                             \
     for (int st = 0; st < 2; ++st)                                                                                \
       for (int li = 0; li < (has_lin ? 2 : 1); ++li)                                                              \
-        run(NAME, c, st, li, [&](const P& p) { k_reg<F, U><<<148 * occ, 256>>>(p); }, alg(st, li));               \
+        run(NAME, c, st, li, [&](const P& p) { k_reg<F, U><<<g_sms * occ, 256>>>(p); }, alg(st, li));               \
   }
   RUN_REG(0, 13, "reg_nc_na")
   RUN_REG(1, 13, "reg_nc_na_L2_64B")
@@ -786,7 +874,7 @@ int main(int argc, char** argv) {
     fprintf(stderr, "%s: %zu B smem / CTA, %d CTAs / SM\n", NAME, sm, occ);                                       \
     for (int st = 0; st < 2; ++st)                                                                                \
       for (int li = 0; li < (has_lin ? 2 : 1); ++li)                                                              \
-        run(NAME, c, st, li, [&](const P& p) { k_cpasync<W, NB><<<148 * occ, W * 32, sm>>>(p); }, alg(st, li));   \
+        run(NAME, c, st, li, [&](const P& p) { k_cpasync<W, NB><<<g_sms * occ, W * 32, sm>>>(p); }, alg(st, li));   \
   }
   RUN_CPA(4, 2, "cpasync_w4_b2")
   RUN_CPA(2, 2, "cpasync_w2_b2")
@@ -805,7 +893,7 @@ int main(int argc, char** argv) {
     fprintf(stderr, "%s: %d CTAs / SM\n", NAME, occ);                                                             \
     for (int st = 0; st < 2; ++st)                                                                                \
       for (int li = (has_lin ? 1 : 0); li < (has_lin ? 2 : 1); ++li)                                              \
-        run(NAME, c, st, li, [&](const P& p) { k_reg2<F, ST, U, PAIR><<<148 * occ, 256, DUMMY>>>(p); }, alg(st, li)); \
+        run(NAME, c, st, li, [&](const P& p) { k_reg2<F, ST, U, PAIR><<<g_sms * occ, 256, DUMMY>>>(p); }, alg(st, li)); \
   }
   RUN_REG2(0, 0, 13, false, -1, 0, "r2_base")
   RUN_REG2(0, 0, 13, true, -1, 0, "r2_pair")
@@ -818,6 +906,26 @@ int main(int argc, char** argv) {
   RUN_REG2(0, 0, 13, false, -1, 100 * 1024, "r2_base_dummy100k")
   RUN_REG2(0, 0, 13, true, 0, 0, "r2_pair_carve0")
 
+
+#define RUN_PF(F, PF, U, W, CPS, NAME)                                                                            \
+  if (want(NAME)) {                                                                                               \
+    int occ = 0;                                                                                                  \
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pf<F, PF, U, W>, W * 32, 0));                        \
+    if (CPS > 0 && occ > CPS) occ = CPS;                                                                          \
+    fprintf(stderr, "%s: %d CTAs / SM\n", NAME, occ);                                                             \
+    for (int st = 0; st < 2; ++st)                                                                                \
+      for (int li = (has_lin ? 1 : 0); li < (has_lin ? 2 : 1); ++li)                                              \
+        run(NAME, c, st, li, [&](const P& p) { k_pf<F, PF, U, W><<<g_sms * occ, W * 32>>>(p); }, alg(st, li));      \
+  }
+  RUN_PF(0, 0, 13, 8, 0, "pf0_w8")            // no prefetch: baseline of this code shape
+  RUN_PF(0, 1, 13, 8, 0, "pf1_w8")
+  RUN_PF(0, 1, 13, 8, 1, "pf1_w8_c1")         // 1 CTA / SM: 31 MB of prefetched lines in flight
+  RUN_PF(0, 2, 13, 8, 0, "pf2_w8")
+  RUN_PF(0, 1, 7, 8, 0, "pf1_w8_u7")
+  RUN_PF(0, 1, 13, 4, 0, "pf1_w4")
+  RUN_PF(0, 1, 26, 8, 1, "pf1_w8_u26_c1")
+  RUN_PF(1, 1, 13, 8, 0, "pf1_w8_L2_64B")
+
 #define RUN_HYB(F, V8, DYN, W, U, NAME)                                                                           \
   if (want(NAME) && (!(V8) || stride == 32)) {                                                                    \
     size_t sm = (size_t)W * (TILE_BYTES + LK * 4);                                                                \
@@ -829,7 +937,7 @@ int main(int argc, char** argv) {
       for (int li = 0; li < (has_lin ? 2 : 1); ++li)                                                              \
         run(NAME, c, st, li, [&](const P& p) {                                                                    \
           if (DYN) { unsigned int z = 0; CK(cudaMemcpyToSymbolAsync(g_tile_counter, &z, 4, 0, cudaMemcpyHostToDevice, 0)); } \
-          k_hyb<F, V8, DYN, W, U><<<148 * occ, W * 32, sm>>>(p); }, alg(st, li));                                 \
+          k_hyb<F, V8, DYN, W, U><<<g_sms * occ, W * 32, sm>>>(p); }, alg(st, li));                                 \
   }
   RUN_HYB(0, false, false, 8, 13, "hyb_v4_nc")
   RUN_HYB(1, false, false, 8, 13, "hyb_v4_L2_64B")
@@ -856,7 +964,7 @@ int main(int argc, char** argv) {
     fprintf(stderr, "%s: %zu B smem / CTA, %d CTAs / SM\n", NAME, sm, occ);                                       \
     for (int st = 0; st < 2; ++st)                                                                                \
       for (int li = 0; li < LINMAX; ++li)                                                                         \
-        run(NAME, c, st, li, [&](const P& p) { k_tma<W, NB, MODE><<<148 * occ, W * 32, sm>>>(p, MAP); }, alg(st, li)); \
+        run(NAME, c, st, li, [&](const P& p) { k_tma<W, NB, MODE><<<g_sms * occ, W * 32, sm>>>(p, MAP); }, alg(st, li)); \
   }
   RUN_TMA(4, 2, 0, tm1, "bulk64_w4_b2", (has_lin ? 2 : 1))
   RUN_TMA(2, 3, 0, tm1, "bulk64_w2_b3", (has_lin ? 2 : 1))
