@@ -42,6 +42,7 @@ _SIGS = {
     "dr_fm_bwd": [_p, _p, _i64, _i, _i, _p, _p],
     "dr_dense_fwd": [_p, _p, _p, _i64, _i, _i, _i, _p, _p],
     "dr_dense_bwd": [_p, _p, _p, _p, _i64, _i, _i, _i, _p, _p, _p, _p, _p],
+    "dr_dense_bwd_chain": [_p, _p, _p, _p, _i64, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p],
     "dr_cross_fwd": [_p, _p, _p, _p, _p, _p, _f, _i64, _i, _i, _p, _p, _p, _p],
     "dr_cross_bwd": [_p, _p, _p, _p, _p, _f, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "dr_inbatch_softmax_fwd": [_p, _p, _p, _p, _p, _f, _i64, _i64, _i, _p, _p, _p],

@@ -18,7 +18,7 @@ void set_error(const char* fmt, ...) {
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
 extern int g_tune_embed_fwd_unroll, g_tune_embed_bwd_unroll, g_tune_embed_block, g_tune_embed_ctas_per_sm,
-    g_tune_embed_bwd_agg, g_tune_embed_bwd_mode, g_tune_embed_fwd_minblocks, g_tune_embed_fwd_linx, g_tune_embed_fwd_linx_shard, g_tune_embed_bwd_linx;
+    g_tune_embed_bwd_agg, g_tune_embed_bwd_mode, g_tune_embed_fwd_minblocks, g_tune_embed_fwd_linx, g_tune_embed_fwd_linx_shard, g_tune_embed_bwd_linx, g_tune_embed_l2_hints;
 extern int g_tune_topk_variant;
 extern int g_tune_gemm_prof, g_tune_tc_tma_out;
 extern int g_tune_gemm_variant, g_tune_gemm_splitk, g_tune_gemm_bn, g_tune_tc_mn, g_tune_tc_min_n;
@@ -43,6 +43,7 @@ extern "C" int dr_tune_set(const char* key, int value) {
   else if (!strcmp(key, "embed_fwd_linx")) g_tune_embed_fwd_linx = value;
   else if (!strcmp(key, "embed_fwd_linx_shard")) g_tune_embed_fwd_linx_shard = value;
   else if (!strcmp(key, "embed_bwd_linx")) g_tune_embed_bwd_linx = value;
+  else if (!strcmp(key, "embed_l2_hints")) g_tune_embed_l2_hints = value;
   else if (!strcmp(key, "gemm_variant")) g_tune_gemm_variant = value;
   else if (!strcmp(key, "gemm_splitk")) g_tune_gemm_splitk = value;
   else if (!strcmp(key, "gemm_bn")) g_tune_gemm_bn = value;

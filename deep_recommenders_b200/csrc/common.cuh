@@ -63,6 +63,44 @@ __device__ __forceinline__ float ldg_nc_na_f32(const float* p) {
   asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
   return r;
 }
+// L2 eviction-priority hints (experiment, knob embed_l2_hints): the random table rows are dead after one use
+// (evict_first), the stacked output is re-read by the next kernel (evict_last), the backward's atomically updated lines
+// should drain to HBM early instead of staying dirty in L2 until the next kernel's stores push them out.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ float4 ldg_nc_na_hint(const float* p, uint64_t pol) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ float ldg_nc_na_f32_hint(const float* p, uint64_t pol) {
+  float r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ void stg4_hint(float* p, float4 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void red_add_v4_hint(float* p, float4 v, uint64_t pol) {
+  asm volatile("red.global.add.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void red_add_f32_hint(float* p, float v, uint64_t pol) {
+  asm volatile("red.global.add.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+}
 // 128-bit load through the normal (L1-allocating) path.
 __device__ __forceinline__ float4 ldg4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 

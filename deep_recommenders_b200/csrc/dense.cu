@@ -125,14 +125,11 @@ extern "C" int dr_dense_fwd(const float* x, const float* w, const float* b, int6
   return gemm_launch(a, false, false, (cudaStream_t)stream);
 }
 
-extern "C" int dr_dense_bwd(const float* x, const float* w, const float* y, const float* gy, int64_t M,
-                            int K, int N, int act, float* gz_ws, float* gx, float* gw, float* gb,
-                            void* stream) {
-  DR_REQUIRE(x && w && gy && (gw || gx), DR_EINVAL, "dr_dense_bwd: null pointer");
-  DR_REQUIRE(M >= 0 && K >= 1 && N >= 1, DR_EINVAL, "dr_dense_bwd: bad shape");
-  DR_REQUIRE(act >= DR_ACT_NONE && act <= DR_ACT_TANH, DR_EINVAL, "dr_dense_bwd: unknown activation %d", act);
-  DR_REQUIRE(act == DR_ACT_NONE || (y && gz_ws), DR_EINVAL, "dr_dense_bwd: activation needs y and gz_ws");
-  cudaStream_t st = (cudaStream_t)stream;
+// prev_y != NULL: gx is written as (gz @ W^T) * act'(prev_y), i.e. ALREADY the pre-activation gradient of the layer
+// that produced x = act(prev_z) -- the activation-gradient pass of that layer disappears into this GEMM's epilogue.
+static int dense_bwd_impl(const float* x, const float* w, const float* y, const float* gy, int64_t M, int K, int N,
+                          int act, float* gz_ws, float* gx, float* gw, float* gb, const float* prev_y, int prev_act,
+                          cudaStream_t st) {
   if (gb) DR_CUDA_CALL(cudaMemsetAsync(gb, 0, sizeof(float) * N, st));
   if (M == 0) {
     if (gw) DR_CUDA_CALL(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)K * N, st));
@@ -147,11 +144,35 @@ extern "C" int dr_dense_bwd(const float* x, const float* w, const float* y, cons
     if (act != DR_ACT_NONE) gz = gz_ws;
   }
   if (gx) {
-    GemmArgs a = mk(gz, w, gx, M, K, N, N, N, K, EPI_STORE);   // gx[M,K] = gz[M,N] @ W^T
+    const bool chain = prev_y != nullptr && prev_act != DR_ACT_NONE;
+    GemmArgs a = mk(gz, w, gx, M, K, N, N, N, K, chain ? EPI_ACTGRAD : EPI_STORE);   // gx[M,K] = gz[M,N] @ W^T
+    if (chain) { a.aux0 = prev_y; a.act = prev_act; }
     if (int rc = gemm_launch(a, false, true, st)) return rc;
   }
   if (!gw) return DR_OK;      // caller computes the weight gradient in a second call (e.g. on another stream)
   return gemm_xt_g(x, gz, gw, M, K, N, st);
+}
+
+extern "C" int dr_dense_bwd(const float* x, const float* w, const float* y, const float* gy, int64_t M,
+                            int K, int N, int act, float* gz_ws, float* gx, float* gw, float* gb,
+                            void* stream) {
+  DR_REQUIRE(x && w && gy && (gw || gx), DR_EINVAL, "dr_dense_bwd: null pointer");
+  DR_REQUIRE(M >= 0 && K >= 1 && N >= 1, DR_EINVAL, "dr_dense_bwd: bad shape");
+  DR_REQUIRE(act >= DR_ACT_NONE && act <= DR_ACT_TANH, DR_EINVAL, "dr_dense_bwd: unknown activation %d", act);
+  DR_REQUIRE(act == DR_ACT_NONE || (y && gz_ws), DR_EINVAL, "dr_dense_bwd: activation needs y and gz_ws");
+  return dense_bwd_impl(x, w, y, gy, M, K, N, act, gz_ws, gx, gw, gb, nullptr, DR_ACT_NONE, (cudaStream_t)stream);
+}
+
+extern "C" int dr_dense_bwd_chain(const float* x, const float* w, const float* y, const float* gy, int64_t M,
+                                  int K, int N, int act, float* gz_ws, float* gx, float* gw, float* gb,
+                                  const float* prev_y, int prev_act, void* stream) {
+  DR_REQUIRE(x && w && gy && (gw || gx), DR_EINVAL, "dr_dense_bwd_chain: null pointer");
+  DR_REQUIRE(M >= 0 && K >= 1 && N >= 1, DR_EINVAL, "dr_dense_bwd_chain: bad shape");
+  DR_REQUIRE(act >= DR_ACT_NONE && act <= DR_ACT_TANH && prev_act >= DR_ACT_NONE && prev_act <= DR_ACT_TANH, DR_EINVAL,
+             "dr_dense_bwd_chain: unknown activation %d / %d", act, prev_act);
+  DR_REQUIRE(act == DR_ACT_NONE || (y && gz_ws), DR_EINVAL, "dr_dense_bwd_chain: activation needs y and gz_ws");
+  DR_REQUIRE(prev_act == DR_ACT_NONE || (prev_y && gx), DR_EINVAL, "dr_dense_bwd_chain: prev_act needs prev_y and gx");
+  return dense_bwd_impl(x, w, y, gy, M, K, N, act, gz_ws, gx, gw, gb, prev_y, prev_act, (cudaStream_t)stream);
 }
 
 extern "C" int dr_cross_fwd(const float* x0, const float* x, const float* w, const float* uk, const float* vk,

@@ -30,6 +30,8 @@ int g_tune_embed_fwd_linx = 1;        // 1 (default) = LINX forward mapping for 
                                       // vs 86.0 us at C2 (tools/ab_embed_fwd.py, profiles/ab_embed_fwd_r01.json), bit-identical
 int g_tune_embed_bwd_linx = 0;        // LINX mapping for the slot-parallel backward (in-row weight, D <= 32): unmeasured
 int g_tune_embed_fwd_linx_shard = 0;  // same mapping for the row-sharded (peer-memory) forward: off until measured at N > 1
+int g_tune_embed_l2_hints = 0;        // bit 0: forward row loads L2::evict_first; bit 1: stacked-output stores L2::evict_last;
+                                      // bit 2: backward vector atomics L2::evict_first; bit 3: backward stack / g_stack loads evict_first
 int g_tune_embed_fwd_minblocks = 0;   // forward register cap: 0 = none (ptxas picks, 108 regs -> 2 CTAs of 256 / SM),
                                       // 3 / 4 = __launch_bounds__(256, n): <= 85 / 64 registers, 24 / 32 warps per SM
 
@@ -56,6 +58,7 @@ struct EmbedFwdParams {
   float* out_stack;
   float* out_sum;
   float* out_logit;
+  int l2_hints;
 };
 
 struct EmbedBwdParams {
@@ -80,6 +83,9 @@ struct EmbedBwdParams {
   float* const* peer_bases;
   const int64_t* slot_offsets;
   int64_t shard_lin_off;
+  int l2_hints;
+  int mode;     // 0 = slot-parallel kernel, 1 = example-parallel; a per-call copy of the developer knob (the entry
+                // points never write a knob: sharded addressing simply passes mode = 0)
 };
 
 constexpr int kMaxShardWorld = 64;
@@ -132,6 +138,8 @@ __global__ void __launch_bounds__(MINB ? 256 : 512, MINB ? MINB : 1) embed_fm_fw
   const bool linx_lane = LINX && p.lin_in_row && c == 0 && p.out_logit != nullptr;
   const float bias = p.bias ? __ldg(p.bias) : 0.f;
   const IdT* __restrict__ ids = reinterpret_cast<const IdT*>(p.ids);
+  const bool h_ld = (p.l2_hints & 1) != 0, h_st = (p.l2_hints & 2) != 0;
+  const uint64_t pol_first = l2_policy_evict_first(), pol_last = l2_policy_evict_last();
 
   const int64_t ntiles = (p.B + G - 1) / G;
   const int64_t warp0 = (int64_t)blockIdx.x * warps_per_cta + warp_in_cta;
@@ -174,8 +182,13 @@ __global__ void __launch_bounds__(MINB ? 256 : 512, MINB ? MINB : 1) embed_fm_fw
               const int64_t local = sw_pow2 ? (r >> sw_shift) : (r / SW);
               rowp = s_peer[owner] + (size_t)local * p.row_stride;
             }
-            v[u] = ldg_nc_na(rowp + c * 4);
-            if (LINX && linx_lane) wv[u] = ldg_nc_na_f32(rowp + D);
+            if (h_ld) {
+              v[u] = ldg_nc_na_hint(rowp + c * 4, pol_first);
+              if (LINX && linx_lane) wv[u] = ldg_nc_na_f32_hint(rowp + D, pol_first);
+            } else {
+              v[u] = ldg_nc_na(rowp + c * 4);
+              if (LINX && linx_lane) wv[u] = ldg_nc_na_f32(rowp + D);
+            }
           }
         }
       }
@@ -190,7 +203,10 @@ __global__ void __launch_bounds__(MINB ? 256 : 512, MINB ? MINB : 1) embed_fm_fw
             sum.x += v[u].x; sum.y += v[u].y; sum.z += v[u].z; sum.w += v[u].w;
             sq.x = fmaf(v[u].x, v[u].x, sq.x); sq.y = fmaf(v[u].y, v[u].y, sq.y);
             sq.z = fmaf(v[u].z, v[u].z, sq.z); sq.w = fmaf(v[u].w, v[u].w, sq.w);
-            if (ostack && ex_ok && chunk_ok) stg4(ostack + (size_t)s * D, v[u]);
+            if (ostack && ex_ok && chunk_ok) {
+              if (h_st) stg4_hint(ostack + (size_t)s * D, v[u], pol_last);
+              else stg4(ostack + (size_t)s * D, v[u]);
+            }
           }
         }
       }
@@ -404,6 +420,8 @@ __global__ void __launch_bounds__(256) embed_fm_bwd_sp_kernel(const EmbedBwdPara
   const int64_t warp0 = (int64_t)blockIdx.x * warps_per_cta + warp_in_cta;
   const int64_t nwarps = (int64_t)gridDim.x * warps_per_cta;
   float bias_acc = 0.f;
+  const bool h_red = (p.l2_hints & 4) != 0, h_ld = (p.l2_hints & 8) != 0;
+  const uint64_t pol_first = l2_policy_evict_first();
 
   for (int64_t b = warp0; b < p.B; b += nwarps) {
     const float gl = has_fm ? __ldg(p.g_logit + b) : 0.f;
@@ -430,8 +448,13 @@ __global__ void __launch_bounds__(256) embed_fm_bwd_sp_kernel(const EmbedBwdPara
         if (s < S) {
           id[u] = (int64_t)__ldg(my_ids + s);
           if (chunk_ok) {
-            if (has_fm) e[u] = ldg_nc_na(p.stack + ex0 + (size_t)s * D);
-            if (has_gs) gs[u] = ldg_nc_na(p.g_stack + ex0 + (size_t)s * D);
+            if (h_ld) {
+              if (has_fm) e[u] = ldg_nc_na_hint(p.stack + ex0 + (size_t)s * D, pol_first);
+              if (has_gs) gs[u] = ldg_nc_na_hint(p.g_stack + ex0 + (size_t)s * D, pol_first);
+            } else {
+              if (has_fm) e[u] = ldg_nc_na(p.stack + ex0 + (size_t)s * D);
+              if (has_gs) gs[u] = ldg_nc_na(p.g_stack + ex0 + (size_t)s * D);
+            }
           }
         }
       }
@@ -454,10 +477,16 @@ __global__ void __launch_bounds__(256) embed_fm_bwd_sp_kernel(const EmbedBwdPara
             d.y = scale * fmaf(gl, sum.y - e[u].y, gs[u].y);
             d.z = scale * fmaf(gl, sum.z - e[u].z, gs[u].z);
             d.w = scale * fmaf(gl, sum.w - e[u].w, gs[u].w);
-            red_add_v4(row + c * 4, d);
-            if (LINX && linx_lane) red_add_f32(row + D, scale * gl);
+            if (h_red) {
+              red_add_v4_hint(row + c * 4, d, pol_first);
+              if (LINX && linx_lane) red_add_f32_hint(row + D, scale * gl, pol_first);
+            } else {
+              red_add_v4(row + c * 4, d);
+              if (LINX && linx_lane) red_add_f32(row + D, scale * gl);
+            }
           } else if (lin_lane) {
-            red_add_v4(row + c * 4, make_float4(scale * gl, 0.f, 0.f, 0.f));
+            if (h_red) red_add_v4_hint(row + c * 4, make_float4(scale * gl, 0.f, 0.f, 0.f), pol_first);
+            else red_add_v4(row + c * 4, make_float4(scale * gl, 0.f, 0.f, 0.f));
           }
           if (has_lin && c == 0) red_add_f32(s_lin[s] + (size_t)id[u] * p.lin_stride, scale * gl);
           if (SHARD && has_fm && p.shard_lin_off > 0 && c == 0) {
@@ -662,7 +691,7 @@ static int launch_bwd_sp_u(const EmbedBwdParams& p, cudaStream_t st) {
 
 template <int LPR, typename IdT>
 static int launch_bwd(const EmbedBwdParams& p, cudaStream_t st) {
-  if (g_tune_embed_bwd_mode == 0) {
+  if (p.mode == 0) {
     switch (g_tune_embed_bwd_unroll) {
       case 1: return launch_bwd_sp_u<LPR, IdT, 1>(p, st);
       case 4: return launch_bwd_sp_u<LPR, IdT, 4>(p, st);
@@ -739,6 +768,7 @@ extern "C" int dr_embed_fm_fwd(const float* const* table_ptrs, const float* cons
   p.table_ptrs = table_ptrs; p.lin_ptrs = lin_ptrs; p.rows = rows; p.ids = ids; p.bias = bias;
   p.B = B; p.S = S; p.D = D; p.out_stack = out_stack; p.out_sum = out_sum; p.out_logit = out_logit;
   p.row_stride = row_stride; p.lin_stride = lin_stride; p.lin_in_row = lin_in_row;
+  p.l2_hints = g_tune_embed_l2_hints;
   cudaStream_t st = (cudaStream_t)stream;
   if (g_tune_embed_fwd_linx && lin_in_row && out_logit && lpr_for(D, 0) <= 8) return dispatch_fwd_linx(p, id_bytes, st);
   DR_DISPATCH_LPR(launch_fwd, p, st);
@@ -770,8 +800,10 @@ extern "C" int dr_embed_fm_bwd(const void* ids, int id_bytes, const int64_t* row
   p.B = B; p.S = S; p.D = D; p.grad_table_ptrs = grad_table_ptrs; p.grad_lin_ptrs = grad_lin_ptrs;
   p.g_bias = g_bias; p.scale = scale; p.row_stride = row_stride; p.lin_stride = lin_stride;
   p.lin_in_row = lin_in_row;
+  p.l2_hints = g_tune_embed_l2_hints;
+  p.mode = g_tune_embed_bwd_mode;
   cudaStream_t st = (cudaStream_t)stream;
-  if (g_tune_embed_bwd_linx && g_tune_embed_bwd_mode == 0 && lin_in_row && g_logit && lpr_for(D, 0) <= 8) {
+  if (g_tune_embed_bwd_linx && p.mode == 0 && lin_in_row && g_logit && lpr_for(D, 0) <= 8) {
     const int lpr = lpr_for(D, 0);
 #define DR_BLINX(L) (id_bytes == 8 ? launch_bwd_sp_u<L, int64_t, 2, true>(p, st) : launch_bwd_sp_u<L, int32_t, 2, true>(p, st))
     switch (lpr) {
@@ -874,9 +906,8 @@ extern "C" int dr_embed_fm_bwd_sharded(float* const* peer_bases, int world, cons
   p.B = B; p.S = S; p.D = D; p.g_bias = g_bias; p.scale = scale;
   p.row_stride = row_stride; p.lin_stride = row_stride; p.lin_in_row = lin_in_row;
   p.shard_world = world; p.peer_bases = peer_bases; p.slot_offsets = slot_offsets; p.shard_lin_off = lin_offset;
+  p.mode = 0;                     // only the slot-parallel kernel implements sharded addressing
   cudaStream_t st = (cudaStream_t)stream;
-  const int saved_mode = g_tune_embed_bwd_mode;
-  g_tune_embed_bwd_mode = 0;      // only the slot-parallel kernel implements sharded addressing
   int rc;
   do {
     const int lpr__ = lpr_for(p.D, p.lin_in_row);
@@ -891,6 +922,5 @@ extern "C" int dr_embed_fm_bwd_sharded(float* const* peer_bases, int world, cons
     }
 #undef DR_SH
   } while (0);
-  g_tune_embed_bwd_mode = saved_mode;
   return rc;
 }

@@ -32,7 +32,7 @@ namespace dr {
 
 // ---- workspace registered by the host (dr_set_workspace) ----------------------------------------
 int g_tune_gemm_bn = 0;   // 0 = auto, 128 or 256: tensor-core tile width
-int g_tune_tc_min_n = 96;
+int g_tune_tc_min_n = 32;   // 32 since round 2 (BN = 32 / 64 tiles of the in-kernel-split core: C2 step 0.849 -> 0.822 ms)
 int g_tune_tc_mn = 1;     // 1 = feed MN-major operands as stored (SWIZZLE_128B_BASE32B); 0 = transpose them in the split pre-pass
 static void* g_ws_ptr = nullptr;
 static size_t g_ws_bytes = 0;
@@ -473,10 +473,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
 #pragma unroll
               for (int jj = 0; jj < 32; ++jj) o[jj] = __uint_as_float(r[jj]);
             } else if (a.epi == EPI_BIAS_ACT) {
+              // one coalesced bias load per slab (lane l holds bias[nb + l]), broadcast by shuffles; the activation
+              // switch is hoisted out of the element loop
+              const float bl = (a.bias && nb + lane < a.N) ? __ldg(a.bias + nb + lane) : 0.f;
+              if (a.act == DR_ACT_RELU) {
 #pragma unroll
-              for (int jj = 0; jj < 32; ++jj) {
-                const float bv = (a.bias && nb + jj < a.N) ? __ldg(a.bias + nb + jj) : 0.f;
-                o[jj] = act_apply(__uint_as_float(r[jj]) + bv, a.act);
+                for (int jj = 0; jj < 32; ++jj)
+                  o[jj] = fmaxf(__uint_as_float(r[jj]) + __shfl_sync(0xffffffffu, bl, jj), 0.f);
+              } else if (a.act == DR_ACT_NONE) {
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) o[jj] = __uint_as_float(r[jj]) + __shfl_sync(0xffffffffu, bl, jj);
+              } else {
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj)
+                  o[jj] = act_apply(__uint_as_float(r[jj]) + __shfl_sync(0xffffffffu, bl, jj), a.act);
+              }
+            } else if (a.epi == EPI_ACTGRAD && a.act == DR_ACT_RELU) {
+              // relu'(y) = [y > 0]: the thread reads its own row of y (128 contiguous bytes per slab)
+#pragma unroll
+              for (int jj = 0; jj < 32; jj += 4) {
+                float4 yv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row_ok && nb + jj + 3 < a.N) yv = __ldg(reinterpret_cast<const float4*>(a.aux0 + m * a.ldc + nb + jj));
+                else if (row_ok) {
+                  if (nb + jj + 0 < a.N) yv.x = __ldg(a.aux0 + m * a.ldc + nb + jj + 0);
+                  if (nb + jj + 1 < a.N) yv.y = __ldg(a.aux0 + m * a.ldc + nb + jj + 1);
+                  if (nb + jj + 2 < a.N) yv.z = __ldg(a.aux0 + m * a.ldc + nb + jj + 2);
+                }
+                o[jj + 0] = yv.x > 0.f ? __uint_as_float(r[jj + 0]) : 0.f;
+                o[jj + 1] = yv.y > 0.f ? __uint_as_float(r[jj + 1]) : 0.f;
+                o[jj + 2] = yv.z > 0.f ? __uint_as_float(r[jj + 2]) : 0.f;
+                o[jj + 3] = yv.w > 0.f ? __uint_as_float(r[jj + 3]) : 0.f;
               }
             } else {
 #pragma unroll
@@ -607,7 +633,7 @@ bool gemm_tc_eligible(const GemmArgs& a, bool ta, bool tb) {
   if (g_tune_gemm_variant != 1) return false;
   // measured (profiles/README.md): for N = 32 the extra hi/lo split of the activations costs more than the
   // 128 x 32 tensor-core tile saves over the FFMA kernel, so skinny layers stay on FFMA unless tc_min_n is lowered
-  if (a.N < g_tune_tc_min_n || (a.N & 3) || a.M < 64 || a.K < 32) return false;
+  if (a.N < (g_tune_tc_min_n > 96 ? g_tune_tc_min_n : 96) || (a.N & 3) || a.M < 64 || a.K < 32) return false;
   // operands already K-major are split in place with float4 accesses
   if ((!ta || g_tune_tc_mn) && ((a.lda & 3) || !aligned16(a.A))) return false;
   if ((tb || g_tune_tc_mn) && ((a.ldb & 3) || !aligned16(a.B))) return false;

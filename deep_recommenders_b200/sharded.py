@@ -256,17 +256,22 @@ class ShardedDeepFMTrainStep:
                                             self.labels.data_ptr(), B, self.prob.data_ptr(), self.loss.data_ptr(),
                                             gz.data_ptr(), st()), "dr_bce")
             mark("bce")
-            for i in range(len(self.layers) - 1, 0, -1):
+            L = len(self.layers)       # chained backward (dr_dense_bwd_chain): see DeepFMTrainStep._enqueue
+            for i in range(L - 1, 0, -1):
                 l = self.layers[i]
+                top = i == L - 1
                 xin, Kin, gx = self.acts[i - 1], self.layers[i - 1].units, self.g_acts[i - 1]
-                check(lib.dr_dense_bwd(xin.data_ptr(), self.w[i].data_ptr(), self.acts[i].data_ptr(),
-                                       self.g_acts[i].data_ptr(), B, Kin, l.units, l._act, ops._ptr(self.gz_ws[i]),
-                                       gx.data_ptr(), self.gw[i].data_ptr(), self.gb[i].data_ptr(), st()),
-                      "dr_dense_bwd")
+                check(lib.dr_dense_bwd_chain(xin.data_ptr(), self.w[i].data_ptr(),
+                                             self.acts[i].data_ptr() if top else None, self.g_acts[i].data_ptr(), B, Kin,
+                                             l.units, l._act if top else 0, ops._ptr(self.gz_ws[i]) if top else None,
+                                             gx.data_ptr(), self.gw[i].data_ptr(), self.gb[i].data_ptr(), xin.data_ptr(),
+                                             self.layers[i - 1]._act, st()), "dr_dense_bwd_chain")
                 mark(f"dense_bwd_{i}")
             l = self.layers[0]      # layer 0: the input gradient first (the embedding update needs it) ...
-            check(lib.dr_dense_bwd(self.stack.data_ptr(), self.w[0].data_ptr(), self.acts[0].data_ptr(),
-                                   self.g_acts[0].data_ptr(), B, S * D, l.units, l._act, ops._ptr(self.gz_ws[0]),
+            top0 = L == 1
+            check(lib.dr_dense_bwd(self.stack.data_ptr(), self.w[0].data_ptr(), self.acts[0].data_ptr() if top0 else None,
+                                   self.g_acts[0].data_ptr(), B, S * D, l.units, l._act if top0 else 0,
+                                   ops._ptr(self.gz_ws[0]) if top0 else None,
                                    self.g_stack.data_ptr(), None, self.gb[0].data_ptr(), st()), "dr_dense_bwd(dx)")
             mark("dense_bwd_0_dx")
 
@@ -280,7 +285,7 @@ class ShardedDeepFMTrainStep:
 
         def seg_dw():               # ... meanwhile, on the main stream: layer-0 weight gradient + FM bias gradient
             l = self.layers[0]
-            gz0 = self.gz_ws[0] if l._act != 0 else self.g_acts[0]
+            gz0 = (self.gz_ws[0] if l._act != 0 else self.g_acts[0]) if len(self.layers) == 1 else self.g_acts[0]
             check(lib.dr_dense_bwd(self.stack.data_ptr(), self.w[0].data_ptr(), None, gz0.data_ptr(), B, S * D, l.units,
                                    0, None, None, self.gw[0].data_ptr(), None, st()), "dr_dense_bwd(dw)")
             check(lib.dr_gemm_plane_cache(0), "dr_gemm_plane_cache")

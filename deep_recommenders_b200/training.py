@@ -153,19 +153,28 @@ class DeepFMTrainStep:
         check(lib.dr_bce_logits_fwd_bwd(self.acts[-1].data_ptr(), self.fm_logit.data_ptr(), self.labels.data_ptr(), B,
                                         self.prob.data_ptr(), self.loss.data_ptr(), gz.data_ptr(), st), "dr_bce")
         mark("bce")
-        for i in range(len(self.layers) - 1, 0, -1):
+        # Chained backward: layer i's input gradient leaves its GEMM already multiplied by act'(output of layer i-1)
+        # (dr_dense_bwd_chain), so g_acts[i-1] IS the pre-activation gradient of layer i-1 and no layer below the top
+        # needs its own activation-gradient pass (only the column sums for the bias gradient).
+        L = len(self.layers)
+        for i in range(L - 1, 0, -1):
             l = self.layers[i]
+            top = i == L - 1
             xin, Kin, gx = self.acts[i - 1], self.layers[i - 1].units, self.g_acts[i - 1]
-            check(lib.dr_dense_bwd(xin.data_ptr(), self.w[i].data_ptr(), self.acts[i].data_ptr(),
-                                   self.g_acts[i].data_ptr(), B, Kin, l.units, l._act, ops._ptr(self.gz_ws[i]),
-                                   gx.data_ptr(), self.gw[i].data_ptr(), ops._ptr(self.gb[i]), st), "dr_dense_bwd")
+            check(lib.dr_dense_bwd_chain(xin.data_ptr(), self.w[i].data_ptr(), self.acts[i].data_ptr() if top else None,
+                                         self.g_acts[i].data_ptr(), B, Kin, l.units, l._act if top else 0,
+                                         ops._ptr(self.gz_ws[i]) if top else None, gx.data_ptr(), self.gw[i].data_ptr(),
+                                         ops._ptr(self.gb[i]), xin.data_ptr(), self.layers[i - 1]._act, st),
+                  "dr_dense_bwd_chain")
             mark(f"dense_bwd_{i}")
-        # layer 0: input gradient first, then its weight gradient (tensor cores, reads cached planes) runs
+        # layer 0: input gradient first, then its weight gradient (tensor cores) runs
         # CONCURRENTLY with the HBM-bound embedding update on a side stream
         l = self.layers[0]
-        gz0 = self.gz_ws[0] if l._act != 0 else self.g_acts[0]
-        check(lib.dr_dense_bwd(self.stack.data_ptr(), self.w[0].data_ptr(), self.acts[0].data_ptr(),
-                               self.g_acts[0].data_ptr(), B, S * D, l.units, l._act, ops._ptr(self.gz_ws[0]),
+        top0 = L == 1
+        gz0 = (self.gz_ws[0] if l._act != 0 else self.g_acts[0]) if top0 else self.g_acts[0]
+        check(lib.dr_dense_bwd(self.stack.data_ptr(), self.w[0].data_ptr(), self.acts[0].data_ptr() if top0 else None,
+                               self.g_acts[0].data_ptr(), B, S * D, l.units, l._act if top0 else 0,
+                               ops._ptr(self.gz_ws[0]) if top0 else None,
                                self.g_stack.data_ptr(), None, ops._ptr(self.gb[0]), st), "dr_dense_bwd(dx)")
         mark("dense_bwd_0_dx")
         main = torch.cuda.current_stream()

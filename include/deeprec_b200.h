@@ -129,6 +129,14 @@ int dr_dense_fwd(const float* x, const float* w, const float* b, int64_t M, int 
 int dr_dense_bwd(const float* x, const float* w, const float* y, const float* gy,
                  int64_t M, int K, int N, int act,
                  float* gz_ws, float* gx, float* gw, float* gb, void* stream);
+/* Same, chained through a stack of Dense layers (deepfm.py:30-34, estimator dnn.py:17-29): x of this layer is
+ * act_prev(z_prev) of the layer below with output prev_y = x; gx is then written as (gz @ W^T) * act_prev'(prev_y),
+ * i.e. already the PRE-activation gradient of the layer below (fused into the GEMM epilogue), so that layer's own
+ * call passes act = DR_ACT_NONE with this gx as its gy.  prev_act == DR_ACT_NONE: identical to dr_dense_bwd. */
+int dr_dense_bwd_chain(const float* x, const float* w, const float* y, const float* gy,
+                       int64_t M, int K, int N, int act,
+                       float* gz_ws, float* gx, float* gw, float* gb,
+                       const float* prev_y, int prev_act, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Row X: Cross layer (DCN-v2 matrix form).

@@ -217,3 +217,34 @@ def test_cross_stack_like_reference_test():
     assert np.allclose(logits.detach().cpu().numpy(), ref, rtol=1e-5, atol=1e-5)
     cfg = c1.get_config()
     assert set(["projection_dim", "diag_scale", "use_bias", "kernel_init", "kernel_regu", "bias_init", "bias_regu"]) <= set(cfg)
+
+
+@pytest.mark.parametrize("M,K,N", [(300, 256, 32), (257, 416, 256), (1000, 32, 1), (130, 33, 17)])
+@pytest.mark.parametrize("prev_act", ["relu", "tanh", None])
+def test_dense_bwd_chain_fuses_previous_activation_gradient(M, K, N, prev_act):
+    """dr_dense_bwd_chain: gx = (gz @ W^T) * act_prev'(prev_y) -- the activation-gradient pass of the layer below,
+    folded into this layer's input-gradient GEMM (deepfm.py:30-34 stack of Dense layers)."""
+    from deep_recommenders_b200 import _lib, ops
+    lib = _lib.load()
+    rng = np.random.default_rng(M + K + N)
+    z_prev = rng.standard_normal((M, K)).astype(np.float32)
+    x = R.act(z_prev, prev_act).astype(np.float32)                     # output of the layer below = this layer's input
+    w = (rng.standard_normal((K, N)) / np.sqrt(K)).astype(np.float32)
+    gy = rng.standard_normal((M, N)).astype(np.float32)
+    xt, wt, gyt = cu(x), cu(w), cu(gy)
+    gx = torch.empty((M, K), device="cuda")
+    gw = torch.empty((K, N), device="cuda")
+    gb = torch.empty((N,), device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.dr_dense_bwd_chain(xt.data_ptr(), wt.data_ptr(), None, gyt.data_ptr(), M, K, N, 0, None, gx.data_ptr(),
+                                      gw.data_ptr(), gb.data_ptr(), xt.data_ptr(), ops.act_code(prev_act), st),
+               "dr_dense_bwd_chain")
+    gy64 = gy.astype(np.float64)
+    gx_lin, gw_ref, gb_ref = gy64 @ w.astype(np.float64).T, x.astype(np.float64).T @ gy64, gy64.sum(0)
+    x64 = x.astype(np.float64)
+    dact = {"relu": (x64 > 0).astype(np.float64), "tanh": 1 - x64 * x64, None: np.ones_like(x64)}[prev_act]
+    agy = np.abs(gy).astype(np.float64)
+    sx = (agy @ np.abs(w).T.astype(np.float64)) * np.abs(dact)
+    assert (np.abs(gx.cpu().numpy() - gx_lin * dact) <= 2e-5 * sx + 1e-6).all()
+    assert (np.abs(gw.cpu().numpy() - gw_ref) <= 2e-5 * (np.abs(x64).T @ agy) + 1e-6).all()
+    assert (np.abs(gb.cpu().numpy() - gb_ref) <= 2e-5 * agy.sum(0) + 1e-6).all()
