@@ -54,11 +54,16 @@ _SIGS = {
     "dr_unpermute_rows": [_p, _p, _i64, _i, _p, _p],
     "dr_sgd_step": [_p, _p, _i64, _f, _p],
     "dr_bce_logits_fwd_bwd": [_p, _p, _p, _i64, _p, _p, _p, _p],
+    "dr_dense_head_bce_fwd_bwd": [_p, _p, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     # SURVEY 8(f) "next" rows
     "dr_adam_step": [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _i, _p, _p],
     "dr_adam_advance": [_p, _f, _f, _f, _p, _p],
     "dr_lazy_adam_rows": [_p, _i, _i64, _i, _i, _p, _p, _p, _p, _p, _p, _i64, _i, _p, _p, _p, _p, _p, _p, _p,
                           _f, _f, _f, _p],
+    "dr_embed_adam_state_stride": [_i],
+    "dr_embed_adam_count": [_p, _i, _i64, _i, _i, _p, _p, _p, _p],
+    "dr_embed_fm_bwd_adam": [_p, _i, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i64, _i64, _i, _p, _p, _p, _p, _p,
+                             _f, _f, _f, _p],
     "dr_hash_bucket_i64": [_p, _i64, _i64, _p, _p],
     "dr_hash_bucket_bytes": [_p, _p, _i64, _i64, _p, _p],
     "dr_hash_bucket_i64_host": [_p, _i64, _i64, _p],

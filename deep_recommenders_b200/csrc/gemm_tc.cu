@@ -488,22 +488,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                 for (int jj = 0; jj < 32; ++jj)
                   o[jj] = act_apply(__uint_as_float(r[jj]) + __shfl_sync(0xffffffffu, bl, jj), a.act);
               }
-            } else if (a.epi == EPI_ACTGRAD && a.act == DR_ACT_RELU) {
-              // relu'(y) = [y > 0]: the thread reads its own row of y (128 contiguous bytes per slab)
+            } else if (a.epi == EPI_ACTGRAD && a.act == DR_ACT_RELU && nb + 31 < a.N && mw + 31 < a.M) {
+              // relu'(y) = [y > 0].  The y slab is fetched COALESCED (each load instruction reads 4 whole 128-B rows) into
+              // the staging buffer in the same swizzled layout, then every thread reads its own row from shared memory
+              // (a thread reading its row straight from global memory costs 32 scattered 16-B requests per instruction).
 #pragma unroll
-              for (int jj = 0; jj < 32; jj += 4) {
-                float4 yv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (row_ok && nb + jj + 3 < a.N) yv = __ldg(reinterpret_cast<const float4*>(a.aux0 + m * a.ldc + nb + jj));
-                else if (row_ok) {
-                  if (nb + jj + 0 < a.N) yv.x = __ldg(a.aux0 + m * a.ldc + nb + jj + 0);
-                  if (nb + jj + 1 < a.N) yv.y = __ldg(a.aux0 + m * a.ldc + nb + jj + 1);
-                  if (nb + jj + 2 < a.N) yv.z = __ldg(a.aux0 + m * a.ldc + nb + jj + 2);
-                }
-                o[jj + 0] = yv.x > 0.f ? __uint_as_float(r[jj + 0]) : 0.f;
-                o[jj + 1] = yv.y > 0.f ? __uint_as_float(r[jj + 1]) : 0.f;
-                o[jj + 2] = yv.z > 0.f ? __uint_as_float(r[jj + 2]) : 0.f;
-                o[jj + 3] = yv.w > 0.f ? __uint_as_float(r[jj + 3]) : 0.f;
+              for (int i = 0; i < 8; ++i) {
+                const int rr = i * 4 + (lane >> 3), ch = lane & 7;
+                const float4 yv = __ldg(reinterpret_cast<const float4*>(a.aux0 + (mw + rr) * a.ldc + nb + ch * 4));
+                *reinterpret_cast<float4*>(sb + rr * 128 + ((ch ^ (rr & 7)) << 4)) = yv;
               }
+              __syncwarp();
+#pragma unroll
+              for (int ch = 0; ch < 8; ++ch) {
+                const float4 yv = *reinterpret_cast<const float4*>(sb + lane * 128 + ((ch ^ (lane & 7)) << 4));
+                o[4 * ch + 0] = yv.x > 0.f ? __uint_as_float(r[4 * ch + 0]) : 0.f;
+                o[4 * ch + 1] = yv.y > 0.f ? __uint_as_float(r[4 * ch + 1]) : 0.f;
+                o[4 * ch + 2] = yv.z > 0.f ? __uint_as_float(r[4 * ch + 2]) : 0.f;
+                o[4 * ch + 3] = yv.w > 0.f ? __uint_as_float(r[4 * ch + 3]) : 0.f;
+              }
+              __syncwarp();     // every lane has read its row before anyone overwrites the buffer with the output
             } else {
 #pragma unroll
               for (int jj = 0; jj < 32; ++jj)
@@ -658,6 +662,8 @@ bool gemm_tc_eligible(const GemmArgs& a, bool ta, bool tb) {
   return true;
 }
 
+int g_tune_tc_stages = 0;    // 0 = default ring depth per tile width; 2 = two stages for BN = 128 (leaves ~64 KB of shared
+                            // memory per SM so an HBM-bound kernel on another stream can co-reside with the persistent GEMM)
 int g_tune_tc_tma_out = 1;   // 1 (default) = epilogue through shared memory + TMA store / reduce-add; 0 = round-1 register stores
 int g_tune_gemm_prof = 0;   // 1 = launch the instrumented instantiation (BN = 128 INSPLIT only); read with dr_gemm_prof_read
 
@@ -744,6 +750,7 @@ int gemm_tc_launch(const GemmArgs& a0, bool ta, bool tb, cudaStream_t st) {
     } while (0)
     if (bn == 32) DR_TC2_LAUNCH(32, 4);
     if (bn == 64) DR_TC2_LAUNCH(64, 4);
+    if (g_tune_tc_stages == 2) DR_TC2_LAUNCH(128, 2);
     DR_TC2_LAUNCH(128, 3);
 #undef DR_TC2_LAUNCH
   }

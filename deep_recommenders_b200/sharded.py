@@ -246,33 +246,49 @@ class ShardedDeepFMTrainStep:
         def seg_tower():
             check(lib.dr_gemm_plane_cache(1), "dr_gemm_plane_cache")
             x, K = self.stack, S * D
-            for i, l in enumerate(self.layers):
+            L = len(self.layers)
+            gz = self.g_acts[-1]
+            head = (L >= 2 and self.layers[-1].units == 1 and self.layers[-1]._act == 0 and self.layers[-2].units <= 256)
+            for i, l in enumerate(self.layers[:L - 1] if head else self.layers):
                 check(lib.dr_dense_fwd(x.data_ptr(), self.w[i].data_ptr(), self.b[i].data_ptr(), B, K, l.units,
                                        l._act, self.acts[i].data_ptr(), st()), "dr_dense_fwd")
                 x, K = self.acts[i], l.units
                 mark(f"dense_fwd_{i}")
-            gz = self.g_acts[-1]
-            check(lib.dr_bce_logits_fwd_bwd(self.acts[-1].data_ptr(), self.fm_logit.data_ptr(),
-                                            self.labels.data_ptr(), B, self.prob.data_ptr(), self.loss.data_ptr(),
-                                            gz.data_ptr(), st()), "dr_bce")
-            mark("bce")
-            L = len(self.layers)       # chained backward (dr_dense_bwd_chain): see DeepFMTrainStep._enqueue
-            for i in range(L - 1, 0, -1):
+            if head:      # final Dense(1) + BCE + their backward: one kernel (see DeepFMTrainStep._enqueue)
+                check(lib.dr_dense_head_bce_fwd_bwd(self.acts[L - 2].data_ptr(), self.w[L - 1].data_ptr(),
+                                                    self.b[L - 1].data_ptr(), self.fm_logit.data_ptr(),
+                                                    self.labels.data_ptr(), B, self.layers[L - 2].units,
+                                                    self.layers[L - 2]._act, self.acts[L - 1].data_ptr(),
+                                                    self.prob.data_ptr(), self.loss.data_ptr(), gz.data_ptr(),
+                                                    self.g_acts[L - 2].data_ptr(), self.gw[L - 1].data_ptr(),
+                                                    self.gb[L - 1].data_ptr(), self.gb[L - 2].data_ptr(), st()),
+                      "dr_dense_head_bce_fwd_bwd")
+                mark("head_bce")
+            else:
+                check(lib.dr_bce_logits_fwd_bwd(self.acts[-1].data_ptr(), self.fm_logit.data_ptr(),
+                                                self.labels.data_ptr(), B, self.prob.data_ptr(), self.loss.data_ptr(),
+                                                gz.data_ptr(), st()), "dr_bce")
+                mark("bce")
+            first = L - 2 if head else L - 1
+            for i in range(first, 0, -1):      # chained backward (dr_dense_bwd_chain): see DeepFMTrainStep._enqueue
                 l = self.layers[i]
                 top = i == L - 1
+                have_gb = head and i == L - 2
                 xin, Kin, gx = self.acts[i - 1], self.layers[i - 1].units, self.g_acts[i - 1]
                 check(lib.dr_dense_bwd_chain(xin.data_ptr(), self.w[i].data_ptr(),
                                              self.acts[i].data_ptr() if top else None, self.g_acts[i].data_ptr(), B, Kin,
                                              l.units, l._act if top else 0, ops._ptr(self.gz_ws[i]) if top else None,
-                                             gx.data_ptr(), self.gw[i].data_ptr(), self.gb[i].data_ptr(), xin.data_ptr(),
+                                             gx.data_ptr(), self.gw[i].data_ptr(),
+                                             None if have_gb else self.gb[i].data_ptr(), xin.data_ptr(),
                                              self.layers[i - 1]._act, st()), "dr_dense_bwd_chain")
                 mark(f"dense_bwd_{i}")
             l = self.layers[0]      # layer 0: the input gradient first (the embedding update needs it) ...
             top0 = L == 1
+            gb0 = None if (head and L == 2) else self.gb[0].data_ptr()
             check(lib.dr_dense_bwd(self.stack.data_ptr(), self.w[0].data_ptr(), self.acts[0].data_ptr() if top0 else None,
                                    self.g_acts[0].data_ptr(), B, S * D, l.units, l._act if top0 else 0,
                                    ops._ptr(self.gz_ws[0]) if top0 else None,
-                                   self.g_stack.data_ptr(), None, self.gb[0].data_ptr(), st()), "dr_dense_bwd(dx)")
+                                   self.g_stack.data_ptr(), None, gb0, st()), "dr_dense_bwd(dx)")
             mark("dense_bwd_0_dx")
 
         def seg_update():           # replayed on the SIDE stream: remote vector atomics into the owners' shards

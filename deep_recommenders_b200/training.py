@@ -37,8 +37,8 @@ class DeepFMTrainStep:
     def __init__(self, model, batch_size: int, lr: float = 0.01, id_dtype=torch.int64, use_graph: bool = True,
                  optimizer: str = "sgd", beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-7):
         self.lib = _lib.load()
-        if optimizer not in ("sgd", "adam", "lazy_adam"):
-            raise ValueError(f"optimizer must be 'sgd', 'adam' or 'lazy_adam', got {optimizer!r}")
+        if optimizer not in ("sgd", "adam", "lazy_adam", "adam_rows"):
+            raise ValueError(f"optimizer must be 'sgd', 'adam', 'lazy_adam' or 'adam_rows', got {optimizer!r}")
         self.optimizer = optimizer
         self.model = model
         coll = model.embeddings
@@ -104,14 +104,22 @@ class DeepFMTrainStep:
         if optimizer != "sgd":
             # optimizer state: gradient arena (all-zero between steps), m, v in the tables' own layout
             self.clock = ops.AdamClock(lr, beta1, beta2, eps, device=dev)
-            z = lambda t: None if t is None else torch.zeros_like(t)
+            z = lambda t: None if (t is None or optimizer == "adam_rows") else torch.zeros_like(t)
             self.g_arena, self.m_arena, self.v_arena = z(coll.weight.data), z(coll.weight.data), z(coll.weight.data)
             self.g_lin, self.m_lin, self.v_lin = z(coll.linear), z(coll.linear), z(coll.linear)
             self.g_bias, self.m_bias, self.v_bias = (torch.zeros((1,), **f) for _ in range(3))
             self.m_flat, self.v_flat = torch.zeros_like(self.flat), torch.zeros_like(self.flat)
-            self.gtp, self.glp, _ = coll.pointers(self.g_arena, self.g_lin, cache=False)
+            if optimizer != "adam_rows":
+                self.gtp, self.glp, _ = coll.pointers(self.g_arena, self.g_lin, cache=False)
             self.stamp = (torch.zeros((coll.total_rows,), device=dev, dtype=torch.int32)
                           if optimizer == "lazy_adam" else None)
+            self.state = None
+            if optimizer == "adam_rows":
+                # row-sparse Adam fused into the backward: ONE state block per row [g | m | v | g_w m_w v_w count]
+                # replaces the three table-shaped arenas (dr_embed_fm_bwd_adam)
+                ss = self.lib.dr_embed_adam_state_stride(D)
+                self.state = torch.zeros((coll.total_rows, ss), **f)
+                self.g_arena = self.m_arena = self.v_arena = self.g_lin = self.m_lin = self.v_lin = None
         kmax = max([S * D] + [l.units for l in layers])
         _lib.ensure_gemm_workspace(B, kmax, kmax, dev)
         # plane cache: x, every activation, every upstream gradient and every kernel, hi + lo
@@ -136,6 +144,12 @@ class DeepFMTrainStep:
         check(lib.dr_gemm_plane_cache(1), "dr_gemm_plane_cache")   # one split per tensor per step
         if self.optimizer != "sgd":
             self.clock.advance()                                  # t += 1, lr_t (device scalars)
+        if self.optimizer == "adam_rows":     # per-row lookup counts of this batch: side stream, hidden behind the forward
+            self._side_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._side_stream):
+                check(lib.dr_embed_adam_count(self.ids.data_ptr(), self.ids.element_size(), B, S, D, self.rows.data_ptr(),
+                                              c._offsets.data_ptr(), self.state.data_ptr(), self._side_stream.cuda_stream),
+                      "dr_embed_adam_count")
         mark("start")
         check(lib.dr_embed_fm_fwd(self.tp.data_ptr(), self.lp.data_ptr(), self.rows.data_ptr(), self.ids.data_ptr(),
                                   self.ids.element_size(), c.bias.data_ptr(), B, S, D, c.row_stride, c.lin_stride,
@@ -144,27 +158,44 @@ class DeepFMTrainStep:
         mark("embed_fm_fwd")
         x = self.stack
         K = S * D
-        for i, l in enumerate(self.layers):
+        L = len(self.layers)
+        gz = self.g_acts[-1]                                   # [B,1]: dL/dlogit
+        # the skinny end (final Dense(1) + BCE + their backward) is ONE kernel when the layer below is <= 256 wide
+        head = (L >= 2 and self.layers[-1].units == 1 and self.layers[-1]._act == 0 and self.layers[-2].units <= 256
+                and self.b[-1] is not None and self.b[-2] is not None)
+        for i, l in enumerate(self.layers[:L - 1] if head else self.layers):
             check(lib.dr_dense_fwd(x.data_ptr(), self.w[i].data_ptr(), ops._ptr(self.b[i]), B, K, l.units, l._act,
                                    self.acts[i].data_ptr(), st), "dr_dense_fwd")
             x, K = self.acts[i], l.units
             mark(f"dense_fwd_{i}")
-        gz = self.g_acts[-1]                                   # [B,1]: dL/dlogit
-        check(lib.dr_bce_logits_fwd_bwd(self.acts[-1].data_ptr(), self.fm_logit.data_ptr(), self.labels.data_ptr(), B,
-                                        self.prob.data_ptr(), self.loss.data_ptr(), gz.data_ptr(), st), "dr_bce")
-        mark("bce")
+        if head:
+            check(lib.dr_dense_head_bce_fwd_bwd(self.acts[L - 2].data_ptr(), self.w[L - 1].data_ptr(),
+                                                self.b[L - 1].data_ptr(), self.fm_logit.data_ptr(), self.labels.data_ptr(),
+                                                B, self.layers[L - 2].units, self.layers[L - 2]._act,
+                                                self.acts[L - 1].data_ptr(), self.prob.data_ptr(), self.loss.data_ptr(),
+                                                gz.data_ptr(), self.g_acts[L - 2].data_ptr(), self.gw[L - 1].data_ptr(),
+                                                self.gb[L - 1].data_ptr(), self.gb[L - 2].data_ptr(), st),
+                  "dr_dense_head_bce_fwd_bwd")
+            mark("head_bce")
+        else:
+            check(lib.dr_bce_logits_fwd_bwd(self.acts[-1].data_ptr(), self.fm_logit.data_ptr(), self.labels.data_ptr(), B,
+                                            self.prob.data_ptr(), self.loss.data_ptr(), gz.data_ptr(), st), "dr_bce")
+            mark("bce")
         # Chained backward: layer i's input gradient leaves its GEMM already multiplied by act'(output of layer i-1)
         # (dr_dense_bwd_chain), so g_acts[i-1] IS the pre-activation gradient of layer i-1 and no layer below the top
-        # needs its own activation-gradient pass (only the column sums for the bias gradient).
-        L = len(self.layers)
-        for i in range(L - 1, 0, -1):
+        # needs its own activation-gradient pass (only the column sums for the bias gradient; the layer right below the
+        # fused head got those from the head kernel too).
+        first = L - 2 if head else L - 1                      # highest layer that still needs its backward here
+        for i in range(first, 0, -1):
             l = self.layers[i]
-            top = i == L - 1
+            top = (i == L - 1)                                # only without the fused head: gy is dL/d(output), not gz
+            have_gb = head and i == L - 2
             xin, Kin, gx = self.acts[i - 1], self.layers[i - 1].units, self.g_acts[i - 1]
             check(lib.dr_dense_bwd_chain(xin.data_ptr(), self.w[i].data_ptr(), self.acts[i].data_ptr() if top else None,
                                          self.g_acts[i].data_ptr(), B, Kin, l.units, l._act if top else 0,
                                          ops._ptr(self.gz_ws[i]) if top else None, gx.data_ptr(), self.gw[i].data_ptr(),
-                                         ops._ptr(self.gb[i]), xin.data_ptr(), self.layers[i - 1]._act, st),
+                                         None if have_gb else ops._ptr(self.gb[i]), xin.data_ptr(),
+                                         self.layers[i - 1]._act, st),
                   "dr_dense_bwd_chain")
             mark(f"dense_bwd_{i}")
         # layer 0: input gradient first, then its weight gradient (tensor cores) runs
@@ -172,10 +203,11 @@ class DeepFMTrainStep:
         l = self.layers[0]
         top0 = L == 1
         gz0 = (self.gz_ws[0] if l._act != 0 else self.g_acts[0]) if top0 else self.g_acts[0]
+        gb0 = None if (head and L == 2) else ops._ptr(self.gb[0])
         check(lib.dr_dense_bwd(self.stack.data_ptr(), self.w[0].data_ptr(), self.acts[0].data_ptr() if top0 else None,
                                self.g_acts[0].data_ptr(), B, S * D, l.units, l._act if top0 else 0,
                                ops._ptr(self.gz_ws[0]) if top0 else None,
-                               self.g_stack.data_ptr(), None, ops._ptr(self.gb[0]), st), "dr_dense_bwd(dx)")
+                               self.g_stack.data_ptr(), None, gb0, st), "dr_dense_bwd(dx)")
         mark("dense_bwd_0_dx")
         main = torch.cuda.current_stream()
         side = self._side_stream
@@ -183,7 +215,18 @@ class DeepFMTrainStep:
         adam = self.optimizer != "sgd"
         with torch.cuda.stream(side):
             sst = side.cuda_stream
-            if not adam:     # fused row-sparse SGD: the backward updates the parameter arena in place
+            if self.optimizer == "adam_rows":     # Adam of the touched rows inside the backward scatter (one kernel)
+                ck = self.clock
+                check(lib.dr_embed_fm_bwd_adam(self.ids.data_ptr(), self.ids.element_size(), self.rows.data_ptr(),
+                                               c._offsets.data_ptr(), self.stack.data_ptr(), self.sum_e.data_ptr(),
+                                               gz.data_ptr(), self.g_stack.data_ptr(), B, S, D, c.row_stride, c.lin_stride,
+                                               c.flags, self.tp.data_ptr(), self.lp.data_ptr(), self.state.data_ptr(),
+                                               self.g_bias.data_ptr(), ck.lr_t.data_ptr(), ck.beta1, ck.beta2, ck.eps, sst),
+                      "dr_embed_fm_bwd_adam")
+                check(lib.dr_adam_step(c.bias.data_ptr(), self.g_bias.data_ptr(), self.m_bias.data_ptr(),
+                                       self.v_bias.data_ptr(), 1, 0.0, ck.beta1, ck.beta2, ck.eps, 1, ck.lr_t.data_ptr(), sst),
+                      "dr_adam_step(bias)")
+            elif not adam:     # fused row-sparse SGD: the backward updates the parameter arena in place
                 check(lib.dr_embed_fm_bwd(self.ids.data_ptr(), self.ids.element_size(), self.rows.data_ptr(),
                                           self.stack.data_ptr(), self.sum_e.data_ptr(), gz.data_ptr(),
                                           self.g_stack.data_ptr(), B, S, D, c.row_stride, c.lin_stride, c.flags,
@@ -291,7 +334,7 @@ class DeepFMTrainStep:
         st += [t.data for t in (c.linear, c.bias) if t is not None]
         if self.optimizer != "sgd":
             st += [t for t in (self.g_arena, self.m_arena, self.v_arena, self.g_lin, self.m_lin, self.v_lin, self.g_bias,
-                               self.m_bias, self.v_bias, self.m_flat, self.v_flat, self.stamp, self.clock.step,
+                               self.m_bias, self.v_bias, self.m_flat, self.v_flat, self.stamp, self.state, self.clock.step,
                                self.clock.lr_t) if t is not None]
         return st
 

@@ -253,6 +253,18 @@ int dr_sgd_step(float* p, const float* g, int64_t n, float lr, void* stream);
 int dr_bce_logits_fwd_bwd(const float* z, const float* z_add, const float* y, int64_t B,
                           float* prob_out, float* loss_out, float* gz, void* stream);
 
+/* The skinny end of the deep tower in ONE kernel: the final Dense(1) layer (deepfm.py:30-34 `+ [Dense(1)]`, estimator
+ * dnn.py hidden_units + [1]), `fm + dnn` (deepfm.py:46-47), binary cross-entropy on the sigmoid, and their backward.
+ *   a [B,K] = act_prev(z_prev): output of the layer below (K <= 256), w [K] (= kernel [K,1]), bias [1] (nullable).
+ *   logit = a.w + bias (+ z_add);  loss[0] = mean BCE as in dr_bce_logits_fwd_bwd;  g_logit[b] = (sigmoid - y)/B.
+ *   g_prev [B,K] = g_logit * w * act_prev'(a): already the PRE-activation gradient of the layer below (cf.
+ *   dr_dense_bwd_chain);  gw [K], gb [1], gb_prev [K] = colsum(g_prev) are OVERWRITTEN.
+ *   logit_out (the Dense(1) output without z_add), prob_out, g_logit, g_prev, gw, gb, gb_prev may each be NULL. */
+int dr_dense_head_bce_fwd_bwd(const float* a, const float* w, const float* bias, const float* z_add,
+                              const float* y, int64_t B, int K, int prev_act, float* logit_out,
+                              float* prob_out, float* loss_out, float* g_logit, float* g_prev, float* gw,
+                              float* gb, float* gb_prev, void* stream);
+
 /* =======================================================================================
  * SURVEY.md 8(f) "next" rows: the callers either side of the hot path.
  * ======================================================================================= */
@@ -287,6 +299,29 @@ int dr_lazy_adam_rows(const void* ids, int id_bytes, int64_t B, int S, int D, co
                       int flags, float* lin_p, float* lin_g, float* lin_m, float* lin_v, int32_t* stamp,
                       const int64_t* step_dev, const float* lr_t_dev, float beta1, float beta2, float eps,
                       void* stream);
+
+/* Row-sparse Adam FUSED INTO the backward scatter (one kernel per step; the same tfa-LazyAdam semantics as
+ * dr_lazy_adam_rows: rows the batch does not touch keep p, m, v -- on touched rows the update is TensorFlow's ApplyAdam
+ * functor exactly).  replaces: the IndexedSlices gradient of the embedding / first-order variables going through
+ * tf.keras.optimizers.Adam (examples/train_deepfm_on_movielens_keras.py:44) for the rows of one batch.
+ *   state: [total rows, stride] floats, stride = dr_embed_adam_state_stride(D) (a 128-B multiple), zero-initialised once
+ *          by the caller; per row [g D | m D | v D | g_w m_w v_w count | pad] (g = gradient accumulator, zero between
+ *          steps; count = int32 countdown, zero between steps).
+ *   dr_embed_adam_count: count[row] += 1 for every valid lookup of the batch (any time before the backward of the
+ *          same batch, e.g. on a side stream while the forward runs).
+ *   dr_embed_fm_bwd_adam: same inputs as dr_embed_fm_bwd (ids, saved stack / sum_e, g_logit, g_stack); every lookup
+ *          adds its gradient row into state with vector atomics and decrements the row's count; the lookup that takes it
+ *          to zero applies m += (g-m)(1-b1), v += (g*g-v)(1-b2), p -= lr_t*m/(sqrt(v)+eps) to the row of the PARAMETER
+ *          table (table_ptrs / lin_ptrs, layouts as in dr_embed_fm_fwd) and clears g.  g_bias (nullable) accumulates the
+ *          FM bias gradient (sum of g_logit) for a following dr_adam_step.  lr_t_dev: maintained by dr_adam_advance. */
+int dr_embed_adam_state_stride(int D);
+int dr_embed_adam_count(const void* ids, int id_bytes, int64_t B, int S, int D, const int64_t* rows,
+                        const int64_t* slot_offsets, float* state, void* stream);
+int dr_embed_fm_bwd_adam(const void* ids, int id_bytes, const int64_t* rows, const int64_t* slot_offsets,
+                         const float* stack, const float* sum_e, const float* g_logit, const float* g_stack,
+                         int64_t B, int S, int D, int64_t row_stride, int64_t lin_stride, int flags,
+                         float* const* table_ptrs, float* const* lin_ptrs, float* state, float* g_bias,
+                         const float* lr_t_dev, float beta1, float beta2, float eps, void* stream);
 
 /* ---- 8(f) #2  id pipeline: raw feature value -> int64 row id, bit-exact with TensorFlow's columns.
  * categorical_column_with_hash_bucket = FarmHash Fingerprint64(bytes of str(value)) mod num_buckets

@@ -248,3 +248,43 @@ def test_dense_bwd_chain_fuses_previous_activation_gradient(M, K, N, prev_act):
     assert (np.abs(gx.cpu().numpy() - gx_lin * dact) <= 2e-5 * sx + 1e-6).all()
     assert (np.abs(gw.cpu().numpy() - gw_ref) <= 2e-5 * (np.abs(x64).T @ agy) + 1e-6).all()
     assert (np.abs(gb.cpu().numpy() - gb_ref) <= 2e-5 * agy.sum(0) + 1e-6).all()
+
+
+@pytest.mark.parametrize("B,K", [(1, 1), (257, 32), (1000, 8), (300, 100), (129, 256)])
+@pytest.mark.parametrize("prev_act", ["relu", None, "sigmoid"])
+def test_dense_head_bce_fused_matches_oracle(B, K, prev_act):
+    """dr_dense_head_bce_fwd_bwd == Dense(1) forward + (fm + dnn) + mean BCE + backward, composed from the oracle
+    (deepfm.py:30-34,46-47; examples/train_deepfm_on_movielens_keras.py:43)."""
+    from deep_recommenders_b200 import _lib, ops
+    lib = _lib.load()
+    rng = np.random.default_rng(B + K)
+    a = R.act(rng.standard_normal((B, K)), prev_act).astype(np.float32)
+    w = (rng.standard_normal((K, 1)) / np.sqrt(K)).astype(np.float32)
+    b = np.asarray([0.3], np.float32)
+    zadd = rng.standard_normal(B).astype(np.float32)
+    y = rng.integers(0, 2, B).astype(np.float32)
+    f = lambda *shape: torch.full(shape, float("nan"), device="cuda")
+    logit, prob, loss, gl, gp, gw, gb, gbp = f(B), f(B), f(1), f(B), f(B, K), f(K), f(1), f(K)
+    at, wt, bt, zt, yt = cu(a), cu(w), cu(b), cu(zadd), cu(y)
+    _lib.check(lib.dr_dense_head_bce_fwd_bwd(at.data_ptr(), wt.data_ptr(), bt.data_ptr(), zt.data_ptr(), yt.data_ptr(), B, K,
+                                             ops.act_code(prev_act), logit.data_ptr(), prob.data_ptr(), loss.data_ptr(),
+                                             gl.data_ptr(), gp.data_ptr(), gw.data_ptr(), gb.data_ptr(), gbp.data_ptr(),
+                                             torch.cuda.current_stream().cuda_stream), "head")
+    a64, w64 = a.astype(np.float64), w.astype(np.float64)
+    z = (a64 @ w64).reshape(-1) + 0.3
+    zi = z + zadd
+    p = 1 / (1 + np.exp(-zi))
+    ref_loss = np.mean(np.maximum(zi, 0) - zi * y + np.log1p(np.exp(-np.abs(zi))))
+    g = (p - y) / B
+    dact = {"relu": (a64 > 0).astype(np.float64), "sigmoid": a64 * (1 - a64), None: np.ones_like(a64)}[prev_act]
+    ref_gp = g[:, None] * w64.reshape(1, -1) * dact
+    zs = np.abs(a64) @ np.abs(w64).reshape(-1) + 0.3
+    assert (np.abs(logit.cpu().numpy() - z) <= 1e-5 * zs + 1e-7).all()
+    assert np.allclose(prob.cpu().numpy(), p, rtol=1e-5, atol=1e-6)
+    assert abs(float(loss) - ref_loss) <= 1e-5 * abs(ref_loss) + 1e-7
+    assert np.allclose(gl.cpu().numpy(), g, rtol=1e-4, atol=1e-6 / B)      # sigmoid of an fp32 logit
+    assert (np.abs(gp.cpu().numpy() - ref_gp) <= 1e-4 * np.abs(ref_gp) + 1e-6 / B).all()
+    ag = np.abs(g)
+    assert (np.abs(gw.cpu().numpy() - a64.T @ g) <= 1e-4 * (np.abs(a64).T @ ag) + 1e-9).all()
+    assert abs(float(gb) - g.sum()) <= 1e-4 * ag.sum() + 1e-9
+    assert (np.abs(gbp.cpu().numpy() - ref_gp.sum(0)) <= 1e-4 * np.abs(ref_gp).sum(0) + 1e-9).all()

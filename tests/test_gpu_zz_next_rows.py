@@ -269,7 +269,7 @@ def _cpu_deepfm_grads(tables, lins, bias, ws, bs, ids, labels):
     return float(loss.detach()), g(tt), g(tl), tb.grad.numpy(), g(tw), g(tbi)
 
 
-@pytest.mark.parametrize("optimizer", ["adam", "lazy_adam"])
+@pytest.mark.parametrize("optimizer", ["adam", "lazy_adam", "adam_rows"])
 @pytest.mark.parametrize("D", [16, 32])                   # fused 128-B rows / split layout
 @pytest.mark.parametrize("use_graph", [False, True])
 def test_train_step_adam_matches_apply_adam_oracle(optimizer, D, use_graph):
@@ -291,7 +291,7 @@ def test_train_step_adam_matches_apply_adam_oracle(optimizer, D, use_graph):
         assert all(torch.equal(a, b) for a, b in zip(snap, (coll.weight, tr.flat, coll.bias) + ((coll.linear,) if coll.linear is not None else ())))
         if optimizer != "sgd":
             for t in (tr.m_arena, tr.v_arena, tr.g_arena, tr.m_flat, tr.v_flat, tr.m_bias, tr.v_bias, tr.g_bias,
-                      tr.m_lin, tr.v_lin, tr.g_lin, tr.stamp, tr.clock.step):
+                      tr.m_lin, tr.v_lin, tr.g_lin, tr.stamp, tr.state, tr.clock.step):
                 assert t is None or not bool(t.any()), "capture() left optimizer state behind"
     tables = [coll.table(s).detach().cpu().numpy().astype(np.float64) for s in range(S)]
     lins = [coll.linear_of(s).detach().cpu().numpy().astype(np.float64) for s in range(S)]
@@ -327,7 +327,14 @@ def test_train_step_adam_matches_apply_adam_oracle(optimizer, D, use_graph):
     assert abs(float(tr.clock.lr_t) - R.adam_lr_t(lr, 3)) <= 1e-6 * R.adam_lr_t(lr, 3)
     # first moments are linear in the gradients: tight; parameters: Adam divides by sqrt(v) + eps, loose
     RS = coll.row_stride
-    m_emb = tr.m_arena.view(-1, RS)[:, :D].cpu().numpy()
+    if optimizer == "adam_rows":         # fused form: one state block per row [g D | m D | v D | g_w m_w v_w count | pad]
+        st = tr.state.cpu().numpy()
+        m_emb = st[:, D:2 * D]
+        assert np.abs(st[:, 3 * D + 1] - np.concatenate(ml, 0)).max() <= 1e-4 * np.abs(np.concatenate(ml, 0)).max() + 1e-9
+        assert not st[:, :D].any() and not st[:, 3 * D].any(), "gradient accumulators must be zero between steps"
+        assert not tr.state[:, 3 * D + 3].view(torch.int32).any(), "row countdowns must be zero between steps"
+    else:
+        m_emb = tr.m_arena.view(-1, RS)[:, :D].cpu().numpy()
     ref_m = np.concatenate(mt, 0)
     assert np.abs(m_emb - ref_m).max() <= 1e-4 * np.abs(ref_m).max() + 1e-9
     got_tables = np.concatenate([coll.table(s).detach().cpu().numpy() for s in range(S)], 0)
@@ -339,7 +346,7 @@ def test_train_step_adam_matches_apply_adam_oracle(optimizer, D, use_graph):
         assert np.abs(tr.w[i].cpu().numpy() - ws[i]).max() <= 3e-2 * lr
         assert np.abs(tr.b[i].cpu().numpy() - bs[i]).max() <= 3e-2 * lr
     # the gradient arena is all-zero again after every step (both variants clear what they consumed)
-    assert float(tr.g_arena.abs().max()) == 0.0 and float(tr.g_bias.abs().max()) == 0.0
+    assert (tr.g_arena is None or float(tr.g_arena.abs().max()) == 0.0) and float(tr.g_bias.abs().max()) == 0.0
     # and the parameters really moved by about lr per step where a gradient flowed
     assert np.abs(got_tables - snap[0].view(-1, RS)[:, :D].cpu().numpy()).max() > 0.5 * lr
 
