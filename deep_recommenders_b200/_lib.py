@@ -47,6 +47,8 @@ _SIGS = {
     "dr_cross_bwd": [_p, _p, _p, _p, _p, _f, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "dr_inbatch_softmax_fwd": [_p, _p, _p, _p, _p, _f, _i64, _i64, _i, _p, _p, _p],
     "dr_inbatch_softmax_bwd": [_p, _p, _p, _p, _p, _f, _i64, _i64, _i, _p, _p, _p, _p, _p],
+    "dr_inbatch_softmax_fwd_ws": [_p, _p, _p, _p, _p, _f, _i64, _i64, _i, _p, _i64, _p, _p, _p],
+    "dr_inbatch_softmax_bwd_ws": [_p, _p, _p, _p, _p, _f, _i64, _i64, _i, _p, _p, _p, _i64, _i, _p, _p, _p],
     "dr_scores_fwd": [_p, _p, _p, _p, _i64, _i64, _i, _p, _p],
     "dr_hard_negative_topk": [_p, _i64, _i64, _i, _p, _p, _p, _p],
     "dr_shard_bucket_ids": [_p, _i, _i64, _i, _p, _p, _i, _i64, _p, _p, _p, _p, _p],

@@ -104,11 +104,27 @@ static GemmArgs mk(const float* A, const float* B, float* C, int64_t M, int64_t 
 
 // gW[Kw,N] = X^T[Kw,M] @ G[M,N] (split-K over the batch, atomics into zeroed gW)
 static int gemm_xt_g(const float* X, const float* G, float* gW, int64_t M, int64_t Kw, int64_t N,
-                     cudaStream_t st) {
-  DR_CUDA_CALL(cudaMemsetAsync(gW, 0, sizeof(float) * Kw * N, st));
+                     cudaStream_t st, bool accumulate = false) {
+  if (!accumulate) DR_CUDA_CALL(cudaMemsetAsync(gW, 0, sizeof(float) * Kw * N, st));
   GemmArgs a = mk(X, G, gW, Kw, N, M, Kw, N, N, EPI_ATOMIC);
   a.splitk = splitk_for(Kw, N, M);
   return gemm_launch(a, /*transA=*/true, /*transB=*/false, st);
+}
+
+// ---- GEMM legs of the tensor-core in-batch softmax (softmax.cu) -------------------------------------------------------
+// raw corrected scores of query rows [row0, row0 + rb): S = Q_blk C^T - log p[n] + dup * MIN_FLOAT  -> ws [rb, nc]
+int softmax_scores_block(const float* q_blk, const float* c, const float* p, const int64_t* ids, int64_t row0, int64_t rb,
+                         int64_t nc, int D, float* ws, cudaStream_t st) {
+  GemmArgs a = mk(q_blk, c, ws, rb, nc, D, D, D, nc, EPI_SCORES);
+  a.bias = p; a.cand_ids = ids; a.row0 = row0;
+  return gemm_launch(a, false, true, st);
+}
+// gQ_blk [rb, D] = G [rb, nc] @ C [nc, D];   gC [nc, D] += G^T @ Q_blk  (split-K atomics; gC zeroed by the caller)
+int softmax_grad_block(const float* g_ws, const float* q_blk, const float* c, int64_t rb, int64_t nc, int D, float* gq_blk,
+                       float* gc, cudaStream_t st) {
+  GemmArgs a = mk(g_ws, c, gq_blk, rb, D, nc, nc, D, D, EPI_STORE);
+  if (int rc = gemm_launch(a, false, false, st)) return rc;
+  return gemm_xt_g(g_ws, q_blk, gc, rb, nc, D, st, /*accumulate=*/true);
 }
 
 }  // namespace dr

@@ -40,7 +40,7 @@ __device__ __forceinline__ float epi_scalar(const GemmArgs& a, float acc, int64_
     case EPI_SCORES: {
       float v = acc;
       if (a.bias) v = v - logf(__ldg(a.bias + n));
-      if (a.cand_ids && m != n && m < a.N && __ldg(a.cand_ids + n) == __ldg(a.cand_ids + m))
+      if (a.cand_ids && m + a.row0 != n && m + a.row0 < a.N && __ldg(a.cand_ids + n) == __ldg(a.cand_ids + m + a.row0))
         v = v + (-FLT_MAX / 100.0f);
       return v;
     }

@@ -35,6 +35,7 @@ struct GemmArgs {
   const float* aux1;
   float* out2;
   const int64_t* cand_ids;   // EPI_SCORES
+  int64_t row0;              // EPI_SCORES: query row m of this call is global query m + row0 (its positive = candidate m + row0)
   int splitk;                // >= 1
 };
 

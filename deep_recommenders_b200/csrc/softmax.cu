@@ -322,6 +322,100 @@ __global__ void __launch_bounds__(256) hard_negative_topk_kernel(const float* __
 
 using namespace dr;
 
+
+namespace dr {
+// ---- tensor-core form (round 2): the contraction Q C^T (sbcnm.py:129) and the two gradient contractions run on the
+// tcgen05 3xTF32 GEMM core; the score block [rb, nc] of rb query rows lives in a caller-provided workspace between the
+// GEMM and two one-pass kernels (the FFMA kernels above never materialise scores but reach ~18 TFLOP/s; this form trades
+// rb * nc * 4 B of scratch traffic -- ~1 ms / GiB at HBM speed -- for tensor-core contractions).
+int softmax_scores_block(const float* q_blk, const float* c, const float* p, const int64_t* ids, int64_t row0, int64_t rb,
+                         int64_t nc, int D, float* ws, cudaStream_t st);
+int softmax_grad_block(const float* g_ws, const float* q_blk, const float* c, int64_t rb, int64_t nc, int D, float* gq_blk,
+                       float* gc, cudaStream_t st);
+
+// one warp per query row: online log-sum-exp over the row of raw scores (x inv_tau), diagonal pick, weighted loss
+__global__ void __launch_bounds__(256) softmax_rows_fwd_kernel(const float* __restrict__ S, int64_t rb, int64_t nc,
+                                                                int64_t row0, int64_t nq, float inv_tau,
+                                                                const float* __restrict__ w, float* __restrict__ lse_out,
+                                                                float* __restrict__ loss_out) {
+  __shared__ float s_part[8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t r = (int64_t)blockIdx.x * 8 + wid;
+  float contrib = 0.f;
+  if (r < rb) {
+    const float* row = S + r * nc;
+    float mx = -INFINITY, sum = 0.f;
+    const bool vec = (nc & 3) == 0;
+    if (vec) {
+      for (int64_t j = lane * 4; j < nc; j += 128) {
+        const float4 v = ldg_nc_na(row + j);
+        const float a = v.x * inv_tau, b = v.y * inv_tau, c = v.z * inv_tau, d = v.w * inv_tau;
+        const float m4 = fmaxf(fmaxf(a, b), fmaxf(c, d));
+        if (m4 > mx) { sum *= expf(mx - m4); mx = m4; }
+        sum += expf(a - mx) + expf(b - mx) + expf(c - mx) + expf(d - mx);
+      }
+    } else {
+      for (int64_t j = lane; j < nc; j += 32) {
+        const float a = __ldg(row + j) * inv_tau;
+        if (a > mx) { sum *= expf(mx - a); mx = a; }
+        sum += expf(a - mx);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, mx, o), os = __shfl_xor_sync(0xffffffffu, sum, o);
+      const float nm = fmaxf(mx, om);
+      sum = (nm == -INFINITY) ? 0.f : sum * expf(mx - nm) + os * expf(om - nm);
+      mx = nm;
+    }
+    const float lse = mx + logf(sum);
+    const int64_t m = row0 + r;
+    if (lane == 0) {
+      lse_out[m] = lse;
+      const float diag = (m < nc) ? __ldg(row + m) * inv_tau : 0.f;
+      contrib = (w ? __ldg(w + m) : 1.f) * (lse - diag);
+    }
+  }
+  if (lane == 0) s_part[wid] = contrib;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += s_part[i];
+    red_add_f32(loss_out, t);
+  }
+}
+
+// in place: G[r, n] = gloss * w_m * inv_tau * (exp(s - lse_m) - [n == m]),  s = S[r, n] * inv_tau,  m = row0 + r
+__global__ void __launch_bounds__(256) softmax_rows_bwd_kernel(float* __restrict__ S, int64_t rb, int64_t nc, int64_t row0,
+                                                                float inv_tau, const float* __restrict__ w,
+                                                                const float* __restrict__ lse,
+                                                                const float* __restrict__ gloss) {
+  const float gs = __ldg(gloss) * inv_tau;
+  const int64_t n4 = nc / 4;
+  const bool vec = (nc & 3) == 0;
+  const int64_t total = vec ? rb * n4 : rb * nc;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < total; f += stride) {
+    if (vec) {
+      const int64_t r = f / n4, j = (f - r * n4) * 4;
+      const int64_t m = row0 + r;
+      const float wm = (w ? __ldg(w + m) : 1.f) * gs, l = __ldg(lse + m);
+      float4 v = *reinterpret_cast<float4*>(S + r * nc + j);
+      v.x = (expf(v.x * inv_tau - l) - (j + 0 == m ? 1.f : 0.f)) * wm;
+      v.y = (expf(v.y * inv_tau - l) - (j + 1 == m ? 1.f : 0.f)) * wm;
+      v.z = (expf(v.z * inv_tau - l) - (j + 2 == m ? 1.f : 0.f)) * wm;
+      v.w = (expf(v.w * inv_tau - l) - (j + 3 == m ? 1.f : 0.f)) * wm;
+      *reinterpret_cast<float4*>(S + r * nc + j) = v;
+    } else {
+      const int64_t r = f / nc, j = f - r * nc;
+      const int64_t m = row0 + r;
+      const float wm = (w ? __ldg(w + m) : 1.f) * gs;
+      S[f] = (expf(S[f] * inv_tau - __ldg(lse + m)) - (j == m ? 1.f : 0.f)) * wm;
+    }
+  }
+}
+}  // namespace dr
+
 static int check_softmax(const char* fn, const float* q, const float* c, int64_t nq, int64_t nc, int D) {
   DR_REQUIRE(q && c, DR_EINVAL, "%s: null Q/C", fn);
   DR_REQUIRE(nq >= 1 && nc >= 1, DR_EINVAL, "%s: empty batch (nq=%lld nc=%lld)", fn, (long long)nq, (long long)nc);
@@ -355,6 +449,50 @@ extern "C" int dr_inbatch_softmax_bwd(const float* q, const float* c, const floa
   sp.D = D; sp.lse = lse; sp.gloss = gloss; sp.gq = gq; sp.gc = gc;
   if (int rc = launch_softmax<MODE_BWD_Q>(sp, nq, st)) return rc;
   return launch_softmax<MODE_BWD_C>(sp, nc, st);
+}
+
+
+extern "C" int dr_inbatch_softmax_fwd_ws(const float* q, const float* c, const float* w, const float* p,
+                                         const int64_t* cand_ids, float inv_tau, int64_t nq, int64_t nc, int D,
+                                         float* scores_ws, int64_t ws_rows, float* lse_out, float* loss_out,
+                                         void* stream) {
+  if (int rc = check_softmax("dr_inbatch_softmax_fwd_ws", q, c, nq, nc, D)) return rc;
+  DR_REQUIRE(lse_out && loss_out && scores_ws && ws_rows >= 1, DR_EINVAL, "dr_inbatch_softmax_fwd_ws: null output / workspace");
+  DR_REQUIRE(aligned16(scores_ws), DR_EALIGN, "dr_inbatch_softmax_fwd_ws: workspace not 16-B aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  DR_CUDA_CALL(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
+  for (int64_t r0 = 0; r0 < nq; r0 += ws_rows) {
+    const int64_t rb = nq - r0 < ws_rows ? nq - r0 : ws_rows;
+    if (int rc = softmax_scores_block(q + r0 * D, c, p, cand_ids, r0, rb, nc, D, scores_ws, st)) return rc;
+    softmax_rows_fwd_kernel<<<(unsigned)((rb + 7) / 8), 256, 0, st>>>(scores_ws, rb, nc, r0, nq, inv_tau, w, lse_out, loss_out);
+    DR_CUDA_LAUNCH_CHECK("softmax_rows_fwd");
+  }
+  return DR_OK;
+}
+
+extern "C" int dr_inbatch_softmax_bwd_ws(const float* q, const float* c, const float* w, const float* p,
+                                         const int64_t* cand_ids, float inv_tau, int64_t nq, int64_t nc, int D,
+                                         const float* lse, const float* gloss, float* scores_ws, int64_t ws_rows,
+                                         int scores_valid, float* gq, float* gc, void* stream) {
+  if (int rc = check_softmax("dr_inbatch_softmax_bwd_ws", q, c, nq, nc, D)) return rc;
+  DR_REQUIRE(lse && gloss && gq && gc && scores_ws && ws_rows >= 1, DR_EINVAL, "dr_inbatch_softmax_bwd_ws: null pointer");
+  DR_REQUIRE(aligned16(gq) && aligned16(gc) && aligned16(scores_ws), DR_EALIGN,
+             "dr_inbatch_softmax_bwd_ws: gq / gc / workspace not 16-B aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  DR_CUDA_CALL(cudaMemsetAsync(gc, 0, sizeof(float) * (size_t)nc * D, st));
+  const bool reuse = scores_valid && ws_rows >= nq;      // the forward's raw scores of ALL rows are still in the workspace
+  for (int64_t r0 = 0; r0 < nq; r0 += ws_rows) {
+    const int64_t rb = nq - r0 < ws_rows ? nq - r0 : ws_rows;
+    if (!reuse)
+      if (int rc = softmax_scores_block(q + r0 * D, c, p, cand_ids, r0, rb, nc, D, scores_ws, st)) return rc;
+    const int64_t work = rb * ((nc & 3) ? nc : nc / 4);
+    int64_t ctas = (work + 255) / 256;
+    if (ctas > (int64_t)kNumSMs * 16) ctas = (int64_t)kNumSMs * 16;
+    softmax_rows_bwd_kernel<<<(unsigned)ctas, 256, 0, st>>>(scores_ws, rb, nc, r0, inv_tau, w, lse, gloss);
+    DR_CUDA_LAUNCH_CHECK("softmax_rows_bwd");
+    if (int rc = softmax_grad_block(scores_ws, q + r0 * D, c, rb, nc, D, gq + r0 * D, gc, st)) return rc;
+  }
+  return DR_OK;
 }
 
 extern "C" int dr_hard_negative_topk(const float* logits, int64_t nq, int64_t nc, int k, float* out_logits,

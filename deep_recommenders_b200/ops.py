@@ -286,6 +286,12 @@ class CrossFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------
 # Row R: in-batch softmax
 # ------------------------------------------------------------------------------------------
+# Retrieval losses with at least this many scores (nq * nc) run the tensor-core form (score blocks materialised in a
+# scratch buffer of at most SOFTMAX_TC_WS_BYTES); smaller ones the fused FFMA kernels that never materialise scores.
+SOFTMAX_TC_MIN_SCORES = 1 << 22
+SOFTMAX_TC_WS_BYTES = 2 << 30
+
+
 class InBatchSoftmax(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, c, sample_weight, sampling_prob, cand_ids, inv_tau: float):
@@ -303,10 +309,20 @@ class InBatchSoftmax(torch.autograd.Function):
             ids = cand_ids.to(torch.int64).contiguous().reshape(nc)
         lse = torch.empty((nq,), device=q.device, dtype=torch.float32)
         loss = torch.empty((1,), device=q.device, dtype=torch.float32)
-        check(lib.dr_inbatch_softmax_fwd(q.data_ptr(), c.data_ptr(), _ptr(w), _ptr(p), _ptr(ids), float(inv_tau),
-                                         nq, nc, D, lse.data_ptr(), loss.data_ptr(), _stream()),
-              "dr_inbatch_softmax_fwd")
+        ws = None
+        if nq * nc >= SOFTMAX_TC_MIN_SCORES and D >= 32:
+            # tensor-core form: score blocks through the tcgen05 GEMM, kept in a scratch buffer for the backward
+            rows = min(nq, max(128, SOFTMAX_TC_WS_BYTES // (4 * nc) // 128 * 128))
+            ws = torch.empty((rows, nc), device=q.device, dtype=torch.float32)
+            check(lib.dr_inbatch_softmax_fwd_ws(q.data_ptr(), c.data_ptr(), _ptr(w), _ptr(p), _ptr(ids), float(inv_tau),
+                                                nq, nc, D, ws.data_ptr(), rows, lse.data_ptr(), loss.data_ptr(), _stream()),
+                  "dr_inbatch_softmax_fwd_ws")
+        else:
+            check(lib.dr_inbatch_softmax_fwd(q.data_ptr(), c.data_ptr(), _ptr(w), _ptr(p), _ptr(ids), float(inv_tau),
+                                             nq, nc, D, lse.data_ptr(), loss.data_ptr(), _stream()),
+                  "dr_inbatch_softmax_fwd")
         ctx.inv_tau = float(inv_tau)
+        ctx.ws = ws
         ctx.save_for_backward(q, c, w, p, ids, lse)
         return loss.reshape(())
 
@@ -319,9 +335,16 @@ class InBatchSoftmax(torch.autograd.Function):
         gl = _f32(gloss, "gloss").reshape(1)
         gq = torch.empty_like(q)
         gc = torch.empty_like(c)
-        check(lib.dr_inbatch_softmax_bwd(q.data_ptr(), c.data_ptr(), _ptr(w), _ptr(p), _ptr(ids), ctx.inv_tau,
-                                         nq, nc, D, lse.data_ptr(), gl.data_ptr(), gq.data_ptr(), gc.data_ptr(),
-                                         _stream()), "dr_inbatch_softmax_bwd")
+        ws = ctx.ws
+        if ws is not None:
+            ctx.ws = None          # consumed (overwritten with the gradient factor) by this call
+            check(lib.dr_inbatch_softmax_bwd_ws(q.data_ptr(), c.data_ptr(), _ptr(w), _ptr(p), _ptr(ids), ctx.inv_tau,
+                                                nq, nc, D, lse.data_ptr(), gl.data_ptr(), ws.data_ptr(), ws.shape[0], 1,
+                                                gq.data_ptr(), gc.data_ptr(), _stream()), "dr_inbatch_softmax_bwd_ws")
+        else:
+            check(lib.dr_inbatch_softmax_bwd(q.data_ptr(), c.data_ptr(), _ptr(w), _ptr(p), _ptr(ids), ctx.inv_tau,
+                                             nq, nc, D, lse.data_ptr(), gl.data_ptr(), gq.data_ptr(), gc.data_ptr(),
+                                             _stream()), "dr_inbatch_softmax_bwd")
         return gq, gc, None, None, None, None
 
 

@@ -84,6 +84,10 @@ class ShardedTwoTowerTrainStep:
         self.gc_rot = torch.empty((G * b, D), **f)
         self.gc_all = torch.empty((G, b, D), **f)
         self.gc_local = torch.empty((b, D), **f)
+        # scores of this rank's b queries against all G b candidates: tcgen05 form when the block is big enough to pay
+        from . import ops as _ops
+        big = b * G * b >= _ops.SOFTMAX_TC_MIN_SCORES and D >= 32 and b * G * b * 4 <= _ops.SOFTMAX_TC_WS_BYTES
+        self.scores_ws = torch.empty((b, G * b), **f) if big else None
         order = shard_plan.own_first_order(self.rank, G)
         self._order = torch.tensor(order, **i64)
         self._inv_order = torch.tensor(shard_plan.inverse_order(order), **i64)
@@ -119,12 +123,21 @@ class ShardedTwoTowerTrainStep:
             else:
                 self.ids_rot.copy_(self.item_ids.view(b))
             ids_ptr = self.ids_rot.data_ptr()
-        check(lib.dr_inbatch_softmax_fwd(self.q.data_ptr(), self.c_rot.data_ptr(), None, None, ids_ptr, self.inv_tau,
-                                         b, G * b, D, self.lse.data_ptr(), self.loss.data_ptr(), st()),
-              "dr_inbatch_softmax_fwd")
-        check(lib.dr_inbatch_softmax_bwd(self.q.data_ptr(), self.c_rot.data_ptr(), None, None, ids_ptr, self.inv_tau,
-                                         b, G * b, D, self.lse.data_ptr(), self.gloss.data_ptr(), self.gq.data_ptr(),
-                                         self.gc_rot.data_ptr(), st()), "dr_inbatch_softmax_bwd")
+        if self.scores_ws is not None:     # tensor-core form: the b x (G b) score block lives in a scratch buffer
+            check(lib.dr_inbatch_softmax_fwd_ws(self.q.data_ptr(), self.c_rot.data_ptr(), None, None, ids_ptr, self.inv_tau,
+                                                b, G * b, D, self.scores_ws.data_ptr(), b, self.lse.data_ptr(),
+                                                self.loss.data_ptr(), st()), "dr_inbatch_softmax_fwd_ws")
+            check(lib.dr_inbatch_softmax_bwd_ws(self.q.data_ptr(), self.c_rot.data_ptr(), None, None, ids_ptr, self.inv_tau,
+                                                b, G * b, D, self.lse.data_ptr(), self.gloss.data_ptr(),
+                                                self.scores_ws.data_ptr(), b, 1, self.gq.data_ptr(),
+                                                self.gc_rot.data_ptr(), st()), "dr_inbatch_softmax_bwd_ws")
+        else:
+            check(lib.dr_inbatch_softmax_fwd(self.q.data_ptr(), self.c_rot.data_ptr(), None, None, ids_ptr, self.inv_tau,
+                                             b, G * b, D, self.lse.data_ptr(), self.loss.data_ptr(), st()),
+                  "dr_inbatch_softmax_fwd")
+            check(lib.dr_inbatch_softmax_bwd(self.q.data_ptr(), self.c_rot.data_ptr(), None, None, ids_ptr, self.inv_tau,
+                                             b, G * b, D, self.lse.data_ptr(), self.gloss.data_ptr(), self.gq.data_ptr(),
+                                             self.gc_rot.data_ptr(), st()), "dr_inbatch_softmax_bwd")
         if G > 1:
             torch.index_select(self.gc_rot.view(G, b, D), 0, self._inv_order, out=self.gc_all)
             dist.reduce_scatter_tensor(self.gc_local, self.gc_all.view(G * b, D), group=self.group)

@@ -144,18 +144,18 @@ class DeepFMTrainStep:
         check(lib.dr_gemm_plane_cache(1), "dr_gemm_plane_cache")   # one split per tensor per step
         if self.optimizer != "sgd":
             self.clock.advance()                                  # t += 1, lr_t (device scalars)
-        if self.optimizer == "adam_rows":     # per-row lookup counts of this batch: side stream, hidden behind the forward
-            self._side_stream.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(self._side_stream):
-                check(lib.dr_embed_adam_count(self.ids.data_ptr(), self.ids.element_size(), B, S, D, self.rows.data_ptr(),
-                                              c._offsets.data_ptr(), self.state.data_ptr(), self._side_stream.cuda_stream),
-                      "dr_embed_adam_count")
         mark("start")
         check(lib.dr_embed_fm_fwd(self.tp.data_ptr(), self.lp.data_ptr(), self.rows.data_ptr(), self.ids.data_ptr(),
                                   self.ids.element_size(), c.bias.data_ptr(), B, S, D, c.row_stride, c.lin_stride,
                                   c.flags, self.stack.data_ptr(),
                                   self.sum_e.data_ptr(), self.fm_logit.data_ptr(), st), "dr_embed_fm_fwd")
         mark("embed_fm_fwd")
+        if self.optimizer == "adam_rows":     # per-row lookup counts of this batch: on the side stream, behind the GEMMs
+            self._side_stream.wait_stream(torch.cuda.current_stream())   # (not behind the gather: both are DRAM-bound)
+            with torch.cuda.stream(self._side_stream):
+                check(lib.dr_embed_adam_count(self.ids.data_ptr(), self.ids.element_size(), B, S, D, self.rows.data_ptr(),
+                                              c._offsets.data_ptr(), self.state.data_ptr(), self._side_stream.cuda_stream),
+                      "dr_embed_adam_count")
         x = self.stack
         K = S * D
         L = len(self.layers)

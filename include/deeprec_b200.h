@@ -181,6 +181,19 @@ int dr_inbatch_softmax_bwd(const float* q, const float* c, const float* w, const
                            const float* lse, const float* gloss,
                            float* gq, float* gc, void* stream);
 
+/* Tensor-core form of the same loss (the contraction of sbcnm.py:129 and both gradient contractions on the tcgen05
+ * 3xTF32 GEMM core).  scores_ws: caller-provided scratch [ws_rows, nc] floats; query rows are processed in blocks of
+ * ws_rows (ws_rows >= nq: one block).  Same arguments, results and reduction as dr_inbatch_softmax_fwd / _bwd.
+ * bwd: scores_valid != 0 and ws_rows >= nq means scores_ws still holds what the forward of the SAME inputs left there
+ * (the raw corrected scores), so the score GEMM is not repeated; the workspace is consumed (overwritten) either way. */
+int dr_inbatch_softmax_fwd_ws(const float* q, const float* c, const float* sample_weight, const float* sampling_prob,
+                              const int64_t* cand_ids, float inv_tau, int64_t nq, int64_t nc, int D,
+                              float* scores_ws, int64_t ws_rows, float* lse_out, float* loss_out, void* stream);
+int dr_inbatch_softmax_bwd_ws(const float* q, const float* c, const float* sample_weight, const float* sampling_prob,
+                              const int64_t* cand_ids, float inv_tau, int64_t nq, int64_t nc, int D,
+                              const float* lse, const float* gloss, float* scores_ws, int64_t ws_rows,
+                              int scores_valid, float* gq, float* gc, void* stream);
+
 /* Materialised score matrix with the same corrections (needed by HardNegativeMining and
  * by metrics): scores [nq,nc] = (Q @ C^T - log p + dup*MIN_FLOAT) (no temperature).       */
 int dr_scores_fwd(const float* q, const float* c, const float* p, const int64_t* cand_ids,

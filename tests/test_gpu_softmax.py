@@ -141,3 +141,45 @@ def test_full_size_c4_properties():
     # => gQ_i = sum_j P_ij c_j - c_i, so  sum_i gQ_i + sum_i c_i = sum_j (sum_i P_ij) c_j ; check against gC identity:
     # sum_j gC_j = sum_i (sum_j G_ij) q_i = 0
     assert float(c.grad.double().sum(0).abs().max()) <= 1e-2
+
+
+@pytest.mark.parametrize("nq,nc,D,tau,use_w,use_p,use_ids,ws_bytes", [
+    (130, 130, 64, 0.2, True, True, True, 2 << 30),       # one score block
+    (257, 300, 128, None, True, True, True, 2 << 30),
+    (513, 513, 64, 0.5, True, False, True, 128 * 513 * 4),    # query rows in blocks of 128 (backward recomputes scores)
+    (300, 300, 32, None, False, False, False, 128 * 300 * 4),
+    (64, 130, 32, None, False, True, False, 2 << 30),
+])
+def test_inbatch_softmax_tensor_core_form(nq, nc, D, tau, use_w, use_p, use_ids, ws_bytes):
+    """The tcgen05 form (dr_inbatch_softmax_fwd_ws / _bwd_ws: score blocks through the 3xTF32 GEMM core) against the
+    float64 oracle and against the fused FFMA kernels -- forced on at sizes the default heuristic gives to the latter."""
+    from deep_recommenders.keras.models.retrieval import sbcnm
+    from deep_recommenders_b200 import ops
+    rng = np.random.default_rng(nq + nc + D + 1)
+    q = (rng.standard_normal((nq, D)) / np.sqrt(D) * 3).astype(np.float32)
+    c = (rng.standard_normal((nc, D)) / np.sqrt(D) * 3).astype(np.float32)
+    w = rng.uniform(0.5, 2.0, nq).astype(np.float32) if use_w else None
+    p = rng.uniform(0.01, 1.0, nc).astype(np.float32) if use_p else None
+    ids = rng.integers(0, max(2, nc // 3), nc).astype(np.int64) if use_ids else None
+    task = sbcnm.Retrieval(temperature=tau)
+    kw = dict(sample_weight=None if w is None else cu(w), candidate_sampling_probability=None if p is None else cu(p),
+              candidate_ids=None if ids is None else cu(ids))
+    out = {}
+    old = (ops.SOFTMAX_TC_MIN_SCORES, ops.SOFTMAX_TC_WS_BYTES)
+    try:
+        for form, min_scores in (("tc", 0), ("ffma", 1 << 62)):
+            ops.SOFTMAX_TC_MIN_SCORES, ops.SOFTMAX_TC_WS_BYTES = min_scores, ws_bytes
+            qt, ct = cu(q).requires_grad_(True), cu(c).requires_grad_(True)
+            loss = task(qt, ct, **kw)
+            (loss * 1.5).backward()
+            out[form] = (float(loss), qt.grad.cpu().numpy(), ct.grad.cpu().numpy())
+    finally:
+        ops.SOFTMAX_TC_MIN_SCORES, ops.SOFTMAX_TC_WS_BYTES = old
+    ref_loss, _, _ = R.retrieval_loss(q, c, w, p, ids, tau, None, np.float64)
+    gq, gc = R.retrieval_grad(q, c, w, p, ids, tau, np.float64)
+    gq, gc = 1.5 * gq, 1.5 * gc
+    for form in ("tc", "ffma"):
+        l, a, b = out[form]
+        assert abs(l - float(ref_loss)) <= 1e-5 * abs(float(ref_loss)) + 1e-4, form
+        assert np.abs(a - gq).max() <= 2e-5 * np.abs(gq).max() + 1e-6, form
+        assert np.abs(b - gc).max() <= 2e-5 * np.abs(gc).max() + 1e-6, form
