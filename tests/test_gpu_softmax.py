@@ -140,7 +140,8 @@ def test_full_size_c4_properties():
     # sum_i gC_i = sum_i sum_j G_ji q_j ... use: sum over all of gQ == sum_j (colsum G)_j c_j; and rows of G sum to 0
     # => gQ_i = sum_j P_ij c_j - c_i, so  sum_i gQ_i + sum_i c_i = sum_j (sum_i P_ij) c_j ; check against gC identity:
     # sum_j gC_j = sum_i (sum_j G_ij) q_i = 0
-    assert float(c.grad.double().sum(0).abs().max()) <= 1e-2
+    # (cancellation-aware bound: 1e-5 of the sum of |terms| of each column sum)
+    assert float((c.grad.double().sum(0).abs() / c.grad.double().abs().sum(0)).max()) <= 1e-5
 
 
 @pytest.mark.parametrize("nq,nc,D,tau,use_w,use_p,use_ids,ws_bytes", [
