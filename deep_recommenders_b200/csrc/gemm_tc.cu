@@ -733,7 +733,8 @@ int gemm_tc_launch(const GemmArgs& a0, bool ta, bool tb, cudaStream_t st) {
     } else {
       if (int rc = make_map(&tm2[0], a.A, a.M, a.K, a.lda, TC_BK, true)) return rc;
     }
-    const int bn = a.N <= 32 ? 32 : (a.N <= 64 ? 64 : 128);
+    const bool wide = g_tune_gemm_bn == 256 && a.N >= 256;      // experiment: 128 x 256 tiles, 2-stage ring
+    const int bn = a.N <= 32 ? 32 : (a.N <= 64 ? 64 : (wide ? 256 : 128));
     if (!B_MN) {
       if (int rc = make_map(&tm2[2], a.B, a.K, a.N, a.ldb, bn)) return rc;
     } else {
@@ -751,6 +752,7 @@ int gemm_tc_launch(const GemmArgs& a0, bool ta, bool tb, cudaStream_t st) {
     if (bn == 32) DR_TC2_LAUNCH(32, 4);
     if (bn == 64) DR_TC2_LAUNCH(64, 4);
     if (g_tune_tc_stages == 2) DR_TC2_LAUNCH(128, 2);
+    if (bn == 256) DR_TC2_LAUNCH(256, 2);
     DR_TC2_LAUNCH(128, 3);
 #undef DR_TC2_LAUNCH
   }
