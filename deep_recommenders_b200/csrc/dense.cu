@@ -115,7 +115,7 @@ static int gemm_xt_g(const float* X, const float* G, float* gW, int64_t M, int64
 // raw corrected scores of query rows [row0, row0 + rb): S = Q_blk C^T - log p[n] + dup * MIN_FLOAT  -> ws [rb, nc]
 int softmax_scores_block(const float* q_blk, const float* c, const float* p, const int64_t* ids, int64_t row0, int64_t rb,
                          int64_t nc, int D, float* ws, cudaStream_t st) {
-  GemmArgs a = mk(q_blk, c, ws, rb, nc, D, D, D, nc, EPI_SCORES);
+  GemmArgs a = mk(q_blk, c, ws, rb, nc, D, D, D, nc, (p || ids) ? EPI_SCORES : EPI_STORE);
   a.bias = p; a.cand_ids = ids; a.row0 = row0;
   return gemm_launch(a, false, true, st);
 }
@@ -249,7 +249,7 @@ extern "C" int dr_scores_fwd(const float* q, const float* c, const float* p, con
                              int64_t nq, int64_t nc, int D, float* scores, void* stream) {
   DR_REQUIRE(q && c && scores, DR_EINVAL, "dr_scores_fwd: null pointer");
   DR_REQUIRE(nq >= 0 && nc >= 1 && D >= 1, DR_EINVAL, "dr_scores_fwd: bad shape");
-  GemmArgs a = mk(q, c, scores, nq, nc, D, D, D, nc, EPI_SCORES);
+  GemmArgs a = mk(q, c, scores, nq, nc, D, D, D, nc, (p || cand_ids) ? EPI_SCORES : EPI_STORE);
   a.bias = p; a.cand_ids = cand_ids;
   return gemm_launch(a, false, true, (cudaStream_t)stream);
 }

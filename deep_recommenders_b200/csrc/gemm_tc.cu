@@ -33,6 +33,7 @@ namespace dr {
 // ---- workspace registered by the host (dr_set_workspace) ----------------------------------------
 int g_tune_gemm_bn = 0;   // 0 = auto, 128 or 256: tensor-core tile width
 int g_tune_tc_min_n = 32;   // 32 since round 2 (BN = 32 / 64 tiles of the in-kernel-split core: C2 step 0.849 -> 0.822 ms)
+int g_tune_tc_l2_promo = 256;
 int g_tune_tc_mn = 1;     // 1 = feed MN-major operands as stored (SWIZZLE_128B_BASE32B); 0 = transpose them in the split pre-pass
 static void* g_ws_ptr = nullptr;
 static size_t g_ws_bytes = 0;
@@ -488,6 +489,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                 for (int jj = 0; jj < 32; ++jj)
                   o[jj] = act_apply(__uint_as_float(r[jj]) + __shfl_sync(0xffffffffu, bl, jj), a.act);
               }
+            } else if (a.epi == EPI_SCORES) {
+              // v = acc - log p[n] + dup(m, n) * MIN_FLOAT (sbcnm.py:78-86, 52-75): lane l holds log p and the id of column
+              // nb + l (one coalesced load each per slab), broadcast by shuffles; the thread's own row id is loaded once
+              const int64_t mg = m + a.row0;
+              const bool col_ok = nb + lane < a.N;
+              const float lpl = (a.bias && col_ok) ? logf(__ldg(a.bias + nb + lane)) : 0.f;
+              const long long idl = (a.cand_ids && col_ok) ? (long long)__ldg(a.cand_ids + nb + lane) : -1ll;
+              const long long idm = (a.cand_ids && row_ok && mg < a.N) ? (long long)__ldg(a.cand_ids + mg) : -2ll;
+#pragma unroll
+              for (int jj = 0; jj < 32; ++jj) {
+                float v = __uint_as_float(r[jj]) - __shfl_sync(0xffffffffu, lpl, jj);
+                if (a.cand_ids) {
+                  const long long idj = __shfl_sync(0xffffffffu, idl, jj);
+                  if (mg != nb + jj && idj == idm) v += (-FLT_MAX / 100.0f);
+                }
+                o[jj] = v;
+              }
             } else if (a.epi == EPI_ACTGRAD && a.act == DR_ACT_RELU && nb + 31 < a.N && mw + 31 < a.M) {
               // relu'(y) = [y > 0].  The y slab is fetched COALESCED (each load instruction reads 4 whole 128-B rows) into
               // the staging buffer in the same swizzled layout, then every thread reads its own row from shared memory
@@ -602,7 +620,10 @@ static int make_map(CUtensorMap* tm, const float* base, int64_t inner, int64_t o
   CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE,
                         mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        // K-major operand: consecutive k-blocks of a tile walk along each row 128 B at a time -- fetch 256 B
+                        // per L2 miss so every second k-block finds its rows in L2 (knob tc_l2_promo: 128 / 256)
+                        (!mn_major && g_tune_tc_l2_promo == 256) ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                                                 : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("gemm_tc: cuTensorMapEncodeTiled failed (CUresult %d; inner=%lld outer=%lld pitch=%lld)", (int)r,
@@ -733,7 +754,10 @@ int gemm_tc_launch(const GemmArgs& a0, bool ta, bool tb, cudaStream_t st) {
     } else {
       if (int rc = make_map(&tm2[0], a.A, a.M, a.K, a.lda, TC_BK, true)) return rc;
     }
-    const bool wide = g_tune_gemm_bn == 256 && a.N >= 256;      // experiment: 128 x 256 tiles, 2-stage ring
+    // 128 x 256 tiles (2-stage ring) when they waste no more columns than 128-wide ones (N = 256, 416: C2 step
+    // 0.686 -> 0.657 ms); N = 832 (C3) keeps 128.  Knob gemm_bn: 0 = this rule, 128 / 256 = force.
+    const int64_t pad256 = (a.N + 255) / 256 * 256, pad128 = (a.N + 127) / 128 * 128;
+    const bool wide = a.N >= 256 && (g_tune_gemm_bn == 256 || (g_tune_gemm_bn == 0 && pad256 <= pad128));
     const int bn = a.N <= 32 ? 32 : (a.N <= 64 ? 64 : (wide ? 256 : 128));
     if (!B_MN) {
       if (int rc = make_map(&tm2[2], a.B, a.K, a.N, a.ldb, bn)) return rc;
