@@ -862,7 +862,7 @@ def test_world1_sharded_trainer_checkpoint_round_trip(tmp_path, D):
         assert torch.equal(a.emb.lin_view(), b.emb.lin_view())
         assert a.get_config() == b.get_config()
         la, lb = float(a.step(ids, lab).item()), float(b.step(ids, lab).item())
-        assert la == lb
+        assert abs(la - lb) <= 1e-6 * abs(la)       # same state, same batch; the loss is summed with float atomics (order)
         with pytest.raises(ValueError, match="was written for"):
             ShardedDeepFMTrainStep(cols, D, [16, 8], batch_size=B, lr=0.05, seed=1, device="cuda", exchange="p2p",
                                    use_graph=False).load(prefix)
