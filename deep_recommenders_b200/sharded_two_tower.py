@@ -105,11 +105,15 @@ class ShardedTwoTowerTrainStep:
                                                ids.data_ptr(), 8, None, None, None, grad.data_ptr(), self.b, 1, self.D,
                                                self.D, 0, 0, None, -self.lr, st), "dr_embed_fm_bwd_sharded")
 
-    def run(self) -> torch.Tensor:
+    def run(self, mark=None) -> torch.Tensor:
+        """`mark(label)` (optional, profiling): called after each phase, on the launching stream."""
         lib, G, b, D = self.lib, self.world, self.b, self.D
         st = lambda: torch.cuda.current_stream().cuda_stream
+        mark = mark or (lambda label: None)
+        mark("start")
         self._gather(self.off_user, self.rows_user, self.user_ids, self.q)
         self._gather(self.off_item, self.rows_item, self.item_ids, self.c_local)
+        mark("gather_p2p")
         if G > 1:
             dist.all_gather_into_tensor(self.c_all.view(G * b, D), self.c_local, group=self.group)
             torch.index_select(self.c_all, 0, self._order, out=self.c_rot.view(G, b, D))
@@ -123,6 +127,7 @@ class ShardedTwoTowerTrainStep:
             else:
                 self.ids_rot.copy_(self.item_ids.view(b))
             ids_ptr = self.ids_rot.data_ptr()
+        mark("all_gather_candidates")
         if self.scores_ws is not None:     # tensor-core form: the b x (G b) score block lives in a scratch buffer
             check(lib.dr_inbatch_softmax_fwd_ws(self.q.data_ptr(), self.c_rot.data_ptr(), None, None, ids_ptr, self.inv_tau,
                                                 b, G * b, D, self.scores_ws.data_ptr(), b, self.lse.data_ptr(),
@@ -138,14 +143,18 @@ class ShardedTwoTowerTrainStep:
             check(lib.dr_inbatch_softmax_bwd(self.q.data_ptr(), self.c_rot.data_ptr(), None, None, ids_ptr, self.inv_tau,
                                              b, G * b, D, self.lse.data_ptr(), self.gloss.data_ptr(), self.gq.data_ptr(),
                                              self.gc_rot.data_ptr(), st()), "dr_inbatch_softmax_bwd")
+        mark("softmax_fwd_bwd")
         if G > 1:
             torch.index_select(self.gc_rot.view(G, b, D), 0, self._inv_order, out=self.gc_all)
             dist.reduce_scatter_tensor(self.gc_local, self.gc_all.view(G * b, D), group=self.group)
         else:
             self.gc_local.copy_(self.gc_rot)
+        mark("reduce_scatter_grads")
         self._update(self.off_user, self.rows_user, self.user_ids, self.gq)
         self._update(self.off_item, self.rows_item, self.item_ids, self.gc_local)
+        mark("update_p2p")
         self.handle.barrier(channel=0)
+        mark("barrier")
         return self.loss
 
     def step(self, user_ids: torch.Tensor, item_ids: torch.Tensor) -> torch.Tensor:

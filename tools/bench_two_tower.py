@@ -46,6 +46,24 @@ def main():
         st.step(*pool[i % 8])
     e1.record()
     barrier()
+    # per-phase times (eager passes with events between the phases; every rank runs them: the step has collectives)
+    runs = []
+    for i in range(8):
+        st.user_ids.copy_(pool[i % 8][0].reshape(-1, 1)); st.item_ids.copy_(pool[i % 8][1].reshape(-1, 1))
+        evs = []
+
+        def mark(label, evs=evs):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            evs.append((label, e))
+
+        st.run(mark)
+        runs.append(evs)
+    barrier()
+    phases = {}
+    for evs in runs[2:]:
+        for (l0, a), (l1, b_) in zip(evs[:-1], evs[1:]):
+            phases[l1] = phases.get(l1, 0.0) + a.elapsed_time(b_) / (len(runs) - 2)
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     loss = st.loss.clone()
@@ -59,7 +77,7 @@ def main():
                                                  "embedding towers, SGD, row-sharded tables",
                                      "softmax_core": "tcgen05 3xTF32 (score block in scratch)" if st.scores_ws is not None
                                      else "fused FFMA (scores never materialised)"},
-                          "global_loss": float(loss)}), flush=True)
+                          "kernel_ms": phases, "global_loss": float(loss)}), flush=True)
     dist.destroy_process_group()
 
 
