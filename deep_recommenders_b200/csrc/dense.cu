@@ -123,6 +123,18 @@ int softmax_scores_block(const float* q_blk, const float* c, const float* p, con
 int softmax_grad_block(const float* g_ws, const float* q_blk, const float* c, int64_t rb, int64_t nc, int D, float* gq_blk,
                        float* gc, cudaStream_t st) {
   GemmArgs a = mk(g_ws, c, gq_blk, rb, D, nc, nc, D, D, EPI_STORE);
+  // few query rows (a sharded rank's b x (G b) block): rb / 128 output tiles cannot fill 148 SMs -- split the long
+  // contraction over the candidates instead (partial sums meet through TMA reduce-adds into the zeroed gq block)
+  const int64_t tiles = ((rb + 127) / 128) * ((D + 63) / 64);
+  if (tiles < kNumSMs / 2 && nc >= 1024) {
+    int64_t sk = (kNumSMs + tiles - 1) / tiles;
+    if (sk > nc / 256) sk = nc / 256;
+    if (sk > 1) {
+      DR_CUDA_CALL(cudaMemsetAsync(gq_blk, 0, sizeof(float) * (size_t)rb * D, st));
+      a.epi = EPI_ATOMIC;
+      a.splitk = (int)sk;
+    }
+  }
   if (int rc = gemm_launch(a, false, false, st)) return rc;
   return gemm_xt_g(g_ws, q_blk, gc, rb, nc, D, st, /*accumulate=*/true);
 }

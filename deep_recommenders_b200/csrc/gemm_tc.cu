@@ -757,7 +757,9 @@ int gemm_tc_launch(const GemmArgs& a0, bool ta, bool tb, cudaStream_t st) {
     // 128 x 256 tiles (2-stage ring) when they waste no more columns than 128-wide ones (N = 256, 416: C2 step
     // 0.686 -> 0.657 ms); N = 832 (C3) keeps 128.  Knob gemm_bn: 0 = this rule, 128 / 256 = force.
     const int64_t pad256 = (a.N + 255) / 256 * 256, pad128 = (a.N + 127) / 128 * 128;
-    const bool wide = a.N >= 256 && (g_tune_gemm_bn == 256 || (g_tune_gemm_bn == 0 && pad256 <= pad128));
+    const int64_t tiles256 = ((a.M + TC_BM - 1) / TC_BM) * (pad256 / 256) * (a.splitk > 0 ? a.splitk : 1);
+    const bool wide = a.N >= 256 && (g_tune_gemm_bn == 256 ||
+                                     (g_tune_gemm_bn == 0 && pad256 <= pad128 && tiles256 >= 2 * kNumSMs));   // enough tiles to fill the SMs
     const int bn = a.N <= 32 ? 32 : (a.N <= 64 ? 64 : (wide ? 256 : 128));
     if (!B_MN) {
       if (int rc = make_map(&tm2[2], a.B, a.K, a.N, a.ldb, bn)) return rc;
