@@ -16,6 +16,7 @@ LIB_PATH = _PKG / "lib" / "libdeeprec_b200.so"
 HEADER_PATH = _PKG.parent / "include" / "deeprec_b200.h"
 
 _lib = None
+_GEMM_ENV = os.environ.get("DR_GEMM", "tc2")
 
 _p = C.c_void_p
 _i64 = C.c_int64
@@ -117,6 +118,10 @@ def load() -> C.CDLL:
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, C.c_int)
     _lib = lib
+    # DR_GEMM names the GEMM core for THIS process (the library's own default is tc2); variant 1 (pre-split planes) is
+    # switched on lazily by ensure_gemm_workspace because it needs the registered scratch
+    if _GEMM_ENV == "ffma":
+        lib.dr_tune_set(b"gemm_variant", 0)
     return lib
 
 
@@ -177,7 +182,6 @@ def disable_tensor_core_gemm() -> None:
 # DR_GEMM selects the default GEMM core: tc2 (default) = tcgen05 3xTF32 with the hi/lo split inside the kernel
 # (bit-identical outputs to tc, 17-23 % faster at the C2 layer shapes: profiles/check_gemm_insplit_r01.json),
 # tc = tcgen05 3xTF32 on pre-split planes, ffma = FFMA.
-_GEMM_ENV = os.environ.get("DR_GEMM", "tc2")
 _tc_enabled = _GEMM_ENV != "ffma"
 _tc_variant = 1 if _GEMM_ENV == "tc" else 2
 _tc_applied = False
