@@ -37,6 +37,8 @@ struct GemmArgs {
   const int64_t* cand_ids;   // EPI_SCORES
   int64_t row0;              // EPI_SCORES: query row m of this call is global query m + row0 (its positive = candidate m + row0)
   int splitk;                // >= 1
+  int stages;                // 0 = default operand-ring depth; 2 = two stages (161 KB of shared memory instead of 225 KB, so
+                             // an HBM / NVLink-bound kernel on another stream can share the SMs with the persistent GEMM)
 };
 
 extern int g_tune_gemm_variant;

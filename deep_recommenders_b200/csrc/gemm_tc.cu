@@ -758,7 +758,8 @@ int gemm_tc_launch(const GemmArgs& a0, bool ta, bool tb, cudaStream_t st) {
     // 0.686 -> 0.657 ms); N = 832 (C3) keeps 128.  Knob gemm_bn: 0 = this rule, 128 / 256 = force.
     const int64_t pad256 = (a.N + 255) / 256 * 256, pad128 = (a.N + 127) / 128 * 128;
     const int64_t tiles256 = ((a.M + TC_BM - 1) / TC_BM) * (pad256 / 256) * (a.splitk > 0 ? a.splitk : 1);
-    const bool wide = a.N >= 256 && (g_tune_gemm_bn == 256 ||
+    const bool two_stage = g_tune_tc_stages == 2 || a.stages == 2;      // forces the 128-wide tile
+    const bool wide = !two_stage && a.N >= 256 && (g_tune_gemm_bn == 256 ||
                                      (g_tune_gemm_bn == 0 && pad256 <= pad128 && tiles256 >= 2 * kNumSMs));   // enough tiles to fill the SMs
     const int bn = a.N <= 32 ? 32 : (a.N <= 64 ? 64 : (wide ? 256 : 128));
     if (!B_MN) {
@@ -777,7 +778,7 @@ int gemm_tc_launch(const GemmArgs& a0, bool ta, bool tb, cudaStream_t st) {
     } while (0)
     if (bn == 32) DR_TC2_LAUNCH(32, 4);
     if (bn == 64) DR_TC2_LAUNCH(64, 4);
-    if (g_tune_tc_stages == 2) DR_TC2_LAUNCH(128, 2);
+    if (two_stage) DR_TC2_LAUNCH(128, 2);
     if (bn == 256) DR_TC2_LAUNCH(256, 2);
     DR_TC2_LAUNCH(128, 3);
 #undef DR_TC2_LAUNCH
