@@ -18,6 +18,7 @@ NAMES = ["producer_wait_free_stage", "splitter_wait_tma", "splitter_work", "mma_
 def main():
     lib = _lib.load()
     _lib.enable_tensor_core_gemm(variant=2)
+    _lib.tune("gemm_bn", 128)      # the instrumented instantiation exists for the 128-wide tile only
     st = torch.cuda.current_stream().cuda_stream
     out = []
     buf = (C.c_uint64 * 16)()

@@ -22,13 +22,16 @@ run zipf --ids zipf
 run zipf_agg --ids zipf --tune embed_bwd_mode=1
 run adam_rows --optimizer adam_rows
 timeout 120 python -u tools/bench_two_tower.py > gpurun_out/r02c_n1_c4.log 2>&1; grep '^{' gpurun_out/r02c_n1_c4.log | cut -c1-300
-timeout 120 python -u tools/gemm_prof.py > gpurun_out/r02_final_gemm_prof.log 2>&1; cut -c1-330 gpurun_out/r02_final_gemm_prof.log
+timeout 120 python -u tools/gemm_prof.py > gpurun_out/r02_final_gemm_prof.log 2>&1; cut -c1-330 gpurun_out/r02_final_gemm_prof.log; cp gpurun_out/gemm_prof.json gpurun_out/r02_final_gemm_prof.json
 bash tools/ncu_launches.sh r02_final > /dev/null 2>&1; python -c "
 import json; [print(o) for o in sorted(json.load(open('gpurun_out/launches_r02_final.json')), key=lambda o: -o['share'])[:10]]"
-timeout 500 ncu --set full --clock-control none --import-source on -k regex:embed_fm -c 4 -f -o gpurun_out/embed_r02 \
+# .ncu-rep files stay on the box (/tmp): only the CSV summaries travel back (gpurun_out is capped at 64 MiB)
+timeout 500 ncu --set full --clock-control none -k regex:embed_fm -c 4 -f -o /tmp/embed_r02 \
     python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_embed_r02.log 2>&1
-timeout 500 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel --launch-skip 6 -c 6 -f -o gpurun_out/gemm_r02 \
+timeout 500 ncu --set full --clock-control none -k regex:gemm_tc_kernel --launch-skip 6 -c 6 -f -o /tmp/gemm_r02 \
     python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_gemm_r02.log 2>&1
-python tools/ncu_summary.py gpurun_out/embed_r02.ncu-rep gpurun_out/embed_r02_ncu.csv
-python tools/ncu_summary.py gpurun_out/gemm_r02.ncu-rep gpurun_out/gemm_r02_ncu.csv
-ls -la gpurun_out/*.ncu-rep
+python tools/ncu_summary.py /tmp/embed_r02.ncu-rep gpurun_out/embed_r02_ncu.csv
+python tools/ncu_summary.py /tmp/gemm_r02.ncu-rep gpurun_out/gemm_r02_ncu.csv
+ncu -i /tmp/embed_r02.ncu-rep --page details --csv > gpurun_out/embed_r02_ncu_details.csv 2>/dev/null
+ncu -i /tmp/gemm_r02.ncu-rep --page details --csv > gpurun_out/gemm_r02_ncu_details.csv 2>/dev/null
+du -sh gpurun_out
