@@ -27,35 +27,39 @@ def main():
         return flops, 4.0 * (reads + writes), t_hbm, t_tc
 
     rows = []
-    alg_f = B * (S * (8 + 4 * D + 4) + 4 * S * D + 4 * D + 4)
+    alg_f = B * (S * (8 + 4 * D + 4) + 4 * S * D + 4)
     rows.append(("embed_fm_fwd (fused gather + first-order + FM)", "hbm", alg_f, None, alg_f / hbm, None, km["embed_fm_fwd"]))
-    x = B * dims[0]
-    for i in range(3):
+    head = "head_bce" in km
+    nfwd = 2 if head else 3
+    for i in range(nfwd):
         M, K, N = B, dims[i], dims[i + 1]
-        fl, by, th, tt = gemm(M, K, N, M * K + K * N, M * N, N >= 96)
+        fl, by, th, tt = gemm(M, K, N, M * K + K * N, M * N, N >= 32)
         rows.append((f"dense_fwd_{i}  [{M} x {K}] @ [{K} x {N}]", "tensor" if tt and tt > th else "hbm", by, fl, th, tt,
                      km[f"dense_fwd_{i}"]))
-    rows.append(("bce (loss + dL/dlogit)", "hbm", 4.0 * B * 4, None, 4.0 * B * 4 / hbm, None, km["bce"]))
-    for i in (2, 1):
+    if head:
+        by = 4.0 * B * (2 * dims[2] + 4)
+        rows.append(("head_bce  Dense(1) + BCE + their backward (one kernel)", "hbm", by, None, by / hbm, None, km["head_bce"]))
+    else:
+        rows.append(("bce (loss + dL/dlogit)", "hbm", 4.0 * B * 4, None, 4.0 * B * 4 / hbm, None, km["bce"]))
+    for i in ((1,) if head else (2, 1)):
         M, K, N = B, dims[i], dims[i + 1]
-        # dX = gZ @ W^T and dW = X^T @ gZ, plus the activation-gradient pass over gZ / y
-        fl = 2 * 2.0 * M * K * N
-        by = 4.0 * (3 * M * N + 2 * M * K + 2 * K * N)
-        tt = 3.0 * fl / tf32 if N >= 96 else None
+        fl = 2 * 2.0 * M * K * N                       # dX (chained: x act'(y) in the epilogue) and dW
+        by = 4.0 * (2 * M * N + 3 * M * K + 2 * K * N)
+        tt = 3.0 * fl / tf32 if N >= 32 else None
         rows.append((f"dense_bwd_{i}  dX + dW of layer {i}", "hbm", by, fl, by / hbm, tt, km[f"dense_bwd_{i}"]))
     M, K, N = B, dims[0], dims[1]
     fl = 2.0 * M * K * N
-    by = 4.0 * (3 * M * N + M * K + K * N)
-    rows.append(("dense_bwd_0_dx  gZ = g . act'(y); dX = gZ @ W^T", "tensor", by, fl, by / hbm, 3.0 * fl / tf32,
+    by = 4.0 * (2 * M * N + M * K + K * N)
+    rows.append(("dense_bwd_0_dx  column sums of gZ; dX = gZ @ W^T", "tensor", by, fl, by / hbm, 3.0 * fl / tf32,
                  km["dense_bwd_0_dx"]))
     alg_b = B * (S * 8 + 8 * S * D + 4 * D + 4 + 4 * S * D + 4 * S)
     by = 4.0 * (M * K + M * N + K * N) + alg_b
-    rows.append(("dense_bwd_0_dw (tensor) || embed_fm_bwd + fused sparse SGD (hbm), two streams", "hbm", by, fl, by / hbm,
+    rows.append(("dense_bwd_0_dw (tensor) then embed_fm_bwd + fused sparse SGD (hbm), two streams", "hbm", by, fl, by / hbm,
                  3.0 * fl / tf32, km["dense_bwd_0_dw+embed_fm_bwd"]))
     nparam = sum(dims[i] * dims[i + 1] + dims[i + 1] for i in range(3))
     rows.append(("sgd (tower)", "hbm", 12.0 * nparam, None, 12.0 * nparam / hbm, None, km["sgd"]))
 
-    print("# Roofline of the C2 train step, round 1\n")
+    print("# Roofline of the C2 train step\n")
     print(f"Source: `{os.path.relpath(sys.argv[1], ROOT)}` (`kernel_ms`: CUDA events between kernel groups, eager pass, GEMM core "
           f"`{bench.get('gemm_core', 'tcgen05 3xTF32, pre-split planes (tc)')}`), peaks from `MEASURED_PEAKS.json`: HBM "
           f"{peaks['hbm_gbs']:.1f} GB/s, bf16 {peaks['bf16_tflops']:.1f} TFLOP/s (TF32 dense = half; a 3xTF32 product = 3 MMAs).\n")
@@ -71,12 +75,13 @@ def main():
               f"{'' if tt is None else f'{tt * 1e6:.1f}'} | {ms * 1e3:.1f} | {ms * 1e-3 / floor:.1f}x |")
     print(f"| **step** | | | | | | **{tot_meas * 1e6:.0f}** (graph replay: {bench['ms_per_step'] * 1e3:.0f}) | "
           f"{tot_meas / tot_floor:.1f}x of {tot_floor * 1e6:.0f} µs |")
-    print("\nReading it: the fused gather + FM forward is at 1.7x its algorithmic floor here (1.9x back to back, 0.535 of the HBM "
-          "peak; 76 % of the copy peak at the DRAM level, DESIGN.md section 6), the backward + sparse SGD hides behind the "
-          "layer-0 weight-gradient GEMM; the wide tower GEMMs are 6.5-7x above their floors and the skinny layers (N = 32, 1: FFMA "
-          "core, activation-gradient pass, ~10 us launch-bound tails) 4-17x -- the step is GEMM-bound, which is why the "
-          "end-of-round work went into the split-in-kernel tcgen05 core (`profiles/check_gemm_insplit_r01.json`: -17 to -23 % at "
-          "the layer level, not yet in this table) and why the GEMM items lead DESIGN.md section 8.")
+    print("\nReading it (round 2): every group is within 1.8-2.8x of its floor except the two launch-latency-bound tails (head, "
+          "tower SGD).  The gather + FM forward sits at the DRAM's random-row rate, not at its byte rate (DESIGN.md section 4: "
+          "same time at half the DRAM bytes, same time on half the SMs); the tcgen05 GEMMs are bound by shared-memory "
+          "bandwidth in the main loop (in-kernel hi/lo split + three operand reads per product: "
+          "profiles/gemm_prof_r02_final.json, 1 650 cycles per k-block against 790 for the MMAs); the layer-0 weight gradient and "
+          "the embedding update share a label because they are issued on two streams, but the persistent GEMM owns every SM's "
+          "shared memory, so they run one after the other (about 110 + 120 us).")
 
 
 if __name__ == "__main__":
