@@ -149,7 +149,7 @@ def main():
                     help="synthetic id distribution: uniform (headline) or Zipf(1.05) clipped to the table (SURVEY 8d second run)")
     ap.add_argument("--tune", action="append", default=[], metavar="KNOB=VALUE",
                     help="developer knob of libdeeprec_b200.so (dr_tune_set), e.g. --tune tc_min_n=32; recorded in the line")
-    ap.add_argument("--optimizer", default="sgd", choices=["sgd", "adam", "lazy_adam", "adam_rows"],
+    ap.add_argument("--optimizer", default="sgd", choices=["sgd", "adam", "lazy_adam", "adam_rows", "adam_rows_tf"],
                     help="N=1: sgd (default, fused row-sparse SGD), adam (TF-exact dense ApplyAdam over the arena), lazy_adam "
                          "(row-sparse, two kernels), adam_rows (row-sparse Adam fused into the backward scatter)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],

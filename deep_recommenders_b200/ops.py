@@ -421,13 +421,21 @@ class AdamClock:
     """Device-resident step counter t and bias-corrected rate lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t)
     (Keras optimizer_v2 Adam._prepare_local), advanced by one kernel so a captured train step needs no host scalar."""
 
-    def __init__(self, lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-7, device="cuda"):
+    def __init__(self, lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-7, device="cuda",
+                 history: int = 0):
         self.lr, self.beta1, self.beta2, self.eps = float(lr), float(beta1), float(beta2), float(eps)
         self.step = torch.zeros((1,), dtype=torch.int64, device=device)
         self.lr_t = torch.zeros((1,), dtype=torch.float32, device=device)
+        # ring of the last `history` bias-corrected rates (dr_adam_advance_hist): what the row-sparse TF-equal Adam
+        # replays the skipped steps of a row with
+        self.lr_hist = torch.zeros((history,), dtype=torch.float32, device=device) if history else None
 
     def advance(self) -> None:
         lib = _lib.load()
+        if self.lr_hist is not None:
+            check(lib.dr_adam_advance_hist(self.step.data_ptr(), self.lr, self.beta1, self.beta2, self.lr_t.data_ptr(),
+                                           self.lr_hist.data_ptr(), self.lr_hist.numel(), _stream()), "dr_adam_advance_hist")
+            return
         check(lib.dr_adam_advance(self.step.data_ptr(), self.lr, self.beta1, self.beta2, self.lr_t.data_ptr(),
                                   _stream()), "dr_adam_advance")
 

@@ -37,8 +37,8 @@ class DeepFMTrainStep:
     def __init__(self, model, batch_size: int, lr: float = 0.01, id_dtype=torch.int64, use_graph: bool = True,
                  optimizer: str = "sgd", beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-7):
         self.lib = _lib.load()
-        if optimizer not in ("sgd", "adam", "lazy_adam", "adam_rows"):
-            raise ValueError(f"optimizer must be 'sgd', 'adam', 'lazy_adam' or 'adam_rows', got {optimizer!r}")
+        if optimizer not in ("sgd", "adam", "lazy_adam", "adam_rows", "adam_rows_tf"):
+            raise ValueError(f"optimizer must be 'sgd', 'adam', 'lazy_adam', 'adam_rows' or 'adam_rows_tf', got {optimizer!r}")
         self.optimizer = optimizer
         self.model = model
         coll = model.embeddings
@@ -103,18 +103,19 @@ class DeepFMTrainStep:
         self.tp, self.lp, self.rows = coll.pointers(coll.weight, coll.linear)
         if optimizer != "sgd":
             # optimizer state: gradient arena (all-zero between steps), m, v in the tables' own layout
-            self.clock = ops.AdamClock(lr, beta1, beta2, eps, device=dev)
-            z = lambda t: None if (t is None or optimizer == "adam_rows") else torch.zeros_like(t)
+            self.clock = ops.AdamClock(lr, beta1, beta2, eps, device=dev,
+                                       history=(1 << 16) if optimizer == "adam_rows_tf" else 0)
+            z = lambda t: None if (t is None or optimizer in ("adam_rows", "adam_rows_tf")) else torch.zeros_like(t)
             self.g_arena, self.m_arena, self.v_arena = z(coll.weight.data), z(coll.weight.data), z(coll.weight.data)
             self.g_lin, self.m_lin, self.v_lin = z(coll.linear), z(coll.linear), z(coll.linear)
             self.g_bias, self.m_bias, self.v_bias = (torch.zeros((1,), **f) for _ in range(3))
             self.m_flat, self.v_flat = torch.zeros_like(self.flat), torch.zeros_like(self.flat)
-            if optimizer != "adam_rows":
+            if optimizer not in ("adam_rows", "adam_rows_tf"):
                 self.gtp, self.glp, _ = coll.pointers(self.g_arena, self.g_lin, cache=False)
             self.stamp = (torch.zeros((coll.total_rows,), device=dev, dtype=torch.int32)
                           if optimizer == "lazy_adam" else None)
             self.state = None
-            if optimizer == "adam_rows":
+            if optimizer in ("adam_rows", "adam_rows_tf"):
                 # row-sparse Adam fused into the backward: ONE state block per row [g | m | v | g_w m_w v_w count]
                 # replaces the three table-shaped arenas (dr_embed_fm_bwd_adam)
                 ss = self.lib.dr_embed_adam_state_stride(D)
@@ -150,7 +151,7 @@ class DeepFMTrainStep:
                                   c.flags, self.stack.data_ptr(),
                                   self.sum_e.data_ptr(), self.fm_logit.data_ptr(), st), "dr_embed_fm_fwd")
         mark("embed_fm_fwd")
-        if self.optimizer == "adam_rows":     # per-row lookup counts of this batch: on the side stream, behind the GEMMs
+        if self.optimizer in ("adam_rows", "adam_rows_tf"):     # per-row lookup counts of this batch: on the side stream, behind the GEMMs
             self._side_stream.wait_stream(torch.cuda.current_stream())   # (not behind the gather: both are DRAM-bound)
             with torch.cuda.stream(self._side_stream):
                 check(lib.dr_embed_adam_count(self.ids.data_ptr(), self.ids.element_size(), B, S, D, self.rows.data_ptr(),
@@ -215,7 +216,19 @@ class DeepFMTrainStep:
         adam = self.optimizer != "sgd"
         with torch.cuda.stream(side):
             sst = side.cuda_stream
-            if self.optimizer == "adam_rows":     # Adam of the touched rows inside the backward scatter (one kernel)
+            if self.optimizer == "adam_rows_tf":  # the same, equal to tf.keras Adam: skipped steps of a row are replayed
+                ck = self.clock
+                check(lib.dr_embed_fm_bwd_adam_tf(self.ids.data_ptr(), self.ids.element_size(), self.rows.data_ptr(),
+                                                  c._offsets.data_ptr(), self.stack.data_ptr(), self.sum_e.data_ptr(),
+                                                  gz.data_ptr(), self.g_stack.data_ptr(), B, S, D, c.row_stride,
+                                                  c.lin_stride, c.flags, self.tp.data_ptr(), self.lp.data_ptr(),
+                                                  self.state.data_ptr(), self.g_bias.data_ptr(), ck.step.data_ptr(),
+                                                  ck.lr_t.data_ptr(), ck.lr_hist.data_ptr(), ck.lr_hist.numel(), ck.lr,
+                                                  ck.beta1, ck.beta2, ck.eps, sst), "dr_embed_fm_bwd_adam_tf")
+                check(lib.dr_adam_step(c.bias.data_ptr(), self.g_bias.data_ptr(), self.m_bias.data_ptr(),
+                                       self.v_bias.data_ptr(), 1, 0.0, ck.beta1, ck.beta2, ck.eps, 1, ck.lr_t.data_ptr(), sst),
+                      "dr_adam_step(bias)")
+            elif self.optimizer == "adam_rows":     # Adam of the touched rows inside the backward scatter (one kernel)
                 ck = self.clock
                 check(lib.dr_embed_fm_bwd_adam(self.ids.data_ptr(), self.ids.element_size(), self.rows.data_ptr(),
                                                c._offsets.data_ptr(), self.stack.data_ptr(), self.sum_e.data_ptr(),
@@ -335,8 +348,21 @@ class DeepFMTrainStep:
         if self.optimizer != "sgd":
             st += [t for t in (self.g_arena, self.m_arena, self.v_arena, self.g_lin, self.m_lin, self.v_lin, self.g_bias,
                                self.m_bias, self.v_bias, self.m_flat, self.v_flat, self.stamp, self.state, self.clock.step,
-                               self.clock.lr_t) if t is not None]
+                               self.clock.lr_t, self.clock.lr_hist) if t is not None]
         return st
+
+    def flush_optimizer(self) -> None:
+        """optimizer="adam_rows_tf": replay the pending (skipped) Adam steps of EVERY table row up to the current step, so
+        that the tables equal what tf.keras Adam's dense update would hold.  Call before reading the tables outside the
+        trainer (evaluation, checkpoint); a no-op for the other optimizers."""
+        if self.optimizer != "adam_rows_tf":
+            return
+        c, ck = self.coll, self.clock
+        check(self.lib.dr_embed_adam_flush(self.rows.data_ptr(), c._offsets.data_ptr(), self.S, self.D, c.total_rows,
+                                           c.row_stride, c.lin_stride, c.flags, self.tp.data_ptr(), self.lp.data_ptr(),
+                                           self.state.data_ptr(), ck.step.data_ptr(), ck.lr_hist.data_ptr(),
+                                           ck.lr_hist.numel(), ck.lr, ck.beta1, ck.beta2, ck.eps,
+                                           torch.cuda.current_stream().cuda_stream), "dr_embed_adam_flush")
 
     def capture(self):
         """Warm up (sets kernel attributes) then record the step into a CUDA graph.

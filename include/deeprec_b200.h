@@ -318,7 +318,7 @@ int dr_lazy_adam_rows(const void* ids, int id_bytes, int64_t B, int S, int D, co
  * functor exactly).  replaces: the IndexedSlices gradient of the embedding / first-order variables going through
  * tf.keras.optimizers.Adam (examples/train_deepfm_on_movielens_keras.py:44) for the rows of one batch.
  *   state: [total rows, stride] floats, stride = dr_embed_adam_state_stride(D) (a 128-B multiple), zero-initialised once
- *          by the caller; per row [g D | m D | v D | g_w m_w v_w count | pad] (g = gradient accumulator, zero between
+ *          by the caller; per row [g D | m D | v D | g_w m_w v_w count stamp | pad] (g = gradient accumulator, zero between
  *          steps; count = int32 countdown, zero between steps).
  *   dr_embed_adam_count: count[row] += 1 for every valid lookup of the batch (any time before the backward of the
  *          same batch, e.g. on a side stream while the forward runs).
@@ -335,6 +335,27 @@ int dr_embed_fm_bwd_adam(const void* ids, int id_bytes, const int64_t* rows, con
                          int64_t B, int S, int D, int64_t row_stride, int64_t lin_stride, int flags,
                          float* const* table_ptrs, float* const* lin_ptrs, float* state, float* g_bias,
                          const float* lr_t_dev, float beta1, float beta2, float eps, void* stream);
+
+/* The same fused row-sparse Adam made EQUAL to tf.keras.optimizers.Adam (which is dense: in a step that does not touch
+ * a row, its m and v still decay and the row still moves by its decayed momentum).  Each state block also holds the
+ * step stamp of the row's last update (float index 3 D + 4); when a row is touched again the kernel first replays the
+ * steps it sat out -- m -= m(1-b1), v -= v(1-b2), p -= lr_j m / (sqrt(v) + eps) for j = stamp+1 .. t-1, lr_j from the
+ * ring `lr_hist` [hist_len] that dr_adam_advance_hist fills (recomputed from lr, beta1, beta2 for steps that fell out of
+ * the ring) -- and then applies step t with the batch's gradient.  dr_embed_adam_flush replays the pending steps of
+ * EVERY row up to the current step: call it before the tables are read outside the trainer (evaluation, checkpoint).
+ * With it, parameters equal those of dr_adam_step applied densely every step (tests: float64 ApplyAdam oracle). */
+int dr_adam_advance_hist(int64_t* step_dev, float lr, float beta1, float beta2, float* lr_t_dev,
+                         float* lr_hist, int hist_len, void* stream);
+int dr_embed_fm_bwd_adam_tf(const void* ids, int id_bytes, const int64_t* rows, const int64_t* slot_offsets,
+                            const float* stack, const float* sum_e, const float* g_logit, const float* g_stack,
+                            int64_t B, int S, int D, int64_t row_stride, int64_t lin_stride, int flags,
+                            float* const* table_ptrs, float* const* lin_ptrs, float* state, float* g_bias,
+                            const int64_t* step_dev, const float* lr_t_dev, const float* lr_hist, int hist_len,
+                            float lr, float beta1, float beta2, float eps, void* stream);
+int dr_embed_adam_flush(const int64_t* rows, const int64_t* slot_offsets, int S, int D, int64_t total_rows,
+                        int64_t row_stride, int64_t lin_stride, int flags, float* const* table_ptrs,
+                        float* const* lin_ptrs, float* state, const int64_t* step_dev, const float* lr_hist,
+                        int hist_len, float lr, float beta1, float beta2, float eps, void* stream);
 
 /* ---- 8(f) #2  id pipeline: raw feature value -> int64 row id, bit-exact with TensorFlow's columns.
  * categorical_column_with_hash_bucket = FarmHash Fingerprint64(bytes of str(value)) mod num_buckets

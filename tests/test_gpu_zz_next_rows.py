@@ -868,3 +868,71 @@ def test_world1_sharded_trainer_checkpoint_round_trip(tmp_path, D):
                                    use_graph=False).load(prefix)
     finally:
         dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("D", [16, 32])                   # fused 128-B rows / split layout
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_train_step_adam_rows_tf_equals_dense_tf_adam(D, use_graph):
+    """optimizer="adam_rows_tf": the row-sparse Adam fused into the backward, with per-row step stamps and replay of the
+    steps a row sat out, must give what tf.keras Adam's DENSE update gives (examples/train_deepfm_on_movielens_keras.py:44):
+    the float64 ApplyAdam oracle applied to every row every step.  Sparse batches over 8 steps: most rows are untouched
+    in most steps, some are touched twice with several steps in between, some never again (flushed at the end)."""
+    from deep_recommenders_b200 import feature_column as fc
+    from deep_recommenders_b200.keras.models.ranking import DeepFM
+    from deep_recommenders_b200.training import DeepFMTrainStep
+    rows, B, lr = [300, 7, 120], 16, 0.01
+    S = len(rows)
+    cols = [fc.categorical_column_with_identity(f"c{i}", r) for i, r in enumerate(rows)]
+    model = DeepFM([fc.indicator_column(c) for c in cols], [fc.embedding_column(c, D) for c in cols],
+                   dnn_units_size=[16, 8], seed=5, device="cuda")
+    coll = model.embeddings
+    with torch.no_grad():
+        coll.lin_view().normal_(0, 0.1)
+    tr = DeepFMTrainStep(model, batch_size=B, lr=lr, use_graph=use_graph, optimizer="adam_rows_tf")
+    if use_graph:
+        tr.capture()
+    tables = [coll.table(s).detach().cpu().numpy().astype(np.float64) for s in range(S)]
+    lins = [coll.linear_of(s).detach().cpu().numpy().astype(np.float64) for s in range(S)]
+    bias = float(coll.bias.detach())
+    ws = [w.detach().cpu().numpy().astype(np.float64) for w in tr.w]
+    bs = [b.detach().cpu().numpy().astype(np.float64) for b in tr.b]
+    state = lambda xs: ([np.zeros_like(x) for x in xs], [np.zeros_like(x) for x in xs])
+    (mt, vt), (ml, vl), (mw, vw), (mb, vb) = state(tables), state(lins), state(ws), state(bs)
+    lazy_t = [t.copy() for t in tables]                       # what the LAZY semantics would give (must differ: see below)
+    lazy_m, lazy_v = [np.zeros_like(t) for t in tables], [np.zeros_like(t) for t in tables]
+    mbias = vbias = np.zeros(1)
+    rng = np.random.default_rng(23)
+    for t in range(1, 9):
+        ids = np.stack([rng.integers(-1, r + 1, size=B) for r in rows], axis=1).astype(np.int64)
+        ids[:4] = [5, 3, 7]                                   # duplicates; row 5 / 7 of the big tables touched EVERY step
+        if t in (1, 6):
+            ids[4:8] = [11, 1, 13]                            # rows 11 / 13: touched at steps 1 and 6 only (gap of 4 steps)
+        labels = rng.integers(0, 2, size=B).astype(np.float32)
+        tr.step(torch.from_numpy(ids).cuda(), torch.from_numpy(labels).cuda())
+        loss, gt, gl, gb, gw, gbi = _cpu_deepfm_grads(tables, lins, bias, ws, bs, ids, labels)
+        lr_t = R.adam_lr_t(lr, t)
+        for s in range(S):
+            lazy_t[s], lazy_m[s], lazy_v[s] = R.adam_rows_lazy(lazy_t[s], gt[s], lazy_m[s], lazy_v[s], ids[:, s], lr_t, dtype=np.float64)
+            tables[s], mt[s], vt[s] = R.adam_dense(tables[s], gt[s], mt[s], vt[s], lr_t, dtype=np.float64)   # TF: dense
+            lins[s], ml[s], vl[s] = R.adam_dense(lins[s], gl[s], ml[s], vl[s], lr_t, dtype=np.float64)
+        b_, mbias, vbias = R.adam_dense(np.array([bias]), gb, mbias, vbias, lr_t, dtype=np.float64)
+        bias = float(b_[0])
+        for i in range(len(ws)):
+            ws[i], mw[i], vw[i] = R.adam_dense(ws[i], gw[i], mw[i], vw[i], lr_t, dtype=np.float64)
+            bs[i], mb[i], vb[i] = R.adam_dense(bs[i], gbi[i], mb[i], vb[i], lr_t, dtype=np.float64)
+    tr.flush_optimizer()                                      # rows not touched by the last steps catch up here
+    torch.cuda.synchronize()
+    got_tables = np.concatenate([coll.table(s).detach().cpu().numpy() for s in range(S)], 0)
+    got_lins = np.concatenate([coll.linear_of(s).detach().cpu().numpy() for s in range(S)], 0)
+    ref_tables, ref_lazy = np.concatenate(tables, 0), np.concatenate(lazy_t, 0)
+    # the test discriminates: under lazy semantics the tables would be off by many times the tolerance
+    assert np.abs(ref_lazy - ref_tables).max() > 1.0 * lr
+    assert np.abs(got_tables - ref_tables).max() <= 3e-2 * lr, np.abs(got_tables - ref_tables).max() / lr
+    assert np.abs(got_lins - np.concatenate(lins, 0)).max() <= 3e-2 * lr
+    # moments too (linear in the gradients: tight), read from the per-row state blocks after the flush
+    st = tr.state.cpu().numpy()
+    ref_m = np.concatenate(mt, 0)
+    assert np.abs(st[:, D:2 * D] - ref_m).max() <= 1e-4 * np.abs(ref_m).max() + 1e-9
+    ref_v = np.concatenate(vt, 0)
+    assert np.abs(st[:, 2 * D:3 * D] - ref_v).max() <= 1e-4 * np.abs(ref_v).max() + 1e-12
+    assert (st[:, 3 * D + 4].view(np.int32)[np.abs(ref_m).sum(1) > 0] == 8).all()      # every updated row is stamped with the last step
