@@ -70,6 +70,7 @@ _SIGS = {
     "dr_adam_advance_hist": [_p, _f, _f, _f, _p, _p, _i, _p],
     "dr_embed_fm_bwd_adam_tf": [_p, _i, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i64, _i64, _i, _p, _p, _p, _p, _p, _p, _p,
                                 _i, _f, _f, _f, _f, _p],
+    "dr_embed_adam_prepare": [_p, _i, _i64, _i, _i, _p, _p, _i64, _i64, _i, _p, _p, _p, _p, _p, _i, _f, _f, _f, _f, _p],
     "dr_embed_adam_flush": [_p, _p, _i, _i, _i64, _i64, _i64, _i, _p, _p, _p, _p, _p, _i, _f, _f, _f, _f, _p],
     "dr_hash_bucket_i64": [_p, _i64, _i64, _p, _p],
     "dr_hash_bucket_bytes": [_p, _p, _i64, _i64, _p, _p],

@@ -97,6 +97,69 @@ __global__ void __launch_bounds__(256) embed_adam_count_kernel(const IdT* __rest
   }
 }
 
+
+// EXACT, before the forward: count the batch's lookups per row (as embed_adam_count_kernel) AND bring every row the batch
+// touches up to date with step t-1, so that the forward reads what tf.keras Adam's dense update would have left there.
+// One lane group per lookup; the lookup that raises a row's count from 0 is the row's first arriver and replays the
+// row's pending steps (stamp, t-1]; the others only count.
+template <int LPR, typename IdT>
+__global__ void __launch_bounds__(256) embed_adam_prepare_kernel(const IdT* __restrict__ ids, int64_t n_lookups, int S, int D,
+                                                                  const int64_t* __restrict__ rows,
+                                                                  const int64_t* __restrict__ slot_offsets,
+                                                                  float* const* __restrict__ table_ptrs,
+                                                                  float* const* __restrict__ lin_ptrs, int64_t row_stride,
+                                                                  int64_t lin_stride, int lin_in_row,
+                                                                  float* __restrict__ state, int SS,
+                                                                  const int64_t* __restrict__ step_dev, AdamHist hist,
+                                                                  float omb1, float omb2, float eps) {
+  constexpr int G = 32 / LPR;
+  const int lane = threadIdx.x & 31, c = lane % LPR, grp = lane / LPR;
+  const int64_t t_now = *step_dev;
+  const int o_m = D, o_v = 2 * D, o_s = 3 * D;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t base = warp * G; base < n_lookups; base += nwarps * G) {
+    const int64_t L = base + grp;
+    int64_t id = -1;
+    int s = 0;
+    if (L < n_lookups) {
+      s = (int)(L % S);
+      id = (int64_t)__ldg(ids + L);
+      if ((uint64_t)id >= (uint64_t)__ldg(rows + s)) id = -1;
+    }
+    float* st = id >= 0 ? state + (size_t)(__ldg(slot_offsets + s) + id) * SS : nullptr;
+    int first = 0, stamp_i = 0;
+    if (id >= 0 && c == 0) {
+      first = atomicAdd(reinterpret_cast<int*>(st + o_s + 3), 1) == 0;
+      if (first) stamp_i = __float_as_int(ld_cg1(st + o_s + 4));
+    }
+    first = __shfl_sync(0xffffffffu, first, grp * LPR);
+    stamp_i = __shfl_sync(0xffffffffu, stamp_i, grp * LPR);
+    const int64_t stamp = stamp_i;
+    if (first && stamp > 0 && stamp < t_now - 1) {
+      float* prow = table_ptrs[s] + (size_t)id * row_stride;
+      if (c * 4 < D) {
+        float4 m = ld_cg4(st + o_m + c * 4), v = ld_cg4(st + o_v + c * 4);
+        float4 w = *reinterpret_cast<const float4*>(prow + c * 4);
+        float pa[4] = {w.x, w.y, w.z, w.w}, ma[4] = {m.x, m.y, m.z, m.w}, va[4] = {v.x, v.y, v.z, v.w};
+        adam_catch_up<4>(pa, ma, va, stamp, t_now - 1, t_now, hist, omb1, omb2, eps);
+        *reinterpret_cast<float4*>(prow + c * 4) = make_float4(pa[0], pa[1], pa[2], pa[3]);
+        stg4(st + o_m + c * 4, make_float4(ma[0], ma[1], ma[2], ma[3]));
+        stg4(st + o_v + c * 4, make_float4(va[0], va[1], va[2], va[3]));
+      }
+      if (c == 0) {
+        if (lin_in_row || lin_ptrs) {
+          float* wp = lin_in_row ? prow + D : lin_ptrs[s] + (size_t)id * lin_stride;
+          float pa[1] = {*wp}, ma[1] = {ld_cg1(st + o_s + 1)}, va[1] = {ld_cg1(st + o_s + 2)};
+          adam_catch_up<1>(pa, ma, va, stamp, t_now - 1, t_now, hist, omb1, omb2, eps);
+          *wp = pa[0]; st[o_s + 1] = ma[0]; st[o_s + 2] = va[0];
+        }
+        st[o_s + 4] = __int_as_float((int)(t_now - 1));
+      }
+    }
+  }
+}
+
 struct AdamBwdParams {
   const void* ids;
   const int64_t* rows;
@@ -433,6 +496,46 @@ extern "C" int dr_adam_advance_hist(int64_t* step_dev, float lr, float beta1, fl
              "dr_adam_advance_hist: beta1=%g beta2=%g hist_len=%d out of range", (double)beta1, (double)beta2, hist_len);
   adam_advance_hist_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev, lr, beta1, beta2, lr_t_dev, lr_hist, hist_len);
   DR_CUDA_LAUNCH_CHECK("dr_adam_advance_hist");
+  return DR_OK;
+}
+
+
+extern "C" int dr_embed_adam_prepare(const void* ids, int id_bytes, int64_t B, int S, int D, const int64_t* rows,
+                                     const int64_t* slot_offsets, int64_t row_stride, int64_t lin_stride, int flags,
+                                     float* const* table_ptrs, float* const* lin_ptrs, float* state,
+                                     const int64_t* step_dev, const float* lr_hist, int hist_len, float lr, float beta1,
+                                     float beta2, float eps, void* stream) {
+  DR_REQUIRE(B >= 0 && S >= 1 && S <= 4096, DR_EINVAL, "dr_embed_adam_prepare: B=%lld S=%d", (long long)B, S);
+  DR_REQUIRE(D >= 4 && D <= 128 && D % 4 == 0, DR_EINVAL, "dr_embed_adam_prepare: D=%d unsupported", D);
+  DR_REQUIRE(id_bytes == 8 || id_bytes == 4, DR_EINVAL, "dr_embed_adam_prepare: id_bytes=%d (need 4 or 8)", id_bytes);
+  if (B == 0) return DR_OK;
+  DR_REQUIRE(ids && rows && slot_offsets && table_ptrs && state && step_dev, DR_EINVAL, "dr_embed_adam_prepare: null pointer");
+  if (row_stride == 0) row_stride = D;
+  if (lin_stride == 0) lin_stride = 1;
+  const int lin_in_row = (flags & DR_EMBED_LIN_IN_ROW) ? 1 : 0;
+  const AdamHist h{lr_hist, hist_len, lr, beta1, beta2};
+  const int lpr = lpr_of(D);
+  const int64_t n = B * S;
+  int64_t ctas = (n * lpr + 255) / 256;
+  if (ctas > (int64_t)kNumSMs * 16) ctas = (int64_t)kNumSMs * 16;
+  cudaStream_t st = (cudaStream_t)stream;
+#define DR_PREP2(L, IdT)                                                                                               \
+  embed_adam_prepare_kernel<L, IdT><<<(unsigned)ctas, 256, 0, st>>>((const IdT*)ids, n, S, D, rows, slot_offsets, table_ptrs, \
+                                                                  lin_in_row ? nullptr : lin_ptrs, row_stride, lin_stride, \
+                                                                  lin_in_row, state, adam_state_stride(D), step_dev, h,  \
+                                                                  1.f - beta1, 1.f - beta2, eps)
+#define DR_PREP(L) do { if (id_bytes == 8) DR_PREP2(L, int64_t); else DR_PREP2(L, int32_t); } while (0)
+  switch (lpr) {
+    case 1: DR_PREP(1); break;
+    case 2: DR_PREP(2); break;
+    case 4: DR_PREP(4); break;
+    case 8: DR_PREP(8); break;
+    case 16: DR_PREP(16); break;
+    default: DR_PREP(32); break;
+  }
+#undef DR_PREP
+#undef DR_PREP2
+  DR_CUDA_LAUNCH_CHECK("dr_embed_adam_prepare");
   return DR_OK;
 }
 

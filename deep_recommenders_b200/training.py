@@ -146,12 +146,22 @@ class DeepFMTrainStep:
         if self.optimizer != "sgd":
             self.clock.advance()                                  # t += 1, lr_t (device scalars)
         mark("start")
+        if self.optimizer == "adam_rows_tf":
+            # tf.keras Adam is dense: rows move in the steps that do not touch them.  Before the forward reads them, the
+            # rows of THIS batch replay their pending steps (and the batch's per-row lookup counts are taken)
+            ck = self.clock
+            check(lib.dr_embed_adam_prepare(self.ids.data_ptr(), self.ids.element_size(), B, S, D, self.rows.data_ptr(),
+                                            c._offsets.data_ptr(), c.row_stride, c.lin_stride, c.flags, self.tp.data_ptr(),
+                                            self.lp.data_ptr(), self.state.data_ptr(), ck.step.data_ptr(),
+                                            ck.lr_hist.data_ptr(), ck.lr_hist.numel(), ck.lr, ck.beta1, ck.beta2, ck.eps, st),
+                  "dr_embed_adam_prepare")
+            mark("adam_prepare")
         check(lib.dr_embed_fm_fwd(self.tp.data_ptr(), self.lp.data_ptr(), self.rows.data_ptr(), self.ids.data_ptr(),
                                   self.ids.element_size(), c.bias.data_ptr(), B, S, D, c.row_stride, c.lin_stride,
                                   c.flags, self.stack.data_ptr(),
                                   self.sum_e.data_ptr(), self.fm_logit.data_ptr(), st), "dr_embed_fm_fwd")
         mark("embed_fm_fwd")
-        if self.optimizer in ("adam_rows", "adam_rows_tf"):     # per-row lookup counts of this batch: on the side stream, behind the GEMMs
+        if self.optimizer == "adam_rows":     # per-row lookup counts of this batch: on the side stream, behind the GEMMs
             self._side_stream.wait_stream(torch.cuda.current_stream())   # (not behind the gather: both are DRAM-bound)
             with torch.cuda.stream(self._side_stream):
                 check(lib.dr_embed_adam_count(self.ids.data_ptr(), self.ids.element_size(), B, S, D, self.rows.data_ptr(),

@@ -339,13 +339,22 @@ int dr_embed_fm_bwd_adam(const void* ids, int id_bytes, const int64_t* rows, con
 /* The same fused row-sparse Adam made EQUAL to tf.keras.optimizers.Adam (which is dense: in a step that does not touch
  * a row, its m and v still decay and the row still moves by its decayed momentum).  Each state block also holds the
  * step stamp of the row's last update (float index 3 D + 4); when a row is touched again the kernel first replays the
- * steps it sat out -- m -= m(1-b1), v -= v(1-b2), p -= lr_j m / (sqrt(v) + eps) for j = stamp+1 .. t-1, lr_j from the
+ * steps it sat out (dr_embed_adam_prepare, before the forward, so the forward already sees the moved row)
+ * -- m -= m(1-b1), v -= v(1-b2), p -= lr_j m / (sqrt(v) + eps) for j = stamp+1 .. t-1, lr_j from the
  * ring `lr_hist` [hist_len] that dr_adam_advance_hist fills (recomputed from lr, beta1, beta2 for steps that fell out of
  * the ring) -- and then applies step t with the batch's gradient.  dr_embed_adam_flush replays the pending steps of
  * EVERY row up to the current step: call it before the tables are read outside the trainer (evaluation, checkpoint).
  * With it, parameters equal those of dr_adam_step applied densely every step (tests: float64 ApplyAdam oracle). */
 int dr_adam_advance_hist(int64_t* step_dev, float lr, float beta1, float beta2, float* lr_t_dev,
                          float* lr_hist, int hist_len, void* stream);
+/* Per step, BEFORE the forward of the batch (it replaces dr_embed_adam_count): counts the batch's lookups per row and
+ * replays the pending steps (stamp, t-1] of every row the batch touches, so that the forward reads the parameters
+ * tf.keras Adam's dense update would have left there. */
+int dr_embed_adam_prepare(const void* ids, int id_bytes, int64_t B, int S, int D, const int64_t* rows,
+                          const int64_t* slot_offsets, int64_t row_stride, int64_t lin_stride, int flags,
+                          float* const* table_ptrs, float* const* lin_ptrs, float* state,
+                          const int64_t* step_dev, const float* lr_hist, int hist_len, float lr, float beta1,
+                          float beta2, float eps, void* stream);
 int dr_embed_fm_bwd_adam_tf(const void* ids, int id_bytes, const int64_t* rows, const int64_t* slot_offsets,
                             const float* stack, const float* sum_e, const float* g_logit, const float* g_stack,
                             int64_t B, int S, int D, int64_t row_stride, int64_t lin_stride, int flags,
