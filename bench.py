@@ -152,6 +152,8 @@ def main():
     ap.add_argument("--optimizer", default="sgd", choices=["sgd", "adam", "lazy_adam", "adam_rows", "adam_rows_tf"],
                     help="N=1: sgd (default, fused row-sparse SGD), adam (TF-exact dense ApplyAdam over the arena), lazy_adam "
                          "(row-sparse, two kernels), adam_rows (row-sparse Adam fused into the backward scatter)")
+    ap.add_argument("--embed-fwd", default="ldg", choices=["ldg", "tma"],
+                    help="N=1: forward gather through register loads (default) or staged through TMA tile::gather4 (opt-in, measured slower)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: fused NVLink peer-memory gather/update (p2p) or NCCL all-to-all pipeline (nccl)")
     args = ap.parse_args()
@@ -213,7 +215,7 @@ def main():
             model = DeepFM([fc.indicator_column(c) for c in cols], [fc.embedding_column(c, D) for c in cols],
                            dnn_units_size=W["dnn"], seed=1, device=dev, sparse_lr=0.01)
             return DeepFMTrainStep(model, batch_size=B, lr=0.01, use_graph=not args.no_graph,
-                                   optimizer=args.optimizer).capture()
+                                   optimizer=args.optimizer, embed_fwd=args.embed_fwd).capture()
         try:
             trainer = build_single()
         except Exception as e:      # the newest GEMM core failing to launch must not cost the measurement: say so, use tc
@@ -346,7 +348,7 @@ def main():
             "gemm_core": {0: "ffma", 1: "tcgen05 3xTF32, pre-split planes (tc)",
                           2: "tcgen05 3xTF32, hi/lo split in kernel (tc2)"}[_lib._tc_variant if _lib._tc_enabled and not gemm_note else (1 if gemm_note else 0)],
             "exchange": getattr(trainer, "exchange", None) if world > 1 else None,
-            "optimizer": args.optimizer if world == 1 else "sgd"}
+            "optimizer": args.optimizer if world == 1 else "sgd", "embed_fwd": args.embed_fwd if world == 1 else "ldg"}
     if world > 1 and exchange_note:
         line["exchange_note"] = exchange_note
     if gemm_note:

@@ -34,6 +34,7 @@ _SIGS = {
     "dr_gemm_prof_read": [_p, _i],
     "dr_debug_gemm": [_p, _p, _p, _i64, _i64, _i64, _i, _i, _p],
     "dr_embed_fm_fwd": [_p, _p, _p, _p, _i, _p, _i64, _i, _i, _i64, _i64, _i, _p, _p, _p, _p],
+    "dr_embed_fm_fwd_tma": [_p, _i64, _p, _p, _p, _i, _p, _i64, _i, _i, _i64, _p, _p, _p, _p],
     "dr_embed_fm_bwd": [_p, _i, _p, _p, _p, _p, _p, _i64, _i, _i, _i64, _i64, _i, _p, _p, _p, _f, _p],
     "dr_embed_fm_fwd_sharded": [_p, _i, _p, _p, _p, _i, _p, _i64, _i, _i, _i64, _i, _i64, _p, _p, _p, _p],
     "dr_embed_fm_bwd_sharded": [_p, _i, _p, _p, _p, _i, _p, _p, _p, _p, _i64, _i, _i, _i64, _i, _i64, _p, _f, _p],

@@ -35,11 +35,15 @@ from ._lib import check
 
 class DeepFMTrainStep:
     def __init__(self, model, batch_size: int, lr: float = 0.01, id_dtype=torch.int64, use_graph: bool = True,
-                 optimizer: str = "sgd", beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-7):
+                 optimizer: str = "sgd", beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-7,
+                 embed_fwd: str = "ldg"):
         self.lib = _lib.load()
         if optimizer not in ("sgd", "adam", "lazy_adam", "adam_rows", "adam_rows_tf"):
             raise ValueError(f"optimizer must be 'sgd', 'adam', 'lazy_adam', 'adam_rows' or 'adam_rows_tf', got {optimizer!r}")
         self.optimizer = optimizer
+        if embed_fwd not in ("ldg", "tma"):
+            raise ValueError(f"embed_fwd must be 'ldg' (register loads, default) or 'tma' (gather4 staging), got {embed_fwd!r}")
+        self.embed_fwd = embed_fwd
         self.model = model
         coll = model.embeddings
         self.coll = coll
@@ -156,10 +160,16 @@ class DeepFMTrainStep:
                                             ck.lr_hist.data_ptr(), ck.lr_hist.numel(), ck.lr, ck.beta1, ck.beta2, ck.eps, st),
                   "dr_embed_adam_prepare")
             mark("adam_prepare")
-        check(lib.dr_embed_fm_fwd(self.tp.data_ptr(), self.lp.data_ptr(), self.rows.data_ptr(), self.ids.data_ptr(),
-                                  self.ids.element_size(), c.bias.data_ptr(), B, S, D, c.row_stride, c.lin_stride,
-                                  c.flags, self.stack.data_ptr(),
-                                  self.sum_e.data_ptr(), self.fm_logit.data_ptr(), st), "dr_embed_fm_fwd")
+        if self.embed_fwd == "tma":      # opt-in: rows staged through TMA (tile::gather4) into shared memory
+            check(lib.dr_embed_fm_fwd_tma(c.weight.data_ptr(), c.total_rows, c._offsets.data_ptr(), self.rows.data_ptr(),
+                                          self.ids.data_ptr(), self.ids.element_size(), c.bias.data_ptr(), B, S, D,
+                                          c.row_stride, self.stack.data_ptr(), self.sum_e.data_ptr(),
+                                          self.fm_logit.data_ptr(), st), "dr_embed_fm_fwd_tma")
+        else:
+            check(lib.dr_embed_fm_fwd(self.tp.data_ptr(), self.lp.data_ptr(), self.rows.data_ptr(), self.ids.data_ptr(),
+                                      self.ids.element_size(), c.bias.data_ptr(), B, S, D, c.row_stride, c.lin_stride,
+                                      c.flags, self.stack.data_ptr(),
+                                      self.sum_e.data_ptr(), self.fm_logit.data_ptr(), st), "dr_embed_fm_fwd")
         mark("embed_fm_fwd")
         if self.optimizer == "adam_rows":     # per-row lookup counts of this batch: on the side stream, behind the GEMMs
             self._side_stream.wait_stream(torch.cuda.current_stream())   # (not behind the gather: both are DRAM-bound)

@@ -97,6 +97,18 @@ int dr_embed_fm_bwd(const void* ids, int id_bytes, const int64_t* rows,
                     float* const* grad_table_ptrs, float* const* grad_lin_ptrs, float* g_bias,
                     float scale, void* stream);
 
+/* Opt-in variant of dr_embed_fm_fwd that stages the rows THROUGH TMA INTO SHARED MEMORY
+ * (cp.async.bulk.tensor ... tile::gather4, four rows per instruction, mbarrier completion; the stacked rows leave as one
+ * cp.async.bulk store per tile).  Same outputs as dr_embed_fm_fwd (stack bit-exact; logit / sum_e up to summation order).
+ * Serves the fused row layout only: all tables in ONE arena `arena` [total_rows, row_stride] with the first-order weight
+ * at float D of the row (DR_EMBED_LIN_IN_ROW), D = 16, S <= 32; slot_offsets[s] = first arena row of table s.
+ * Returns DR_ENOTSUP otherwise.  Measured slower than the register-load kernel for uniform and for Zipf ids on B200
+ * (DESIGN.md section 4): shipped as the measured alternative, not as the default. */
+int dr_embed_fm_fwd_tma(const float* arena, int64_t total_rows, const int64_t* slot_offsets,
+                        const int64_t* rows, const void* ids, int id_bytes, const float* bias, int64_t B, int S,
+                        int D, int64_t row_stride, float* out_stack, float* out_sum, float* out_logit,
+                        void* stream);
+
 /* Plain single-table gather / scatter-add (two-tower user & item towers).
  *   replaces: tf.keras.layers.DenseFeatures(embedding_column) on one column
  *             (keras/models/ranking/fm.py:47-51).  D % 4 == 0, 4 <= D <= 128.      */

@@ -263,3 +263,39 @@ def test_full_size_c2_properties():
                                            B, S, D, coll.row_stride, coll.lin_stride, 0, tp.data_ptr(), None, None, 1.0,
                                            torch.cuda.current_stream().cuda_stream), "bwd")
     assert float(gw.sum()) == float(B * S * D)
+
+
+@pytest.mark.parametrize("B,rows", [(1, [7]), (5, [11, 3]), (64, [100] * 6), (257, [50, 60, 70, 2, 7, 21]), (1000, [1000] * 26),
+                                    (123, [40] * 32)])
+@pytest.mark.parametrize("id_dtype", [np.int64, np.int32])
+def test_forward_tma_staged_variant_matches(B, rows, id_dtype):
+    """dr_embed_fm_fwd_tma (rows staged through TMA tile::gather4 into shared memory, opt-in): same stack bit for bit,
+    same logit / sum_e within the oracle tolerance, OOV ids -> zero rows via the TMA out-of-bounds fill."""
+    from deep_recommenders_b200 import _lib
+    lib = _lib.load()
+    D = 16
+    tables, lins, bias, ids = make_problem(B, rows, D, seed=B + len(rows), oov_frac=0.1, id_dtype=id_dtype)
+    coll = to_collection(tables, lins, bias, layout="fused")
+    idt = torch.from_numpy(ids).cuda()
+    S = len(rows)
+    stack = torch.full((B, S, D), float("nan"), device="cuda")
+    sum_e = torch.full((B, D), float("nan"), device="cuda")
+    logit = torch.full((B,), float("nan"), device="cuda")
+    _lib.check(lib.dr_embed_fm_fwd_tma(coll.weight.data_ptr(), coll.total_rows, coll._offsets.data_ptr(), coll._rows.data_ptr(),
+                                       idt.data_ptr(), idt.element_size(), coll.bias.data_ptr(), B, S, D, coll.row_stride,
+                                       stack.data_ptr(), sum_e.data_ptr(), logit.data_ptr(),
+                                       torch.cuda.current_stream().cuda_stream), "dr_embed_fm_fwd_tma")
+    torch.cuda.synchronize()
+    ref_stack = R.stack_embeddings(tables, ids)
+    assert np.array_equal(stack.cpu().numpy().view(np.uint32), ref_stack.view(np.uint32))
+    ref_logit, _ = R.fm_logit(tables, lins, bias, ids, np.float64)
+    err = np.abs(logit.cpu().numpy().astype(np.float64) - ref_logit.reshape(-1))
+    tol = 1e-5 * logit_scale(tables, lins, bias, ids) + 1e-6
+    assert (err <= tol).all(), f"max err {err.max()}"
+    ssum = ref_stack.astype(np.float64).sum(1)
+    assert (np.abs(sum_e.cpu().numpy() - ssum) <= 1e-5 * np.abs(ref_stack.astype(np.float64)).sum(1) + 1e-7).all()
+    # unsupported shapes are refused, not mis-served
+    rc = lib.dr_embed_fm_fwd_tma(coll.weight.data_ptr(), coll.total_rows, coll._offsets.data_ptr(), coll._rows.data_ptr(),
+                                 idt.data_ptr(), idt.element_size(), coll.bias.data_ptr(), B, S, 32, coll.row_stride,
+                                 stack.data_ptr(), sum_e.data_ptr(), logit.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert rc < 0
