@@ -25,6 +25,7 @@ extern int g_tune_gemm_variant, g_tune_gemm_splitk, g_tune_gemm_bn, g_tune_tc_mn
 
 }  // namespace dr
 
+namespace dr { int gemm_set_store_hi(int v); }
 extern "C" int dr_version(void) { return 100; /* 0.1.0 */ }
 extern "C" const char* dr_last_error(void) { return dr::g_err; }
 extern "C" uint64_t dr_launch_count(void) { return dr::g_launches.load(std::memory_order_relaxed); }
@@ -54,6 +55,7 @@ extern "C" int dr_tune_set(const char* key, int value) {
   else if (!strcmp(key, "tc_tma_out")) g_tune_tc_tma_out = value;
   else if (!strcmp(key, "tc_stages")) g_tune_tc_stages = value;
   else if (!strcmp(key, "tc_l2_promo")) g_tune_tc_l2_promo = value;
+  else if (!strcmp(key, "tc_store_hi")) return gemm_set_store_hi(value);
   else if (!strcmp(key, "tc_dw_stages")) g_tune_tc_dw_stages = value;
   else if (!strcmp(key, "l2_fetch_granularity")) {
     // device-wide hint: how many bytes L2 fetches from HBM around a missing 32-B sector (32/64/128)
