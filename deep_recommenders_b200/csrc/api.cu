@@ -20,7 +20,7 @@ void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_r
 extern int g_tune_embed_fwd_unroll, g_tune_embed_bwd_unroll, g_tune_embed_block, g_tune_embed_ctas_per_sm,
     g_tune_embed_bwd_agg, g_tune_embed_bwd_mode, g_tune_embed_fwd_minblocks, g_tune_embed_fwd_linx, g_tune_embed_fwd_linx_shard, g_tune_embed_bwd_linx, g_tune_embed_l2_hints;
 extern int g_tune_topk_variant;
-extern int g_tune_gemm_prof, g_tune_tc_tma_out, g_tune_tc_stages, g_tune_tc_l2_promo, g_tune_tc_dw_stages;
+extern int g_tune_gemm_prof, g_tune_tc_tma_out, g_tune_tc_stages, g_tune_tc_l2_promo, g_tune_tc_dw_stages, g_tune_tc_dw_share;
 extern int g_tune_gemm_variant, g_tune_gemm_splitk, g_tune_gemm_bn, g_tune_tc_mn, g_tune_tc_min_n;
 
 }  // namespace dr
@@ -57,6 +57,7 @@ extern "C" int dr_tune_set(const char* key, int value) {
   else if (!strcmp(key, "tc_l2_promo")) g_tune_tc_l2_promo = value;
   else if (!strcmp(key, "tc_store_hi")) return gemm_set_store_hi(value);
   else if (!strcmp(key, "tc_dw_stages")) g_tune_tc_dw_stages = value;
+  else if (!strcmp(key, "tc_dw_share")) g_tune_tc_dw_share = value;
   else if (!strcmp(key, "l2_fetch_granularity")) {
     // device-wide hint: how many bytes L2 fetches from HBM around a missing 32-B sector (32/64/128)
     cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value);

@@ -76,6 +76,7 @@ __global__ void __launch_bounds__(256) cross_bwd_prologue_kernel(const float* __
 }
 
 int g_tune_tc_dw_stages = 0;   // 2: weight-gradient GEMMs use the two-stage ring (co-residency with the embedding update)
+int g_tune_tc_dw_share = 0;    // 1: weight-gradient GEMMs use the co-residency build (capped registers, smaller staging)
 
 static int64_t rows_per_cta_for(int64_t M) {
   int64_t r = (M + (int64_t)kNumSMs * 4 - 1) / ((int64_t)kNumSMs * 4);
@@ -111,6 +112,7 @@ static int gemm_xt_g(const float* X, const float* G, float* gW, int64_t M, int64
   GemmArgs a = mk(X, G, gW, Kw, N, M, Kw, N, N, EPI_ATOMIC);
   a.splitk = splitk_for(Kw, N, M);
   a.stages = g_tune_tc_dw_stages;
+  a.share = g_tune_tc_dw_share;
   return gemm_launch(a, /*transA=*/true, /*transB=*/false, st);
 }
 

@@ -39,6 +39,8 @@ struct GemmArgs {
   int splitk;                // >= 1
   int stages;                // 0 = default operand-ring depth; 2 = two stages (161 KB of shared memory instead of 225 KB, so
                              // an HBM / NVLink-bound kernel on another stream can share the SMs with the persistent GEMM)
+  int share;                 // 1 = co-residency build of the tcgen05 kernel (registers capped, 16 KB less shared memory): the
+                             // HBM / NVLink-bound embedding update on another stream runs on the same SMs (gemm_tc.cu SHARE)
 };
 
 extern int g_tune_gemm_variant;

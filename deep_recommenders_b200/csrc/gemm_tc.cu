@@ -293,8 +293,12 @@ __device__ __forceinline__ TcItem tc_decode(int64_t item, int64_t n_tiles, int64
 
 // Persistent, warp-specialised: the accumulator is double buffered in TMEM (2 x BN columns) so the
 // epilogue of item j overlaps the TMA/MMA main loop of item j+1.
-template <int BN, int STAGES, bool A_MN, bool B_MN, bool INSPLIT = false, bool PROF = false>
-__global__ void __launch_bounds__(INSPLIT ? TC_THREADS_INSPLIT : TC_THREADS, 1)
+// SHARE (per-call GemmArgs::share, weight-gradient GEMMs that run beside the HBM-bound embedding update): the same kernel
+// built to leave room on the SM for a second resident kernel -- registers capped at 96 / thread (30.7 K of the 64 K file
+// instead of 53.8 K) and ONE epilogue staging slab per warp (16 KB less shared memory), so that CTAs of the embedding
+// backward (58 registers, 1 KB of shared memory) run on the same SMs while the GEMM's main loop is shared-memory bound.
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool INSPLIT = false, bool PROF = false, bool SHARE = false>
+__global__ void __launch_bounds__(INSPLIT ? TC_THREADS_INSPLIT : TC_THREADS, SHARE ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                const __grid_constant__ CUtensorMap tmC, const int tma_out,
@@ -453,7 +457,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     // -- or a TMA reduce-add for split-K partial sums -- which also clips the M / N edges.
     const int q = warp & 3;
     const bool vec_ok = ((a.ldc & 3) == 0) && aligned16(a.C);
-    uint8_t* stg = smem + (size_t)STAGES * STAGE + (size_t)q * 8192;
+    uint8_t* stg = smem + (size_t)STAGES * STAGE + (size_t)q * (SHARE ? 4096 : 8192);
     uint32_t j = 0, slab = 0;
     for (int64_t item = blockIdx.x; item < total_items; item += gridDim.x, ++j) {
       const TcItem t = tc_decode(item, n_tiles, m_tiles, kblocks, per, BN);
@@ -470,8 +474,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         const int64_t nb = t.n0 + c * 32;
         if (tma_out) {
           if (mw < a.M && nb < a.N) {            // warp-uniform
-            uint8_t* sb = stg + (slab & 1u) * 4096;
-            if (lane == 0) bulk_wait_group_read<1>();   // the store issued from this buffer two slabs ago has read it
+            uint8_t* sb = SHARE ? stg : stg + (slab & 1u) * 4096;
+            if (lane == 0) {                            // the store issued from this buffer two slabs ago (SHARE: the
+              if (SHARE) bulk_wait_group_read<0>();     // previous one) has read it
+              else bulk_wait_group_read<1>();
+            }
             __syncwarp();
             const bool row_ok = m < a.M;
             float o[32];
@@ -693,14 +700,15 @@ int g_tune_tc_stages = 0;    // 0 = default ring depth per tile width; 2 = two s
 int g_tune_tc_tma_out = 1;   // 1 (default) = epilogue through shared memory + TMA store / reduce-add; 0 = round-1 register stores
 int g_tune_gemm_prof = 0;   // 1 = launch the instrumented instantiation (BN = 128 INSPLIT only); read with dr_gemm_prof_read
 
-template <int BN, int STAGES, bool A_MN, bool B_MN, bool INSPLIT = false>
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool INSPLIT = false, bool SHARE = false>
 static int launch_tc(const CUtensorMap* tms, const GemmArgs& a, cudaStream_t st) {
   constexpr int STAGE = 2 * TC_BM * TC_BK * 4 + 2 * BN * TC_BK * 4;
-  constexpr size_t smem = (size_t)STAGES * STAGE + TC_EPI_STAGING + 1024;
+  constexpr size_t smem = (size_t)STAGES * STAGE + (SHARE ? TC_EPI_STAGING / 2 : TC_EPI_STAGING) + 1024;
   static_assert(smem <= 232448, "operand ring + epilogue staging exceed the 227 KB of shared memory per CTA");
   constexpr bool kProfInst = INSPLIT && BN == 128;
-  auto k = (kProfInst && g_tune_gemm_prof) ? gemm_tc_kernel<BN, STAGES, A_MN, B_MN, INSPLIT, kProfInst>
-                                           : gemm_tc_kernel<BN, STAGES, A_MN, B_MN, INSPLIT, false>;
+  auto k = SHARE ? gemm_tc_kernel<BN, STAGES, A_MN, B_MN, INSPLIT, false, SHARE>
+           : (kProfInst && g_tune_gemm_prof) ? gemm_tc_kernel<BN, STAGES, A_MN, B_MN, INSPLIT, kProfInst>
+                                             : gemm_tc_kernel<BN, STAGES, A_MN, B_MN, INSPLIT, false>;
   DR_CUDA_CALL(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // output through TMA (store / reduce-add) whenever C is 16-B aligned with a 16-B multiple pitch
   CUtensorMap tmC;
@@ -764,7 +772,7 @@ int gemm_tc_launch(const GemmArgs& a0, bool ta, bool tb, cudaStream_t st) {
     const int64_t pad256 = (a.N + 255) / 256 * 256, pad128 = (a.N + 127) / 128 * 128;
     const int64_t tiles256 = ((a.M + TC_BM - 1) / TC_BM) * (pad256 / 256) * (a.splitk > 0 ? a.splitk : 1);
     const bool two_stage = g_tune_tc_stages == 2 || a.stages == 2;      // forces the 128-wide tile
-    const bool wide = !two_stage && a.N >= 256 && (g_tune_gemm_bn == 256 ||
+    const bool wide = !two_stage && !a.share && a.N >= 256 && (g_tune_gemm_bn == 256 ||
                                      (g_tune_gemm_bn == 0 && pad256 <= pad128 && tiles256 >= 2 * kNumSMs));   // enough tiles to fill the SMs
     const int bn = a.N <= 32 ? 32 : (a.N <= 64 ? 64 : (wide ? 256 : 128));
     if (!B_MN) {
@@ -784,6 +792,8 @@ int gemm_tc_launch(const GemmArgs& a0, bool ta, bool tb, cudaStream_t st) {
     if (bn == 32) DR_TC2_LAUNCH(32, 4);
     if (bn == 64) DR_TC2_LAUNCH(64, 4);
     if (two_stage) DR_TC2_LAUNCH(128, 2);
+    // co-residency build (GemmArgs::share): only the operand layout of the weight-gradient GEMM (X^T and gZ as stored)
+    if (a.share && bn == 128 && A_MN && B_MN) return launch_tc<128, 3, true, true, true, true>(tm2, a, st);
     if (bn == 256) DR_TC2_LAUNCH(256, 2);
     DR_TC2_LAUNCH(128, 3);
 #undef DR_TC2_LAUNCH

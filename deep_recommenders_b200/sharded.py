@@ -86,7 +86,8 @@ class ShardedEmbedding:
 
 class ShardedDeepFMTrainStep:
     def __init__(self, columns, dim: int, dnn_units: Sequence[int], batch_size: int, lr: float = 0.01,
-                 seed: int = 0, device=None, group=None, use_graph: bool = True, exchange: str = "p2p"):
+                 seed: int = 0, device=None, group=None, use_graph: bool = True, exchange: str = "p2p",
+                 dw_first: bool = False):
         if not dist.is_initialized():
             raise RuntimeError("ShardedDeepFMTrainStep needs an initialised torch.distributed process group")
         self.lib = _lib.load()
@@ -102,6 +103,7 @@ class ShardedDeepFMTrainStep:
         if exchange not in ("p2p", "nccl"):
             raise ValueError(f"exchange must be 'p2p' or 'nccl', got {exchange!r}")
         self.exchange = exchange
+        self.dw_first = bool(dw_first)
         self.emb = ShardedEmbedding(rows, dim, self.rank, self.world, dev, seed, exchange, group)
         B, S, D, G = self.B, self.S, self.D, self.world
         self.n = B * S
@@ -323,6 +325,12 @@ class ShardedDeepFMTrainStep:
             self.emb.handle.barrier(channel=0)          # all remote atomics of this step have been issued
             mark("barrier")
 
+        if self.dw_first:
+            # the persistent weight-gradient GEMM is submitted BEFORE the remote update (both depend only on the layer-0
+            # input gradient): it takes its one CTA per SM and the update's CTAs fill what is left (knob tc_dw_share)
+            return [(seg_gather, "graph"), (col_reads_done, "eager"), (seg_tower, "graph"), (None, "fork"),
+                    (seg_dw, "graph"), (seg_update, "graph_side_fork"), (col_allreduce, "eager"), (seg_sgd, "graph"),
+                    (None, "join_side"), (col_barrier, "eager")]
         return [(seg_gather, "graph"), (col_reads_done, "eager"), (seg_tower, "graph"), (seg_update, "graph_side"),
                 (seg_dw, "graph"), (col_allreduce, "eager"), (seg_sgd, "graph"), (None, "join_side"),
                 (col_barrier, "eager")]
@@ -426,6 +434,13 @@ class ShardedDeepFMTrainStep:
                 self._side_stream.wait_stream(main)
                 with torch.cuda.stream(self._side_stream):
                     fn()
+            elif kind == "fork":
+                fork = torch.cuda.Event()
+                fork.record(main)
+            elif kind == "graph_side_fork":
+                self._side_stream.wait_event(fork)
+                with torch.cuda.stream(self._side_stream):
+                    fn()
             elif kind == "join_side":
                 main.wait_stream(self._side_stream)
             else:
@@ -469,7 +484,7 @@ class ShardedDeepFMTrainStep:
         if self.use_graph:
             plan = []
             for fn, kind in self._segments(lambda label: None):
-                if kind in ("graph", "graph_side"):
+                if kind in ("graph", "graph_side", "graph_side_fork"):
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g):
                         fn()
@@ -531,6 +546,14 @@ class ShardedDeepFMTrainStep:
         loss = float(self.loss.item())
         self.check_overflow()
         return loss
+
+    def fit_host(self, batches, depth: int = 2):
+        """Pipelined epoch loop over HOST batches (training.fit_host): H2D of the next batch and the D2H read of every
+        step's loss stay off the critical path; the overflow flag of the NCCL exchange is checked once at the end."""
+        from .training import fit_host
+        losses = fit_host(self, batches, depth)
+        self.check_overflow()
+        return losses
 
     def time_embed_fwd(self, ids_pool, iters: int = 30) -> float:
         """Mean duration (ms) of this rank's fused gather+FM forward alone (p2p: (G-1)/G of the rows are

@@ -33,11 +33,65 @@ from . import _lib, ops
 from ._lib import check
 
 
+def fit_host(trainer, batches, depth: int = 2) -> List[float]:
+    """Pipelined end-to-end loop shared by DeepFMTrainStep and ShardedDeepFMTrainStep (`trainer.fit_host(batches)`).
+
+    `batches`: sequence of (ids_host, labels_host) HOST tensors (pinned for asynchronous copies).  Per step, inside this
+    call: the H2D copy of the batch (copy stream, overlapping the previous step's kernels), the D2D swap into the static
+    buffers the CUDA graph reads, the step, and an asynchronous D2H copy of the step's loss into a pinned ring.  The host
+    reads the loss of step k - depth while step k is being enqueued, i.e. it never idles the GPU waiting for a scalar
+    (train_step_host blocks on `loss.item()` every step); returns every step's loss, in order."""
+    batches = list(batches)
+    if not batches:
+        return []
+    cur = torch.cuda.current_stream()
+    ring = getattr(trainer, "_loss_ring", None)
+    if ring is None or ring.numel() < depth + 1:
+        ring = trainer._loss_ring = torch.empty((depth + 1,), dtype=torch.float32).pin_memory()
+    events: List[Optional[torch.cuda.Event]] = [None] * (depth + 1)
+    losses: List[float] = []
+    trainer._copy_stream.wait_stream(cur)        # whatever still reads the spare buffers has been enqueued on `cur`
+    trainer.stage_host(*batches[0])
+    for k, _ in enumerate(batches):
+        cur.wait_event(trainer._staged)
+        trainer.ids.copy_(trainer._spare[0], non_blocking=True)          # D2D swap into the graph's static buffers
+        trainer.labels.copy_(trainer._spare[1], non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(cur)
+        trainer._staged = None
+        if k + 1 < len(batches):
+            trainer._copy_stream.wait_event(done)                        # the spare buffers are free again
+            trainer.stage_host(*batches[k + 1])
+        trainer.run()
+        slot = k % (depth + 1)
+        if events[slot] is not None:                                     # the loss that lived in this slot: step k-depth-1
+            events[slot].synchronize()
+            losses.append(float(ring[slot]))
+        ring[slot:slot + 1].copy_(trainer.loss.reshape(-1)[:1], non_blocking=True)      # D2H read of this step's result
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        events[slot] = ev
+    n = len(batches)
+    for k in range(max(0, n - (depth + 1)), n):                          # drain, in step order
+        slot = k % (depth + 1)
+        events[slot].synchronize()
+        losses.append(float(ring[slot]))
+    return losses
+
+
 class DeepFMTrainStep:
     def __init__(self, model, batch_size: int, lr: float = 0.01, id_dtype=torch.int64, use_graph: bool = True,
                  optimizer: str = "sgd", beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-7,
-                 embed_fwd: str = "ldg"):
+                 embed_fwd: str = "ldg", fwd_chunks: int = 1, dw_first: bool = False):
         self.lib = _lib.load()
+        # fwd_chunks > 1: the gather and the first tower GEMM run as `fwd_chunks` alternating launches over slices of the
+        # batch (gather slice k -> GEMM slice k -> gather slice k+1 ...): a slice's stacked rows are still dirty in L2 when
+        # its GEMM reads them, and their write-back drains behind the (shared-memory-bound) GEMM instead of inside the
+        # DRAM-bound gather.  Same kernels, same results (examples are independent in both).
+        self.fwd_chunks = max(1, int(fwd_chunks))
+        # dw_first: enqueue the layer-0 weight-gradient GEMM BEFORE the embedding update of the side stream (both depend
+        # only on the layer-0 input gradient), so the persistent GEMM owns one CTA slot per SM and the update co-resides
+        self.dw_first = bool(dw_first)
         if optimizer not in ("sgd", "adam", "lazy_adam", "adam_rows", "adam_rows_tf"):
             raise ValueError(f"optimizer must be 'sgd', 'adam', 'lazy_adam', 'adam_rows' or 'adam_rows_tf', got {optimizer!r}")
         self.optimizer = optimizer
@@ -160,17 +214,39 @@ class DeepFMTrainStep:
                                             ck.lr_hist.data_ptr(), ck.lr_hist.numel(), ck.lr, ck.beta1, ck.beta2, ck.eps, st),
                   "dr_embed_adam_prepare")
             mark("adam_prepare")
-        if self.embed_fwd == "tma":      # opt-in: rows staged through TMA (tile::gather4) into shared memory
-            check(lib.dr_embed_fm_fwd_tma(c.weight.data_ptr(), c.total_rows, c._offsets.data_ptr(), self.rows.data_ptr(),
-                                          self.ids.data_ptr(), self.ids.element_size(), c.bias.data_ptr(), B, S, D,
-                                          c.row_stride, self.stack.data_ptr(), self.sum_e.data_ptr(),
-                                          self.fm_logit.data_ptr(), st), "dr_embed_fm_fwd_tma")
+        nch = self.fwd_chunks if self.embed_fwd == "ldg" else 1
+        if nch > 1:
+            # slices on 128-row boundaries (the GEMM's tile height)
+            per = (((B + nch - 1) // nch) + 127) // 128 * 128
+            bounds = [(b0, min(B, b0 + per)) for b0 in range(0, B, per)]
         else:
-            check(lib.dr_embed_fm_fwd(self.tp.data_ptr(), self.lp.data_ptr(), self.rows.data_ptr(), self.ids.data_ptr(),
-                                      self.ids.element_size(), c.bias.data_ptr(), B, S, D, c.row_stride, c.lin_stride,
-                                      c.flags, self.stack.data_ptr(),
-                                      self.sum_e.data_ptr(), self.fm_logit.data_ptr(), st), "dr_embed_fm_fwd")
-        mark("embed_fm_fwd")
+            bounds = [(0, B)]
+        l0 = self.layers[0]
+        L = len(self.layers)
+        # the skinny end (final Dense(1) + BCE + their backward) is ONE kernel when the layer below is <= 256 wide
+        head = (L >= 2 and self.layers[-1].units == 1 and self.layers[-1]._act == 0 and self.layers[-2].units <= 256
+                and self.b[-1] is not None and self.b[-2] is not None)
+        fwd_layers = list(enumerate(self.layers[:L - 1] if head else self.layers))
+        chunk_l0 = len(bounds) > 1 and len(fwd_layers) >= 1
+        esz = self.ids.element_size()
+        for (b0, b1) in bounds:
+            if self.embed_fwd == "tma":      # opt-in: rows staged through TMA (tile::gather4) into shared memory
+                check(lib.dr_embed_fm_fwd_tma(c.weight.data_ptr(), c.total_rows, c._offsets.data_ptr(), self.rows.data_ptr(),
+                                              self.ids.data_ptr(), esz, c.bias.data_ptr(), B, S, D,
+                                              c.row_stride, self.stack.data_ptr(), self.sum_e.data_ptr(),
+                                              self.fm_logit.data_ptr(), st), "dr_embed_fm_fwd_tma")
+            else:
+                check(lib.dr_embed_fm_fwd(self.tp.data_ptr(), self.lp.data_ptr(), self.rows.data_ptr(),
+                                          self.ids.data_ptr() + b0 * S * esz, esz, c.bias.data_ptr(), b1 - b0, S, D,
+                                          c.row_stride, c.lin_stride, c.flags, self.stack.data_ptr() + b0 * S * D * 4,
+                                          self.sum_e.data_ptr() + b0 * D * 4, self.fm_logit.data_ptr() + b0 * 4, st),
+                      "dr_embed_fm_fwd")
+            mark("embed_fm_fwd")
+            if chunk_l0:
+                check(lib.dr_dense_fwd(self.stack.data_ptr() + b0 * S * D * 4, self.w[0].data_ptr(), ops._ptr(self.b[0]),
+                                       b1 - b0, S * D, l0.units, l0._act, self.acts[0].data_ptr() + b0 * l0.units * 4, st),
+                      "dr_dense_fwd")
+                mark("dense_fwd_0")
         if self.optimizer == "adam_rows":     # per-row lookup counts of this batch: on the side stream, behind the GEMMs
             self._side_stream.wait_stream(torch.cuda.current_stream())   # (not behind the gather: both are DRAM-bound)
             with torch.cuda.stream(self._side_stream):
@@ -179,16 +255,13 @@ class DeepFMTrainStep:
                       "dr_embed_adam_count")
         x = self.stack
         K = S * D
-        L = len(self.layers)
         gz = self.g_acts[-1]                                   # [B,1]: dL/dlogit
-        # the skinny end (final Dense(1) + BCE + their backward) is ONE kernel when the layer below is <= 256 wide
-        head = (L >= 2 and self.layers[-1].units == 1 and self.layers[-1]._act == 0 and self.layers[-2].units <= 256
-                and self.b[-1] is not None and self.b[-2] is not None)
-        for i, l in enumerate(self.layers[:L - 1] if head else self.layers):
-            check(lib.dr_dense_fwd(x.data_ptr(), self.w[i].data_ptr(), ops._ptr(self.b[i]), B, K, l.units, l._act,
-                                   self.acts[i].data_ptr(), st), "dr_dense_fwd")
+        for i, l in fwd_layers:
+            if not (chunk_l0 and i == 0):
+                check(lib.dr_dense_fwd(x.data_ptr(), self.w[i].data_ptr(), ops._ptr(self.b[i]), B, K, l.units, l._act,
+                                       self.acts[i].data_ptr(), st), "dr_dense_fwd")
+                mark(f"dense_fwd_{i}")
             x, K = self.acts[i], l.units
-            mark(f"dense_fwd_{i}")
         if head:
             check(lib.dr_dense_head_bce_fwd_bwd(self.acts[L - 2].data_ptr(), self.w[L - 1].data_ptr(),
                                                 self.b[L - 1].data_ptr(), self.fm_logit.data_ptr(), self.labels.data_ptr(),
@@ -232,8 +305,17 @@ class DeepFMTrainStep:
         mark("dense_bwd_0_dx")
         main = torch.cuda.current_stream()
         side = self._side_stream
-        side.wait_stream(main)
         adam = self.optimizer != "sgd"
+        fork = torch.cuda.Event()
+        fork.record(main)                                  # layer-0 input gradient done: both branches may start
+
+        def launch_dw():
+            check(lib.dr_dense_bwd(self.stack.data_ptr(), self.w[0].data_ptr(), None, gz0.data_ptr(), B, S * D, l.units, 0,
+                                   None, None, self.gw[0].data_ptr(), None, st), "dr_dense_bwd(dw)")
+
+        if self.dw_first:                                  # the persistent GEMM takes its one CTA per SM first; the update's
+            launch_dw()                                    # CTAs fill what is left of every SM (knob tc_dw_share)
+        side.wait_event(fork)
         with torch.cuda.stream(side):
             sst = side.cuda_stream
             if self.optimizer == "adam_rows_tf":  # the same, equal to tf.keras Adam: skipped steps of a row are replayed
@@ -297,8 +379,8 @@ class DeepFMTrainStep:
                 check(lib.dr_adam_step(c.bias.data_ptr(), self.g_bias.data_ptr(), self.m_bias.data_ptr(),
                                        self.v_bias.data_ptr(), 1, 0.0, ck.beta1, ck.beta2, ck.eps, 1, lt, sst),
                       "dr_adam_step(bias)")
-        check(lib.dr_dense_bwd(self.stack.data_ptr(), self.w[0].data_ptr(), None, gz0.data_ptr(), B, S * D, l.units, 0,
-                               None, None, self.gw[0].data_ptr(), None, st), "dr_dense_bwd(dw)")
+        if not self.dw_first:
+            launch_dw()
         main.wait_stream(side)
         mark("dense_bwd_0_dw+embed_fm_bwd")
         if not adam:
@@ -456,3 +538,7 @@ class DeepFMTrainStep:
             self.stage_host(next_ids_host, next_labels_host)
         self.run()
         return float(self.loss.item())          # D2H read of the step's result (synchronises)
+
+    def fit_host(self, batches, depth: int = 2) -> List[float]:
+        """Pipelined epoch loop over HOST batches (see module-level fit_host): the public end-to-end call."""
+        return fit_host(self, batches, depth)

@@ -30,16 +30,20 @@ def _sample_rows(M, n, rng):
     return np.unique(np.concatenate([edge, rng.integers(0, M, size=n)]))
 
 
-@pytest.fixture(params=["tc2", "tc", "ffma"])
+@pytest.fixture(params=["tc2", "tc", "ffma", "tc2share"])
 def gemm_core(request):
+    """tc2share = the shipped core with the co-residency build of the weight-gradient GEMM (knob tc_dw_share: registers
+    capped at 96, one epilogue staging slab) -- the instantiation the train steps run beside the embedding update."""
     from deep_recommenders_b200 import _lib
     if request.param == "tc":
         _lib.enable_tensor_core_gemm(variant=1)
-    elif request.param == "tc2":
+    elif request.param in ("tc2", "tc2share"):
         _lib.enable_tensor_core_gemm(variant=2)
+        _lib.tune("tc_dw_share", 1 if request.param == "tc2share" else 0)
     else:
         _lib.disable_tensor_core_gemm()
     yield request.param
+    _lib.tune("tc_dw_share", 0)
     _lib.enable_tensor_core_gemm()
 
 

@@ -207,3 +207,99 @@ def test_keras_compile_fit_evaluate_like_reference_example():
     # EarlyStopping: stops after `patience` epochs without improvement
     es = K.EarlyStopping(patience=2)
     assert [es.on_epoch_end(i, {"val_loss": v}) for i, v in enumerate([1.0, 0.9, 0.95, 0.97])] == [False, False, False, True]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("chunks", [2, 3])
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_train_step_fwd_chunks_equal_whole_batch(chunks, use_graph):
+    """fwd_chunks > 1 runs the gather and the first tower GEMM as alternating launches over slices of the batch; examples
+    are independent in both kernels, so every activation, the loss and the updated parameters equal the unsliced step
+    (bit for bit in the forward; the parameter update differs only by atomic summation order)."""
+    from deep_recommenders_b200 import feature_column as fc
+    from deep_recommenders_b200.keras.models.ranking import DeepFM
+    from deep_recommenders_b200.training import DeepFMTrainStep
+    rows, B, D = [500, 7, 300, 41], 1000, 16       # B not a multiple of 128: the last slice is ragged
+    cols = [fc.categorical_column_with_identity(f"c{i}", r) for i, r in enumerate(rows)]
+
+    def make(n):
+        model = DeepFM([fc.indicator_column(c) for c in cols], [fc.embedding_column(c, D) for c in cols],
+                       dnn_units_size=[64, 32], seed=7, device="cuda", sparse_lr=0.05)
+        with torch.no_grad():
+            model.embeddings.lin_view().normal_(0, 0.1, generator=torch.Generator(device="cuda").manual_seed(3))
+        tr = DeepFMTrainStep(model, batch_size=B, lr=0.05, use_graph=use_graph, fwd_chunks=n)
+        return model, (tr.capture() if use_graph else tr)
+
+    (m1, t1), (m2, t2) = make(1), make(chunks)
+    rng = np.random.default_rng(5)
+    for _ in range(3):
+        ids = torch.from_numpy(np.stack([rng.integers(-1, r, size=B) for r in rows], axis=1).astype(np.int64)).cuda()
+        lab = torch.from_numpy(rng.integers(0, 2, size=B).astype(np.float32)).cuda()
+        l1, l2 = float(t1.step(ids, lab).item()), float(t2.step(ids, lab).item())
+        assert abs(l1 - l2) <= 1e-6 * abs(l1)
+    assert torch.equal(t1.stack, t2.stack) and torch.equal(t1.fm_logit, t2.fm_logit)
+    assert torch.allclose(t1.acts[0], t2.acts[0], rtol=1e-6, atol=1e-7)
+    assert torch.allclose(m1.embeddings.weight, m2.embeddings.weight, rtol=1e-5, atol=1e-7)
+    assert torch.allclose(t1.flat, t2.flat, rtol=1e-5, atol=1e-7)
+
+
+def _small_deepfm_trainer(B=1000, use_graph=True, rows=(500, 7, 300, 41), dnn=(64, 32), **kw):
+    from deep_recommenders_b200 import feature_column as fc
+    from deep_recommenders_b200.keras.models.ranking import DeepFM
+    from deep_recommenders_b200.training import DeepFMTrainStep
+    rows, D = list(rows), 16
+    cols = [fc.categorical_column_with_identity(f"c{i}", r) for i, r in enumerate(rows)]
+    model = DeepFM([fc.indicator_column(c) for c in cols], [fc.embedding_column(c, D) for c in cols],
+                   dnn_units_size=list(dnn), seed=7, device="cuda", sparse_lr=0.05)
+    with torch.no_grad():
+        model.embeddings.lin_view().normal_(0, 0.1, generator=torch.Generator(device="cuda").manual_seed(3))
+    tr = DeepFMTrainStep(model, batch_size=B, lr=0.05, use_graph=use_graph, **kw)
+    return rows, model, (tr.capture() if use_graph else tr)
+
+
+def test_fit_host_returns_every_steps_loss_like_blocking_calls():
+    """fit_host (pipelined: H2D of the next batch and the D2H loss read off the critical path) must produce exactly the
+    losses of the same batches fed one blocking train_step_host call at a time."""
+    rows, m1, t1 = _small_deepfm_trainer()
+    _, m2, t2 = _small_deepfm_trainer()
+    rng = np.random.default_rng(9)
+    B = t1.B
+    batches = []
+    for _ in range(7):
+        ids = torch.from_numpy(np.stack([rng.integers(-1, r, size=B) for r in rows], axis=1).astype(np.int64)).pin_memory()
+        lab = torch.from_numpy(rng.integers(0, 2, size=B).astype(np.float32)).pin_memory()
+        batches.append((ids, lab))
+    ref = [t1.train_step_host(*batches[k], *(batches[k + 1] if k + 1 < len(batches) else (None, None))) for k in range(7)]
+    t1._staged = None
+    got = t2.fit_host(batches[:3]) + t2.fit_host(batches[3:])        # two calls: the second one restages its first batch
+    assert len(got) == 7
+    for a, b in zip(ref, got):
+        assert abs(a - b) <= 2e-6 * abs(a), (ref, got)
+    assert ref[-1] < ref[0]
+    assert t2.fit_host([]) == []
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_train_step_dw_first_with_shared_sm_gemm_equals_default(use_graph):
+    """dw_first + knob tc_dw_share: the layer-0 weight-gradient GEMM (co-residency build: capped registers, one staging
+    slab) is enqueued before the embedding update and shares the SMs with it -- scheduling only, same arithmetic."""
+    from deep_recommenders_b200 import _lib
+    shape = dict(rows=(500, 7, 300, 41, 90, 1000, 3, 64), dnn=(256, 32), B=3000)     # layer-0 dW: [128 x 3000] x [3000 x 256]
+    rows, m1, t1 = _small_deepfm_trainer(use_graph=use_graph, **shape)
+    _lib.tune("tc_dw_share", 1)
+    try:
+        _, m2, t2 = _small_deepfm_trainer(use_graph=use_graph, dw_first=True, **shape)
+        rng = np.random.default_rng(5)
+        B = t1.B
+        for _ in range(3):
+            ids = torch.from_numpy(np.stack([rng.integers(-1, r, size=B) for r in rows], axis=1).astype(np.int64)).cuda()
+            lab = torch.from_numpy(rng.integers(0, 2, size=B).astype(np.float32)).cuda()
+            l1 = float(t1.step(ids, lab).item())
+            l2 = float(t2.step(ids, lab).item())
+            assert abs(l1 - l2) <= 1e-6 * abs(l1)
+        torch.cuda.synchronize()
+    finally:
+        _lib.tune("tc_dw_share", 0)
+    assert torch.allclose(t1.gw[0], t2.gw[0], rtol=1e-5, atol=1e-7)          # split-K partial sums meet in another order
+    assert torch.allclose(m1.embeddings.weight, m2.embeddings.weight, rtol=1e-5, atol=1e-7)
+    assert torch.allclose(t1.flat, t2.flat, rtol=1e-5, atol=1e-7)
