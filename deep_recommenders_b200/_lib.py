@@ -29,6 +29,7 @@ _SIGS = {
     "dr_last_error": [],
     "dr_launch_count": [],
     "dr_tune_set": [C.c_char_p, _i],
+    "dr_tune_get": [C.c_char_p, _p],
     "dr_set_workspace": [_p, C.c_uint64],
     "dr_gemm_plane_cache": [_i],
     "dr_gemm_prof_read": [_p, _i],
@@ -145,6 +146,12 @@ def launch_count() -> int:
 
 def tune(key: str, value: int) -> None:
     check(load().dr_tune_set(key.encode(), int(value)), "dr_tune_set")
+
+
+def tune_get(key: str) -> int:
+    v = C.c_int(0)
+    check(load().dr_tune_get(key.encode(), C.byref(v)), "dr_tune_get")
+    return int(v.value)
 
 
 _workspace = None

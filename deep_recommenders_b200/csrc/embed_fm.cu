@@ -32,6 +32,7 @@ int g_tune_embed_bwd_linx = 0;        // LINX mapping for the slot-parallel back
 int g_tune_embed_fwd_linx_shard = 0;  // same mapping for the row-sharded (peer-memory) forward: off until measured at N > 1
 int g_tune_embed_l2_hints = 0;        // bit 0: forward row loads L2::evict_first; bit 1: stacked-output stores L2::evict_last;
                                       // bit 2: backward vector atomics L2::evict_first; bit 3: backward stack / g_stack loads evict_first
+int g_tune_embed_bwd_carveout = 0;     // backward: preferred shared-memory carveout in percent (0 = leave the driver default)
 int g_tune_embed_fwd_minblocks = 0;   // forward register cap: 0 = none (ptxas picks, 108 regs -> 2 CTAs of 256 / SM),
                                       // 3 / 4 = __launch_bounds__(256, n): <= 85 / 64 registers, 24 / 32 warps per SM
 
@@ -682,9 +683,15 @@ static int launch_bwd_sp_u(const EmbedBwdParams& p, cudaStream_t st) {
   int per_sm = g_tune_embed_ctas_per_sm > 0 ? g_tune_embed_ctas_per_sm : 8;
   if (ctas > (int64_t)kNumSMs * per_sm) ctas = (int64_t)kNumSMs * per_sm;
   if (ctas < 1) ctas = 1;
-  if (p.shard_world > 0) embed_fm_bwd_sp_kernel<LPR, IdT, U, true><<<(unsigned)ctas, threads, smem, st>>>(p);
-  else if (LINX) embed_fm_bwd_sp_kernel<LPR, IdT, U, false, LINX><<<(unsigned)ctas, threads, smem, st>>>(p);
-  else embed_fm_bwd_sp_kernel<LPR, IdT, U, false><<<(unsigned)ctas, threads, smem, st>>>(p);
+  void (*k)(EmbedBwdParams) = p.shard_world > 0 ? embed_fm_bwd_sp_kernel<LPR, IdT, U, true>
+                              : (LINX ? embed_fm_bwd_sp_kernel<LPR, IdT, U, false, LINX>
+                                      : embed_fm_bwd_sp_kernel<LPR, IdT, U, false>);
+  // The update runs beside the persistent tcgen05 weight-gradient GEMM, which configures its SMs with the maximum
+  // shared-memory carveout (214+ KB of dynamic shared memory).  A kernel that prefers another L1 / shared split cannot
+  // become resident on an SM in that configuration, so the update asks for the same carveout (it uses 2 KB either way).
+  if (g_tune_embed_bwd_carveout)
+    DR_CUDA_CALL(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, g_tune_embed_bwd_carveout));
+  k<<<(unsigned)ctas, threads, smem, st>>>(p);
   DR_CUDA_LAUNCH_CHECK("embed_fm_bwd_sp");
   return DR_OK;
 }

@@ -272,6 +272,127 @@ __device__ __forceinline__ void split_tile_inplace(uint8_t* hi, uint8_t* lo, int
   }
 }
 
+// Epilogue of ONE work item for one epilogue warp (TMEM lane quarter q): tcgen05.ld 32 x 32 slabs of the accumulator at
+// `tmem_acc`, fused epilogue, output through the swizzled staging buffer + TMA store / reduce-add (or register stores).
+// Shared by the single-CTA kernel and the CTA-pair kernel.  mw = first output row of this warp's quarter.
+template <int BN, bool SHARE>
+__device__ __forceinline__ void tc_epilogue_item(const GemmArgs& a, const CUtensorMap* tmC, const int tma_out,
+                                                 const uint32_t tmem_acc, const int q, const int lane, const int64_t mw,
+                                                 const int64_t n0, uint8_t* stg, uint32_t& slab, const bool vec_ok) {
+  const int64_t m = mw + lane;
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    uint32_t r[32];
+    tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+    const int64_t nb = n0 + c * 32;
+    if (tma_out) {
+      if (mw < a.M && nb < a.N) {            // warp-uniform
+        uint8_t* sb = SHARE ? stg : stg + (slab & 1u) * 4096;
+        if (lane == 0) {                            // the store issued from this buffer two slabs ago (SHARE: the
+          if (SHARE) bulk_wait_group_read<0>();     // previous one) has read it
+          else bulk_wait_group_read<1>();
+        }
+        __syncwarp();
+        const bool row_ok = m < a.M;
+        float o[32];
+        if (a.epi == EPI_STORE || a.epi == EPI_ATOMIC) {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) o[jj] = __uint_as_float(r[jj]);
+        } else if (a.epi == EPI_BIAS_ACT) {
+          // one coalesced bias load per slab (lane l holds bias[nb + l]), broadcast by shuffles; the activation
+          // switch is hoisted out of the element loop
+          const float bl = (a.bias && nb + lane < a.N) ? __ldg(a.bias + nb + lane) : 0.f;
+          if (a.act == DR_ACT_RELU) {
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj)
+              o[jj] = fmaxf(__uint_as_float(r[jj]) + __shfl_sync(0xffffffffu, bl, jj), 0.f);
+          } else if (a.act == DR_ACT_NONE) {
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) o[jj] = __uint_as_float(r[jj]) + __shfl_sync(0xffffffffu, bl, jj);
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj)
+              o[jj] = act_apply(__uint_as_float(r[jj]) + __shfl_sync(0xffffffffu, bl, jj), a.act);
+          }
+        } else if (a.epi == EPI_SCORES) {
+          // v = acc - log p[n] + dup(m, n) * MIN_FLOAT (sbcnm.py:78-86, 52-75): lane l holds log p and the id of column
+          // nb + l (one coalesced load each per slab), broadcast by shuffles; the thread's own row id is loaded once
+          const int64_t mg = m + a.row0;
+          const bool col_ok = nb + lane < a.N;
+          const float lpl = (a.bias && col_ok) ? logf(__ldg(a.bias + nb + lane)) : 0.f;
+          const long long idl = (a.cand_ids && col_ok) ? (long long)__ldg(a.cand_ids + nb + lane) : -1ll;
+          const long long idm = (a.cand_ids && row_ok && mg < a.N) ? (long long)__ldg(a.cand_ids + mg) : -2ll;
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            float v = __uint_as_float(r[jj]) - __shfl_sync(0xffffffffu, lpl, jj);
+            if (a.cand_ids) {
+              const long long idj = __shfl_sync(0xffffffffu, idl, jj);
+              if (mg != nb + jj && idj == idm) v += (-FLT_MAX / 100.0f);
+            }
+            o[jj] = v;
+          }
+        } else if (a.epi == EPI_ACTGRAD && a.act == DR_ACT_RELU && nb + 31 < a.N && mw + 31 < a.M) {
+          // relu'(y) = [y > 0].  The y slab is fetched COALESCED (each load instruction reads 4 whole 128-B rows) into
+          // the staging buffer in the same swizzled layout, then every thread reads its own row from shared memory
+          // (a thread reading its row straight from global memory costs 32 scattered 16-B requests per instruction).
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + (lane >> 3), ch = lane & 7;
+            const float4 yv = __ldg(reinterpret_cast<const float4*>(a.aux0 + (mw + rr) * a.ldc + nb + ch * 4));
+            *reinterpret_cast<float4*>(sb + rr * 128 + ((ch ^ (rr & 7)) << 4)) = yv;
+          }
+          __syncwarp();
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            const float4 yv = *reinterpret_cast<const float4*>(sb + lane * 128 + ((ch ^ (lane & 7)) << 4));
+            o[4 * ch + 0] = yv.x > 0.f ? __uint_as_float(r[4 * ch + 0]) : 0.f;
+            o[4 * ch + 1] = yv.y > 0.f ? __uint_as_float(r[4 * ch + 1]) : 0.f;
+            o[4 * ch + 2] = yv.z > 0.f ? __uint_as_float(r[4 * ch + 2]) : 0.f;
+            o[4 * ch + 3] = yv.w > 0.f ? __uint_as_float(r[4 * ch + 3]) : 0.f;
+          }
+          __syncwarp();     // every lane has read its row before anyone overwrites the buffer with the output
+        } else {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj)
+            o[jj] = (row_ok && nb + jj < a.N) ? epi_scalar_tc(a, __uint_as_float(r[jj]), m, nb + jj) : 0.f;
+        }
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch)
+          *reinterpret_cast<float4*>(sb + lane * 128 + ((ch ^ (lane & 7)) << 4)) =
+              make_float4(o[4 * ch], o[4 * ch + 1], o[4 * ch + 2], o[4 * ch + 3]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          if (a.epi == EPI_ATOMIC) tma_reduce_add_2d(tmC, sb, (int)nb, (int)mw);
+          else tma_store_2d(tmC, sb, (int)nb, (int)mw);
+          bulk_commit_group();
+        }
+        ++slab;
+      }
+    } else if (m < a.M && nb < a.N) {
+      if (a.epi == EPI_ATOMIC) {
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj)
+          if (nb + jj < a.N) red_add_f32(a.C + m * a.ldc + nb + jj, __uint_as_float(r[jj]));
+      } else if (vec_ok && nb + 31 < a.N) {
+#pragma unroll
+        for (int jj = 0; jj < 32; jj += 4) {
+          float4 o;
+          o.x = epi_scalar_tc(a, __uint_as_float(r[jj + 0]), m, nb + jj + 0);
+          o.y = epi_scalar_tc(a, __uint_as_float(r[jj + 1]), m, nb + jj + 1);
+          o.z = epi_scalar_tc(a, __uint_as_float(r[jj + 2]), m, nb + jj + 2);
+          o.w = epi_scalar_tc(a, __uint_as_float(r[jj + 3]), m, nb + jj + 3);
+          *reinterpret_cast<float4*>(a.C + m * a.ldc + nb + jj) = o;
+        }
+      } else {
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj)
+          if (nb + jj < a.N) a.C[m * a.ldc + nb + jj] = epi_scalar_tc(a, __uint_as_float(r[jj]), m, nb + jj);
+      }
+    }
+  }
+}
+
 // Work item = (m tile, n tile, k split).  Items are strided over the persistent grid.
 struct TcItem {
   int64_t m0, n0;
@@ -465,119 +586,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       mbar_wait_t<PROF>(&tmem_full_bar[as], aph, pw0);
       const long long te0 = PROF ? clock64() : 0;
       tc_fence_after();
-      const int64_t mw = t.m0 + q * 32;          // first row of this warp's quarter
-      const int64_t m = mw + lane;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + as * (uint32_t)BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-        const int64_t nb = t.n0 + c * 32;
-        if (tma_out) {
-          if (mw < a.M && nb < a.N) {            // warp-uniform
-            uint8_t* sb = SHARE ? stg : stg + (slab & 1u) * 4096;
-            if (lane == 0) {                            // the store issued from this buffer two slabs ago (SHARE: the
-              if (SHARE) bulk_wait_group_read<0>();     // previous one) has read it
-              else bulk_wait_group_read<1>();
-            }
-            __syncwarp();
-            const bool row_ok = m < a.M;
-            float o[32];
-            if (a.epi == EPI_STORE || a.epi == EPI_ATOMIC) {
-#pragma unroll
-              for (int jj = 0; jj < 32; ++jj) o[jj] = __uint_as_float(r[jj]);
-            } else if (a.epi == EPI_BIAS_ACT) {
-              // one coalesced bias load per slab (lane l holds bias[nb + l]), broadcast by shuffles; the activation
-              // switch is hoisted out of the element loop
-              const float bl = (a.bias && nb + lane < a.N) ? __ldg(a.bias + nb + lane) : 0.f;
-              if (a.act == DR_ACT_RELU) {
-#pragma unroll
-                for (int jj = 0; jj < 32; ++jj)
-                  o[jj] = fmaxf(__uint_as_float(r[jj]) + __shfl_sync(0xffffffffu, bl, jj), 0.f);
-              } else if (a.act == DR_ACT_NONE) {
-#pragma unroll
-                for (int jj = 0; jj < 32; ++jj) o[jj] = __uint_as_float(r[jj]) + __shfl_sync(0xffffffffu, bl, jj);
-              } else {
-#pragma unroll
-                for (int jj = 0; jj < 32; ++jj)
-                  o[jj] = act_apply(__uint_as_float(r[jj]) + __shfl_sync(0xffffffffu, bl, jj), a.act);
-              }
-            } else if (a.epi == EPI_SCORES) {
-              // v = acc - log p[n] + dup(m, n) * MIN_FLOAT (sbcnm.py:78-86, 52-75): lane l holds log p and the id of column
-              // nb + l (one coalesced load each per slab), broadcast by shuffles; the thread's own row id is loaded once
-              const int64_t mg = m + a.row0;
-              const bool col_ok = nb + lane < a.N;
-              const float lpl = (a.bias && col_ok) ? logf(__ldg(a.bias + nb + lane)) : 0.f;
-              const long long idl = (a.cand_ids && col_ok) ? (long long)__ldg(a.cand_ids + nb + lane) : -1ll;
-              const long long idm = (a.cand_ids && row_ok && mg < a.N) ? (long long)__ldg(a.cand_ids + mg) : -2ll;
-#pragma unroll
-              for (int jj = 0; jj < 32; ++jj) {
-                float v = __uint_as_float(r[jj]) - __shfl_sync(0xffffffffu, lpl, jj);
-                if (a.cand_ids) {
-                  const long long idj = __shfl_sync(0xffffffffu, idl, jj);
-                  if (mg != nb + jj && idj == idm) v += (-FLT_MAX / 100.0f);
-                }
-                o[jj] = v;
-              }
-            } else if (a.epi == EPI_ACTGRAD && a.act == DR_ACT_RELU && nb + 31 < a.N && mw + 31 < a.M) {
-              // relu'(y) = [y > 0].  The y slab is fetched COALESCED (each load instruction reads 4 whole 128-B rows) into
-              // the staging buffer in the same swizzled layout, then every thread reads its own row from shared memory
-              // (a thread reading its row straight from global memory costs 32 scattered 16-B requests per instruction).
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int rr = i * 4 + (lane >> 3), ch = lane & 7;
-                const float4 yv = __ldg(reinterpret_cast<const float4*>(a.aux0 + (mw + rr) * a.ldc + nb + ch * 4));
-                *reinterpret_cast<float4*>(sb + rr * 128 + ((ch ^ (rr & 7)) << 4)) = yv;
-              }
-              __syncwarp();
-#pragma unroll
-              for (int ch = 0; ch < 8; ++ch) {
-                const float4 yv = *reinterpret_cast<const float4*>(sb + lane * 128 + ((ch ^ (lane & 7)) << 4));
-                o[4 * ch + 0] = yv.x > 0.f ? __uint_as_float(r[4 * ch + 0]) : 0.f;
-                o[4 * ch + 1] = yv.y > 0.f ? __uint_as_float(r[4 * ch + 1]) : 0.f;
-                o[4 * ch + 2] = yv.z > 0.f ? __uint_as_float(r[4 * ch + 2]) : 0.f;
-                o[4 * ch + 3] = yv.w > 0.f ? __uint_as_float(r[4 * ch + 3]) : 0.f;
-              }
-              __syncwarp();     // every lane has read its row before anyone overwrites the buffer with the output
-            } else {
-#pragma unroll
-              for (int jj = 0; jj < 32; ++jj)
-                o[jj] = (row_ok && nb + jj < a.N) ? epi_scalar_tc(a, __uint_as_float(r[jj]), m, nb + jj) : 0.f;
-            }
-#pragma unroll
-            for (int ch = 0; ch < 8; ++ch)
-              *reinterpret_cast<float4*>(sb + lane * 128 + ((ch ^ (lane & 7)) << 4)) =
-                  make_float4(o[4 * ch], o[4 * ch + 1], o[4 * ch + 2], o[4 * ch + 3]);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) {
-              if (a.epi == EPI_ATOMIC) tma_reduce_add_2d(&tmC, sb, (int)nb, (int)mw);
-              else tma_store_2d(&tmC, sb, (int)nb, (int)mw);
-              bulk_commit_group();
-            }
-            ++slab;
-          }
-        } else if (m < a.M && nb < a.N) {
-          if (a.epi == EPI_ATOMIC) {
-#pragma unroll
-            for (int jj = 0; jj < 32; ++jj)
-              if (nb + jj < a.N) red_add_f32(a.C + m * a.ldc + nb + jj, __uint_as_float(r[jj]));
-          } else if (vec_ok && nb + 31 < a.N) {
-#pragma unroll
-            for (int jj = 0; jj < 32; jj += 4) {
-              float4 o;
-              o.x = epi_scalar_tc(a, __uint_as_float(r[jj + 0]), m, nb + jj + 0);
-              o.y = epi_scalar_tc(a, __uint_as_float(r[jj + 1]), m, nb + jj + 1);
-              o.z = epi_scalar_tc(a, __uint_as_float(r[jj + 2]), m, nb + jj + 2);
-              o.w = epi_scalar_tc(a, __uint_as_float(r[jj + 3]), m, nb + jj + 3);
-              *reinterpret_cast<float4*>(a.C + m * a.ldc + nb + jj) = o;
-            }
-          } else {
-#pragma unroll
-            for (int jj = 0; jj < 32; ++jj)
-              if (nb + jj < a.N) a.C[m * a.ldc + nb + jj] = epi_scalar_tc(a, __uint_as_float(r[jj]), m, nb + jj);
-          }
-        }
-      }
+      tc_epilogue_item<BN, SHARE>(a, &tmC, tma_out, tmem_base + as * (uint32_t)BN, q, lane, t.m0 + q * 32, t.n0, stg, slab, vec_ok);
       tc_fence_before();
       mbar_arrive(&tmem_empty_bar[as]);      // this thread is done reading accumulator stage `as`
       if (PROF) pw1 += (unsigned long long)(clock64() - te0);
@@ -599,6 +608,224 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN))
+                 : "memory");
+  }
+}
+
+
+// ======================================================================================================================
+// CTA-pair variant (tcgen05 cta_group::2): two SMs of one TPC work on one 256 x BN output tile.
+//
+// Why: the single-CTA in-kernel-split main loop is SHARED-MEMORY-BANDWIDTH bound -- per 128 x 256 x 32 k-block an SM moves
+// 288 KB through its shared memory (48 KB TMA in, 48 + 48 KB split read / lo write, 144 KB tensor-core operand reads)
+// = 2250 cycles at 128 B / cycle against 1536 cycles of MMA time (profiles/gemm_prof_*).  In a CTA pair each CTA stages
+// its own 128 rows of A and only HALF of the B tile (BN / 2 columns); one `tcgen05.mma.cta_group::2` (M = 256) issued by
+// the leader CTA feeds both SMs' tensor cores, each SM reading its half of B once for both.  Per SM and k-block:
+// 32 KB TMA in, 32 + 32 KB split, 96 KB operand reads = 192 KB = 1500 cycles < the 1536 cycles of its 12 MMAs.
+//
+// Roles per CTA are those of gemm_tc_kernel<INSPLIT> (TMA producer, MMA issuer, 4 epilogue warps, 4 splitter warps);
+// what crosses the pair:
+//   * splitter threads of BOTH CTAs arrive on the LEADER's per-stage `split` mbarrier (remote arrive through mapa) after
+//     their fence.proxy.async -- the leader's MMA thread waits for 256 arrivals, then issues the 12 MMAs of the k-block;
+//   * tcgen05.commit ... multicast::cluster frees the stage in both CTAs (`empty`) and, after the last k-block, publishes
+//     the accumulator (each CTA's TMEM holds its own 128 rows x BN columns) to both epilogues (`tmem_full`);
+//   * epilogue threads of both CTAs arrive on the leader's `tmem_empty` mbarrier (256 arrivals);
+//   * TMEM is allocated / freed with cta_group::2 by warp 1 of each CTA; cluster barriers bracket the kernel so that no
+//     remote arrive or peer shared-memory read can hit a CTA that has not initialised or has already exited.
+// Work item = (256-row m tile, n tile, k split), strided over the persistent grid of pairs.
+constexpr int TC_PAIR_BM = 256;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(rank)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {     // arrives on `bar` in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS_INSPLIT, 1)
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, const int tma_out, const GemmArgs a, const int64_t m_tiles,
+                    const int64_t n_tiles, const int64_t per, const int64_t total_items) {
+  constexpr int BH = BN / 2;                     // columns of the B tile this CTA stages
+  constexpr int A_TILE = TC_BM * TC_BK * 4;      // this CTA's 128 rows: 16 KB
+  constexpr int B_TILE = BH * TC_BK * 4;
+  constexpr int STAGE = 2 * A_TILE + 2 * B_TILE; // [A raw = hi | A lo | B raw = hi | B lo]
+  constexpr bool SHARE = false;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], split_bar[STAGES], tmem_full_bar[2],
+      tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();       // 0 = leader (issues the MMAs), 1 = peer
+  const int64_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int64_t kblocks = (a.K + TC_BK - 1) / TC_BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    if (tma_out) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);                         // one multicast commit of the leader per phase
+      mbar_init(&split_bar[s], 2 * 32 * TC_SPLIT_WARPS);   // leader only: the splitter threads of both CTAs
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 2 * 128);              // leader only: the epilogue threads of both CTAs
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {   // TMEM: 2 accumulator stages x BN fp32 columns, in both CTAs (same address)
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"((uint32_t)(2 * BN))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();          // barriers of BOTH CTAs are initialised, TMEM is allocated in both
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer (each CTA: its 128 rows of A, its BN/2 columns of B, its own barriers) =====
+      uint32_t it = 0;
+      for (int64_t item = pair; item < total_items; item += npairs) {
+        const TcItem t = tc_decode(item, n_tiles, m_tiles, kblocks, per, BN);
+        const int m0 = (int)(t.m0 * 2) + (int)rank * TC_BM;          // tc_decode counts 128-row tiles: pair tiles are 256
+        const int n0 = (int)t.n0 + (int)rank * BH;
+        for (int i = 0; i < t.nkb; ++i, ++it) {
+          const int s = (int)(it % STAGES);
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          mbar_expect_tx(&full_bar[s], (uint32_t)(A_TILE + B_TILE));
+          uint8_t* st = smem + (size_t)s * STAGE;
+          const int k = (t.kb0 + i) * TC_BK;
+          if (!A_MN) {
+            tma_load_2d(st, &tmA, &full_bar[s], k, m0);
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < TC_BM / 32; ++jj) tma_load_2d(st + jj * 4096, &tmA, &full_bar[s], m0 + jj * 32, k);
+          }
+          if (!B_MN) {
+            tma_load_2d(st + 2 * A_TILE, &tmB, &full_bar[s], k, n0);
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < BH / 32; ++jj)
+              tma_load_2d(st + 2 * A_TILE + jj * 4096, &tmB, &full_bar[s], n0 + jj * 32, k);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // ===== MMA issuer (leader CTA only): M = 256 across the pair =====
+      constexpr uint32_t idesc = make_idesc(TC_PAIR_BM, BN, A_MN, B_MN);
+      uint32_t it = 0, j = 0;
+      for (int64_t item = pair; item < total_items; item += npairs, ++j) {
+        const TcItem t = tc_decode(item, n_tiles, m_tiles, kblocks, per, BN);
+        const uint32_t as = j & 1u, aph = (j >> 1) & 1u;
+        mbar_wait(&tmem_empty_bar[as], aph ^ 1u);      // both epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * (uint32_t)BN;
+        for (int i = 0; i < t.nkb; ++i, ++it) {
+          const int s = (int)(it % STAGES);
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(&split_bar[s], ph);                // both CTAs have split this stage
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * STAGE);
+          const uint32_t sb = sa + 2 * A_TILE;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; ++k) {
+            const uint32_t a_off = A_MN ? (uint32_t)k * 1024u : (uint32_t)k * 32u;
+            const uint32_t b_off = B_MN ? (uint32_t)k * 1024u : (uint32_t)k * 32u;
+            const uint32_t a_lbo = A_MN ? 4096u : 16u, a_sbo = A_MN ? 512u : 1024u, a_lt = A_MN ? 1u : 2u;
+            const uint32_t b_lbo = B_MN ? 4096u : 16u, b_sbo = B_MN ? 512u : 1024u, b_lt = B_MN ? 1u : 2u;
+            const uint64_t dAh = make_smem_desc(sa + a_off, a_lbo, a_sbo, a_lt);
+            const uint64_t dAl = make_smem_desc(sa + A_TILE + a_off, a_lbo, a_sbo, a_lt);
+            const uint64_t dBh = make_smem_desc(sb + b_off, b_lbo, b_sbo, b_lt);
+            const uint64_t dBl = make_smem_desc(sb + B_TILE + b_off, b_lbo, b_sbo, b_lt);
+            const uint32_t acc0 = (i > 0 || k > 0) ? 1u : 0u;
+            tc_mma_tf32_pair(d_tmem, dAl, dBh, idesc, acc0);
+            tc_mma_tf32_pair(d_tmem, dAh, dBl, idesc, 1u);
+            tc_mma_tf32_pair(d_tmem, dAh, dBh, idesc, 1u);
+          }
+          tc_commit_pair(&empty_bar[s]);               // stage reusable in both CTAs once these MMAs retire
+        }
+        tc_commit_pair(&tmem_full_bar[as]);            // accumulator complete in both CTAs' TMEM
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 6) {
+    // ===== splitter warps 6..9: lo = raw - trunc_tf32(raw) next to the raw tile (the raw tile is the hi plane) =====
+    const int tid = (int)threadIdx.x - TC_THREADS;
+    constexpr int NSPLIT = 32 * TC_SPLIT_WARPS;
+    uint32_t it = 0;
+    for (int64_t item = pair; item < total_items; item += npairs) {
+      const TcItem t = tc_decode(item, n_tiles, m_tiles, kblocks, per, BN);
+      for (int i = 0; i < t.nkb; ++i, ++it) {
+        const int s = (int)(it % STAGES);
+        const uint32_t ph = (it / STAGES) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        uint8_t* st = smem + (size_t)s * STAGE;
+        split_tile_inplace<A_TILE, NSPLIT>(st, st + A_TILE, tid);
+        split_tile_inplace<B_TILE, NSPLIT>(st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, tid);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive_cluster(&split_bar[s], 0);         // on the leader's barrier
+      }
+    }
+  } else {
+    // ===== epilogue warps 2..5 (each CTA: its own 128 rows) =====
+    const int q = warp & 3;
+    const bool vec_ok = ((a.ldc & 3) == 0) && aligned16(a.C);
+    uint8_t* stg = smem + (size_t)STAGES * STAGE + (size_t)q * 8192;
+    uint32_t j = 0, slab = 0;
+    for (int64_t item = pair; item < total_items; item += npairs, ++j) {
+      const TcItem t = tc_decode(item, n_tiles, m_tiles, kblocks, per, BN);
+      const uint32_t as = j & 1u, aph = (j >> 1) & 1u;
+      mbar_wait(&tmem_full_bar[as], aph);
+      tc_fence_after();
+      tc_epilogue_item<BN, SHARE>(a, &tmC, tma_out, tmem_base + as * (uint32_t)BN, q, lane,
+                                  t.m0 * 2 + (int64_t)rank * TC_BM + q * 32, t.n0, stg, slab, vec_ok);
+      tc_fence_before();
+      mbar_arrive_cluster(&tmem_empty_bar[as], 0);     // on the leader's barrier
+    }
+    if (tma_out && lane == 0) bulk_wait_group_all();
+  }
+  tc_fence_before();
+  cluster_sync_all();          // every MMA has retired (the epilogues saw the last commit), every remote arrive has landed
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN))
                  : "memory");
   }
 }
@@ -728,6 +955,51 @@ static int launch_tc(const CUtensorMap* tms, const GemmArgs& a, cudaStream_t st)
   return DR_OK;
 }
 
+
+int g_tune_tc_pair = 1;      // 1 (default) = CTA-pair kernel (cta_group::2) for N >= 128 outputs where its 74 workers beat the 148
+                             // single CTAs (rule in gemm_tc_launch); 2 = always for N >= 128; 0 = never
+
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+static int launch_tc_pair(const CUtensorMap* tms, const GemmArgs& a, cudaStream_t st) {
+  constexpr int STAGE = 2 * TC_BM * TC_BK * 4 + 2 * (BN / 2) * TC_BK * 4;
+  constexpr size_t smem = (size_t)STAGES * STAGE + TC_EPI_STAGING + 1024;
+  static_assert(smem <= 232448, "operand ring + epilogue staging exceed the 227 KB of shared memory per CTA");
+  auto k = gemm_tc_pair_kernel<BN, STAGES, A_MN, B_MN>;
+  DR_CUDA_CALL(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUtensorMap tmC;
+  memset(&tmC, 0, sizeof(tmC));
+  int tma_out = (g_tune_tc_tma_out && (a.ldc & 3) == 0 && aligned16(a.C)) ? 1 : 0;
+  if (tma_out)
+    if (int rc = make_map(&tmC, a.C, a.N, a.M, a.ldc, 32)) return rc;
+  const int64_t m_tiles = (a.M + TC_PAIR_BM - 1) / TC_PAIR_BM, n_tiles = (a.N + BN - 1) / BN;
+  const int64_t kblocks = (a.K + TC_BK - 1) / TC_BK;
+  const int64_t pairs_max = kNumSMs / 2;
+  int64_t splitk = a.splitk;
+  if (a.epi == EPI_ATOMIC && a.splitk > 1) {
+    // split-K callers sized `splitk` for 128 x 128 tiles on 148 CTAs; here the workers are 74 pairs on 256 x BN tiles:
+    // the split count whose item total fills whole rounds of the pairs best (>= 8 k-blocks per split)
+    const int64_t base = m_tiles * n_tiles;
+    int64_t best = 1;
+    double best_eff = 0.0;
+    const int64_t smax = kblocks / 8 > 1 ? (kblocks / 8 < 256 ? kblocks / 8 : 256) : 1;
+    for (int64_t sk = 1; sk <= smax; ++sk) {
+      const int64_t items = base * sk;
+      const int64_t rounds = (items + pairs_max - 1) / pairs_max;
+      const double eff = (double)items / (double)(rounds * pairs_max);
+      if (eff > best_eff + 1e-9 && (rounds <= 4 || eff > 0.97)) { best_eff = eff; best = sk; }
+      if (rounds > 4) break;
+    }
+    splitk = best;
+  }
+  const int64_t per = (kblocks + splitk - 1) / splitk;
+  const int64_t splits = (kblocks + per - 1) / per;
+  const int64_t total = m_tiles * n_tiles * splits;
+  const int64_t pairs = total < pairs_max ? total : pairs_max;
+  k<<<(unsigned)(2 * pairs), TC_THREADS_INSPLIT, smem, st>>>(tms[0], tms[2], tmC, tma_out, a, m_tiles, n_tiles, per, total);
+  DR_CUDA_LAUNCH_CHECK("gemm_tc_pair");
+  return DR_OK;
+}
+
 // Produce K-major hi/lo planes [rows, pitch] of an operand.  `stored_k_major`: src is [rows, K] with
 // pitch ld (flat split, same pitch); otherwise src is [K, rows] with pitch ld (transpose-split).
 static int make_planes(const float* src, bool stored_k_major, int64_t rows, int64_t K, int64_t ld, float* hi,
@@ -775,6 +1047,38 @@ int gemm_tc_launch(const GemmArgs& a0, bool ta, bool tb, cudaStream_t st) {
     const bool wide = !two_stage && !a.share && a.N >= 256 && (g_tune_gemm_bn == 256 ||
                                      (g_tune_gemm_bn == 0 && pad256 <= pad128 && tiles256 >= 2 * kNumSMs));   // enough tiles to fill the SMs
     const int bn = a.N <= 32 ? 32 : (a.N <= 64 ? 64 : (wide ? 256 : 128));
+    const int pbn = (a.N >= 256 && pad256 <= pad128) ? 256 : 128;
+    bool use_pair = g_tune_tc_pair != 0 && a.N >= 128 && !a.share && !two_stage && a.M >= 128;
+    if (use_pair && g_tune_tc_pair == 1 && !(a.epi == EPI_ATOMIC && a.splitk > 1)) {
+      // rounds x cycles per k-block of one worker (measured, profiles/gemm_prof_*: the single-CTA loop is bound by shared
+      // memory at 2250 / 1500 cycles per 128 x 256 / 128 x 128 x 32 k-block, a pair by its MMAs at 1536 per 256 x 256 and by
+      // shared memory at 1125 per 256 x 128): small problems that fill the 148 single CTAs better than the 74 pairs stay
+      // on the single-CTA kernel (knob tc_pair = 2 forces the pair kernel)
+      const int64_t items_p = ((a.M + TC_PAIR_BM - 1) / TC_PAIR_BM) * ((a.N + pbn - 1) / pbn);
+      const int64_t items_s = ((a.M + TC_BM - 1) / TC_BM) * ((a.N + bn - 1) / bn);
+      const int64_t pairs_max = kNumSMs / 2;
+      const double t_p = (double)((items_p + pairs_max - 1) / pairs_max) * (pbn == 256 ? 1536.0 : 1125.0);
+      const double t_s = (double)((items_s + kNumSMs - 1) / kNumSMs) * (bn == 256 ? 2250.0 : 1500.0);
+      if (t_p > 0.9 * t_s) use_pair = false;
+    }
+    if (use_pair) {
+      // CTA-pair kernel: 256 x BN tiles, each CTA stages its 128 rows of A and BN / 2 columns of B
+      if (!B_MN) {
+        if (int rc = make_map(&tm2[2], a.B, a.K, a.N, a.ldb, pbn / 2)) return rc;
+      } else {
+        if (int rc = make_map(&tm2[2], a.B, a.N, a.K, a.ldb, TC_BK, true)) return rc;
+      }
+#define DR_TCP_LAUNCH(BN_, ST_)                                                             \
+      do {                                                                                  \
+        if (!A_MN && !B_MN) return launch_tc_pair<BN_, ST_, false, false>(tm2, a, st);      \
+        if (!A_MN && B_MN) return launch_tc_pair<BN_, ST_, false, true>(tm2, a, st);        \
+        if (A_MN && !B_MN) return launch_tc_pair<BN_, ST_, true, false>(tm2, a, st);        \
+        return launch_tc_pair<BN_, ST_, true, true>(tm2, a, st);                            \
+      } while (0)
+      if (pbn == 256) DR_TCP_LAUNCH(256, 3);
+      DR_TCP_LAUNCH(128, 4);
+#undef DR_TCP_LAUNCH
+    }
     if (!B_MN) {
       if (int rc = make_map(&tm2[2], a.B, a.K, a.N, a.ldb, bn)) return rc;
     } else {

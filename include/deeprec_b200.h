@@ -489,6 +489,8 @@ int dr_gemm_plane_cache(int enable);
 /* Developer hook (not reference-facing): set a kernel tuning knob by name, e.g.
  * "embed_fwd_unroll", "embed_block", "embed_bwd_agg", "gemm_splitk".                     */
 int dr_tune_set(const char* key, int value);
+/* Developer hook: read a knob back (tc_pair, tc_dw_share, gemm_variant, gemm_bn, tc_min_n); DR_EINVAL for other keys. */
+int dr_tune_get(const char* key, int* value);
 /* Developer hook: per-role wait cycles of the tcgen05 GEMM core, accumulated over the launches made while the knob
  * `gemm_prof` is 1 (instrumented instantiation: BN = 128, split in kernel).  out16 (HOST pointer, 16 counters):
  * 0 producer waits for a free stage, 1 splitter waits for TMA data, 2 splitter work, 3 MMA issuer waits for operands,

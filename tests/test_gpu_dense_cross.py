@@ -13,18 +13,23 @@ from oracle import reference_np as R
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["ffma", "tc", "tc2"])
+@pytest.fixture(autouse=True, params=["ffma", "tc", "tc2", "tc2single", "tc2pair"])
 def gemm_variant(request):
     """Every test in this file runs under all GEMM cores: FFMA, tcgen05 3xTF32 on pre-split planes (tc) and
-    tcgen05 3xTF32 with the hi/lo split inside the kernel (tc2)."""
+    tcgen05 3xTF32 with the hi/lo split inside the kernel (tc2 = library defaults; tc2single / tc2pair force the
+    single-CTA kernel / the CTA-pair kernel `tcgen05.mma.cta_group::2` for every output at least 128 wide)."""
     from deep_recommenders_b200 import _lib
+    pair_default = _lib.tune_get("tc_pair")
     if request.param == "tc":
         _lib.enable_tensor_core_gemm(variant=1)
-    elif request.param == "tc2":
+    elif request.param.startswith("tc2"):
         _lib.enable_tensor_core_gemm(variant=2)
+        if request.param != "tc2":
+            _lib.tune("tc_pair", 2 if request.param == "tc2pair" else 0)
     else:
         _lib.disable_tensor_core_gemm()
     yield request.param
+    _lib.tune("tc_pair", pair_default)
     _lib.enable_tensor_core_gemm()
 
 

@@ -30,20 +30,25 @@ def _sample_rows(M, n, rng):
     return np.unique(np.concatenate([edge, rng.integers(0, M, size=n)]))
 
 
-@pytest.fixture(params=["tc2", "tc", "ffma", "tc2share"])
+@pytest.fixture(params=["tc2", "tc", "ffma", "tc2share", "tc2single", "tc2pair"])
 def gemm_core(request):
-    """tc2share = the shipped core with the co-residency build of the weight-gradient GEMM (knob tc_dw_share: registers
-    capped at 96, one epilogue staging slab) -- the instantiation the train steps run beside the embedding update."""
+    """tc2 = the shipped core under the library defaults; tc2single / tc2pair force the single-CTA kernel / the CTA-pair
+    kernel (tcgen05.mma.cta_group::2, 256 x BN tiles over two SMs); tc2share = the co-residency build of the
+    weight-gradient GEMM (knob tc_dw_share: registers capped at 96, one epilogue staging slab)."""
     from deep_recommenders_b200 import _lib
+    pair_default = _lib.tune_get("tc_pair")
     if request.param == "tc":
         _lib.enable_tensor_core_gemm(variant=1)
-    elif request.param in ("tc2", "tc2share"):
+    elif request.param.startswith("tc2"):
         _lib.enable_tensor_core_gemm(variant=2)
         _lib.tune("tc_dw_share", 1 if request.param == "tc2share" else 0)
+        if request.param in ("tc2single", "tc2pair", "tc2share"):
+            _lib.tune("tc_pair", 2 if request.param == "tc2pair" else 0)
     else:
         _lib.disable_tensor_core_gemm()
     yield request.param
     _lib.tune("tc_dw_share", 0)
+    _lib.tune("tc_pair", pair_default)
     _lib.enable_tensor_core_gemm()
 
 
@@ -63,7 +68,7 @@ FULL_DENSE = [
 @pytest.mark.parametrize("M,K,N,act", FULL_DENSE)
 def test_dense_full_size(M, K, N, act, gemm_core):
     from deep_recommenders_b200 import ops
-    if gemm_core != "tc2" and M > 65536:
+    if gemm_core not in ("tc2", "tc2pair") and M > 65536:
         pytest.skip("C3 shapes: shipped core only")
     rng = np.random.default_rng(M + K + N)
     x = rng.standard_normal((M, K), dtype=np.float32)

@@ -1,0 +1,24 @@
+#!/bin/bash
+# N-GPU A/B of the co-resident update: default vs (dW GEMM submitted first + co-residency build + matching carveout)
+N=${1:-2}
+TAG=r02s
+mkdir -p gpurun_out
+T="timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+B="bench.py --gpus $N --steps 20 --warmup 5 --no-cpu-baseline"
+CO="--dw-first 1 --tune tc_dw_share=1 --tune embed_bwd_carveout=100"
+$T --master-port 29511 $B                      > gpurun_out/${TAG}_n${N}_default.log 2>&1
+$T --master-port 29512 $B $CO                  > gpurun_out/${TAG}_n${N}_default_co.log 2>&1
+$T --master-port 29513 $B --workload c5        > gpurun_out/${TAG}_n${N}_c5.log 2>&1
+$T --master-port 29514 $B --workload c5 $CO    > gpurun_out/${TAG}_n${N}_c5_co.log 2>&1
+for f in default default_co c5 c5_co; do
+  python - "$f" "$N" "$TAG" <<'PY'
+import json, sys
+f, n, tag = sys.argv[1:4]
+try:
+    d = json.loads([l for l in open(f"gpurun_out/{tag}_n{n}_{f}.log") if l.startswith("{")][-1])
+    print(f, "N=" + n, round(d["value"] / 1e6, 2), "M ex/s", round(d["ms_per_step"], 4), "ms loss", round(d["final_loss"], 5),
+          {k: round(v * 1e3, 1) for k, v in d.get("kernel_ms", {}).items()})
+except Exception as e:
+    print(f, "FAILED", e); print(open(f"gpurun_out/{tag}_n{n}_{f}.log").read()[-1200:])
+PY
+done
