@@ -21,10 +21,12 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "deep_recommenders_b200", "lib", "libdeeprec_b200.so")
 
-MNEMONICS = ["UTCHMMA", "UTMALDG", "UTMACCTL", "UTCBAR", "UTCATOMSWS", "LDTM", "SYNCS", "REDG", "MATCH", "LDG.E.NA",
+MNEMONICS = ["UTCHMMA", "UTMALDG", "UTMASTG", "UTMAREDG", "UCGABAR", "STTM", "UTMACCTL", "UTCBAR", "UTCATOMSWS", "LDTM", "SYNCS", "REDG", "MATCH", "LDG.E.NA",
              "ATOMG", "REDUX", "FFMA", "HMMA", "IMMA"]
 # the instantiations the C2/C3/C4 steps actually launch (profiles/launches_*.json), not all ~600 template variants
-HOT = ["embed_fm_fwd_kernel<8, long, 8, ", "embed_fm_fwd_kernel<8, long, 4, ", "embed_fm_bwd_sp_kernel<8, long, 2, ",
+HOT = ["embed_fm_fwd_kernel<4, long, 8, false, 0, true", "gemm_tc_pair_kernel<256, 3, ", "gemm_tc_pair_kernel<128, 4, true, true",
+       "gemm_tc_kernel<256, 2, ", "gemm_tc_kernel<32, 4, ", "head_bce_kernel", "actgrad_colsum_v4_kernel<2>",
+       "embed_fm_fwd_kernel<8, long, 8, ", "embed_fm_fwd_kernel<8, long, 4, ", "embed_fm_bwd_sp_kernel<8, long, 2, ",
        "embed_fm_bwd_kernel<8, long, 2, true", "gather_rows_kernel<long", "scatter_add_rows_kernel<long",
        "gemm_tc_kernel<128, 3, ", "split_tf32", "sgemm_kernel<128, 128, 16, 8, 8, false, false>",
        "sgemm_kernel<128, 32, 16, 8, 2, false, false>", "sgemm_kernel<256, 16, 16, 8, 2, false, false>",
