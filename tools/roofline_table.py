@@ -75,14 +75,16 @@ def main():
               f"{'' if tt is None else f'{tt * 1e6:.1f}'} | {ms * 1e3:.1f} | {ms * 1e-3 / floor:.1f}x |")
     print(f"| **step** | | | | | | **{tot_meas * 1e6:.0f}** (graph replay: {bench['ms_per_step'] * 1e3:.0f}) | "
           f"{tot_meas / tot_floor:.1f}x of {tot_floor * 1e6:.0f} µs |")
-    print("\nReading it (round 2): every group is within 1.8-2.8x of its floor except the two launch-latency-bound tails (head, "
-          "tower SGD).  The gather + FM forward sits at the DRAM's random-row rate, not at its byte rate (DESIGN.md section 4: "
-          "same time at half the DRAM bytes, same time on half the SMs); the tcgen05 GEMMs are bound by shared-memory "
-          "bandwidth in the main loop (in-kernel hi/lo split + three operand reads per product: "
-          "profiles/gemm_prof_r02_final.json, 1 650 cycles per k-block against 790 for the MMAs); the layer-0 weight gradient and "
-          "the embedding update share a label because they are issued on two streams, but the persistent GEMM owns every SM's "
-          "shared memory, so they run one after the other (about 110 + 120 us).")
-
+    print("\nReading it (end of round 2): the two big tensor-core GEMMs run on the CTA-pair kernel (tcgen05 cta_group::2) at "
+          "1.4-1.7x of the 3xTF32 tensor floor (ncu: tensor pipe 76-82 % active, profiles/gemm_r02z_ncu.csv); before it the "
+          "single-CTA main loop was bound by shared-memory bandwidth (2 250 cycles per 128 x 256 x 32 k-block against 1 536 of MMA "
+          "time, profiles/r02u_gemm_prof.json).  The gather + FM forward sits at the DRAM's random-row rate, not at its byte "
+          "rate (DESIGN.md section 4: same time at half the DRAM bytes, same time on half the SMs).  The layer-0 weight "
+          "gradient and the embedding update share a label because they are issued on two streams; they run one after the "
+          "other (about 70 + 130 us): making them co-resident is possible (profiles/r02r_probe_coresidency.jsonl: equal "
+          "shared-memory carveout + a register-capped GEMM build) but the update then runs at 40 % of its solo rate and nothing is "
+          "gained (profiles/r02q_probe_overlap.jsonl).  The skinny layers (256 -> 32 -> 1 and their backward) and the two "
+          "launch-latency-bound tails are 2.8x and more above their HBM floors: 160 us of the step.")
 
 if __name__ == "__main__":
     main()
