@@ -192,9 +192,16 @@ class ShardedDeepFMTrainStep:
         arrays = {"weight": self.emb.weight}
         if not self.emb.lin_in_row:
             arrays["lin"] = self.emb.lin
-        checkpoint.save_rows(prefix, self.rank, self.world, self.emb.total_rows, arrays)
-        if self.rank == 0:
-            checkpoint.save_meta(prefix, self.get_config(), {"flat": self.flat})
+        # one id per save, the same on every rank and in the meta file, so that files of two saves cannot be mixed
+        import time
+        sid = torch.tensor([time.time_ns() // 1000 if self.rank == 0 else 0], dtype=torch.int64, device=self.dev)
+        dist.broadcast(sid, src=0 if self.group is None else dist.get_global_rank(self.group, 0), group=self.group)
+        save_id = int(sid.item())
+        checkpoint.save_rows(prefix, self.rank, self.world, self.emb.total_rows, arrays, save_id=save_id)
+        dist.barrier(group=self.group)          # every shard is on disk ...
+        if self.rank == 0:                      # ... before the meta file, the commit marker, is written
+            checkpoint.save_meta(prefix, self.get_config(), {"flat": self.flat}, world=self.world, save_id=save_id)
+            checkpoint.remove_stale_shards(prefix, self.world)
         dist.barrier(group=self.group)
 
     def load(self, prefix: str) -> None:

@@ -46,3 +46,29 @@ def test_meta_and_error_paths(tmp_path):
     checkpoint.save_rows(prefix, 0, 2, 6, {"weight": W[0::2]})
     with pytest.raises(FileNotFoundError):                                            # shard 1 of 2 missing
         checkpoint.load_rows(prefix, 0, 1)
+
+
+def test_save_id_and_meta_commit_marker(tmp_path):
+    """Round-1 advisor finding: shards and the meta file carry one save id; a mix of two saves is refused; the meta file
+    names the writer's world, so stale shards of another world size do not make the checkpoint ambiguous."""
+    total = 10
+    W, _ = _global(total, 3)
+    prefix = str(tmp_path / "c")
+    for r in range(2):
+        checkpoint.save_rows(prefix, r, 2, total, {"weight": W[r::2]}, save_id=11)
+    checkpoint.save_meta(prefix, {"rows": [total]}, {"flat": torch.zeros(2)}, world=2, save_id=11)
+    assert torch.equal(checkpoint.load_rows(prefix, 0, 1)["weight"], W)
+    # a later save at world 3 crashed after writing its shards but before the meta file: the committed save still loads
+    for r in range(3):
+        checkpoint.save_rows(prefix, r, 3, total, {"weight": W[r::3] + 1}, save_id=12)
+    assert checkpoint.saved_world(prefix) == 2
+    assert torch.equal(checkpoint.load_rows(prefix, 0, 1)["weight"], W)
+    # a later save at the SAME world crashed between the shards: shard 0 is new, shard 1 old -> refused
+    checkpoint.save_rows(prefix, 0, 2, total, {"weight": W[0::2] + 2}, save_id=13)
+    with pytest.raises(ValueError, match="different saves"):
+        checkpoint.load_rows(prefix, 0, 1)
+    # completing that save (shard 1, then the meta file last) makes it the checkpoint; stale world-3 shards are removed
+    checkpoint.save_rows(prefix, 1, 2, total, {"weight": W[1::2] + 2}, save_id=13)
+    checkpoint.save_meta(prefix, {"rows": [total]}, {"flat": torch.zeros(2)}, world=2, save_id=13)
+    assert checkpoint.remove_stale_shards(prefix, 2) == 3
+    assert torch.equal(checkpoint.load_rows(prefix, 1, 2)["weight"], (W + 2)[1::2])
