@@ -177,3 +177,36 @@ def test_plain_c_program_links_and_calls_the_library(tmp_path):
     want = hash_bucket(np.array([6040, -1], dtype=np.int64), 1000).tolist()
     assert lines[4] == f"hash_bucket_i64 {want[0]} {want[1]}"
     assert lines[5].startswith("dr_gather_fwd(D=6) rc=-1") and "D=6" in lines[5]
+
+
+def test_shipped_library_contains_the_blackwell_kernels_it_claims():
+    """Static check of the built .so (no GPU): the CTA-pair tcgen05 GEMM and the single-CTA one are in it, sized to be
+    launchable (no spills to local memory, registers x threads within the SM's file), and the pair kernel really is a
+    cta_group::2 kernel (UTCHMMA.2CTA, the multicast commit, the cluster barrier) fed by TMA."""
+    import os
+    import re
+    import shutil
+    import subprocess
+    from deep_recommenders_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not installed")
+    _lib.load()
+    so = str(_lib.LIB_PATH)
+    res = subprocess.run([cuobjdump, "-res-usage", so], capture_output=True, text=True, check=True).stdout.splitlines()
+    found = {}
+    for i, line in enumerate(res):
+        m = re.match(r"\s*Function (\S+):", line)
+        if m and i + 1 < len(res):
+            r = re.search(r"REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)", res[i + 1])
+            if r:
+                found[m.group(1)] = tuple(map(int, r.groups()))
+    pair = {k: v for k, v in found.items() if "gemm_tc_pair_kernel" in k}
+    single = {k: v for k, v in found.items() if "14gemm_tc_kernel" in k}
+    assert len(pair) == 8 and len(single) >= 16, (len(pair), len(single))
+    for k, (reg, stack, shared, local) in pair.items():
+        assert local == 0 and stack == 0 and reg * 320 <= 65536, (k, reg, stack, local)
+    name = next(k for k in pair if "ILi256ELi3ELb0ELb1E" in k)          # the forward instantiation of the C2 / C5 towers
+    sass = subprocess.run([cuobjdump, "-sass", "-fun", name, so], capture_output=True, text=True, check=True).stdout
+    for op in ("UTCHMMA.2CTA", "UTCBAR.2CTA.MULTICAST", "UCGABAR_ARV", "UTMALDG.2D", "UTMASTG.2D", "UTMAREDG.2D.ADD", "LDTM"):
+        assert op in sass, f"{op} missing from {name}"
