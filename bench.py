@@ -369,7 +369,7 @@ def main():
             "cpu_baseline": cpu, "final_loss": final_loss,
             "cuda_graph": trainer.graph is not None,
             "gemm_core": {0: "ffma", 1: "tcgen05 3xTF32, pre-split planes (tc)",
-                          2: "tcgen05 3xTF32, hi/lo split in kernel (tc2)"}[_lib._tc_variant if _lib._tc_enabled and not gemm_note else (1 if gemm_note else 0)],
+                          2: "tcgen05 3xTF32, hi/lo split in kernel (tc2); outputs >= 128 wide on the CTA-pair kernel (cta_group::2)"}[_lib._tc_variant if _lib._tc_enabled and not gemm_note else (1 if gemm_note else 0)],
             "exchange": getattr(trainer, "exchange", None) if world > 1 else None,
             "optimizer": args.optimizer if world == 1 else "sgd", "embed_fwd": args.embed_fwd if world == 1 else "ldg",
             "fwd_chunks": args.fwd_chunks if world == 1 else 1, "dw_first": bool(args.dw_first)}
