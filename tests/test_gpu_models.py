@@ -236,7 +236,7 @@ def test_train_step_fwd_chunks_equal_whole_batch(chunks, use_graph):
         ids = torch.from_numpy(np.stack([rng.integers(-1, r, size=B) for r in rows], axis=1).astype(np.int64)).cuda()
         lab = torch.from_numpy(rng.integers(0, 2, size=B).astype(np.float32)).cuda()
         l1, l2 = float(t1.step(ids, lab).item()), float(t2.step(ids, lab).item())
-        assert abs(l1 - l2) <= 1e-6 * abs(l1)
+        assert abs(l1 - l2) <= 5e-6 * abs(l1)        # float atomics: summation order differs run to run
         if k == 0:      # same parameters going in: the sliced forward is bit-identical (later steps start from parameters
             torch.cuda.synchronize()          # that differ by the atomic summation order of the previous update)
             assert torch.equal(t1.stack, t2.stack) and torch.equal(t1.fm_logit, t2.fm_logit)
@@ -279,7 +279,7 @@ def test_fit_host_returns_every_steps_loss_like_blocking_calls():
     got = t2.fit_host(batches[:3]) + t2.fit_host(batches[3:])        # two calls: the second one restages its first batch
     assert len(got) == 7
     for a, b in zip(ref, got):
-        assert abs(a - b) <= 2e-6 * abs(a), (ref, got)
+        assert abs(a - b) <= 5e-6 * abs(a), (ref, got)      # float atomics: summation order differs run to run
     assert t2.fit_host([]) == []
 
 
@@ -300,7 +300,7 @@ def test_train_step_dw_first_with_shared_sm_gemm_equals_default(use_graph):
             lab = torch.from_numpy(rng.integers(0, 2, size=B).astype(np.float32)).cuda()
             l1 = float(t1.step(ids, lab).item())
             l2 = float(t2.step(ids, lab).item())
-            assert abs(l1 - l2) <= 1e-6 * abs(l1)
+            assert abs(l1 - l2) <= 5e-6 * abs(l1)        # float atomics: summation order differs run to run
         torch.cuda.synchronize()
     finally:
         _lib.tune("tc_dw_share", 0)
