@@ -304,7 +304,7 @@ def test_train_step_dw_first_with_shared_sm_gemm_equals_default(use_graph):
         torch.cuda.synchronize()
     finally:
         _lib.tune("tc_dw_share", 0)
-    assert torch.allclose(t1.gw[0], t2.gw[0], rtol=1e-5, atol=1e-7)          # split-K partial sums meet in another order
+    assert float((t1.gw[0] - t2.gw[0]).abs().max()) <= 1e-5 * float(t1.gw[0].abs().max())   # split-K partial sums meet in another order
     assert torch.allclose(m1.embeddings.weight, m2.embeddings.weight, rtol=1e-5, atol=1e-7)
     for a, b in zip(t1.w + t1.b, t2.w + t2.b):          # (the flat buffer has uninitialised 16-B padding between them)
         assert torch.allclose(a, b, rtol=1e-5, atol=1e-7)
